@@ -1,0 +1,227 @@
+// jp_common.h -- internal runtime shared by the .cu files of libjpetra_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/jpetra_b200.h"
+
+namespace jp {
+
+struct Error {
+  int32_t code;
+  std::string msg;
+};
+
+void set_last_error(const std::string& m);
+
+[[noreturn]] inline void fail(int32_t code, const std::string& m) { throw Error{code, m}; }
+
+#define JP_CUDA(call)                                                                                         \
+  do {                                                                                                        \
+    cudaError_t e__ = (call);                                                                                 \
+    if (e__ != cudaSuccess)                                                                                   \
+      ::jp::fail(JP_CUDA_ERROR, std::string(#call) + " failed: " + cudaGetErrorString(e__) + " (" __FILE__ ":" + \
+                                    std::to_string(__LINE__) + ")");                                          \
+  } while (0)
+
+#define JP_NCCL(call)                                                                                         \
+  do {                                                                                                        \
+    ncclResult_t r__ = (call);                                                                                \
+    if (r__ != ncclSuccess)                                                                                   \
+      ::jp::fail(JP_NCCL_ERROR, std::string(#call) + " failed: " + ncclGetErrorString(r__) + " (" __FILE__ ":" + \
+                                    std::to_string(__LINE__) + ")");                                          \
+  } while (0)
+
+#define JP_REQUIRE(cond, msg)                                  \
+  do {                                                         \
+    if (!(cond)) ::jp::fail(JP_INVALID_ARGUMENT, (msg));       \
+  } while (0)
+
+#define JP_REQUIRE_STATE(cond, msg)                         \
+  do {                                                      \
+    if (!(cond)) ::jp::fail(JP_INVALID_STATE, (msg));       \
+  } while (0)
+
+// ---- runtime context: one per process (one process per GPU) -------------------------------
+struct Context {
+  bool initialised = false;
+  int device = -1;
+  int sm_count = 0;
+  cudaStream_t compute = nullptr;  // kernels of the hot path
+  cudaStream_t comm = nullptr;     // pack + NCCL send/recv, overlapped with interior rows
+  cudaStream_t copy = nullptr;     // D2H of results in the host-buffer path
+  cudaEvent_t ev_x_ready = nullptr, ev_halo_ready = nullptr, ev_tmp = nullptr;
+  std::atomic<int64_t> launches{0};
+  void* scratch = nullptr;  // device staging for host-array collectives / reductions
+  size_t scratch_bytes = 0;
+  void* host_scratch = nullptr;  // pinned
+  size_t host_scratch_bytes = 0;
+  void* flush_buf = nullptr;
+  size_t flush_bytes = 0;
+};
+Context& ctx();
+void require_init();
+void* scratch(size_t bytes);
+void* host_scratch(size_t bytes);
+
+inline void count_launch(int n = 1) { ctx().launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define JP_LAUNCH_CHECK()            \
+  do {                               \
+    ::jp::count_launch();            \
+    JP_CUDA(cudaGetLastError());     \
+  } while (0)
+
+// ---- handle registry ------------------------------------------------------------------------
+enum class Kind : int { Comm = 1, Csr, MultiVector, Plan, Event };
+
+struct Object {
+  Kind kind;
+  explicit Object(Kind k) : kind(k) {}
+  virtual ~Object() {}
+};
+
+jp_handle register_object(std::unique_ptr<Object> obj);
+Object* lookup(jp_handle h, Kind kind, const char* what);
+void destroy_object(jp_handle h, Kind kind, const char* what);
+void destroy_all_objects();
+
+template <class T>
+T* get(jp_handle h, Kind kind, const char* what) {
+  return static_cast<T*>(lookup(h, kind, what));
+}
+
+template <class F>
+int32_t guarded(F&& f) {
+  try {
+    f();
+    return JP_OK;
+  } catch (const Error& e) {
+    set_last_error(e.msg);
+    return e.code;
+  } catch (const std::exception& e) {
+    set_last_error(std::string("internal error: ") + e.what());
+    return JP_CUDA_ERROR;
+  }
+}
+
+// ---- objects ----------------------------------------------------------------------------------
+struct DeviceBuffer {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DeviceBuffer() {}
+  DeviceBuffer(const DeviceBuffer&) = delete;
+  DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+  ~DeviceBuffer() { release(); }
+  void alloc(size_t n) {
+    release();
+    if (n == 0) n = 16;
+    JP_CUDA(cudaMalloc(&p, n));
+    bytes = n;
+  }
+  void ensure(size_t n) {
+    if (n > bytes) alloc(n);
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+struct Comm : Object {
+  Comm() : Object(Kind::Comm) {}
+  ~Comm() override;
+  bool serial = true;
+  int nproc = 1;
+  int rank0 = 0;  // 0-based
+  ncclComm_t nccl = nullptr;
+};
+
+struct MultiVector : Object {
+  MultiVector() : Object(Kind::MultiVector) {}
+  int32_t n = 0, k = 0;  // column-major, ld == n
+  DeviceBuffer data;
+  double* d() const { return data.as<double>(); }
+};
+
+// One launch list of the row-block SpMV kernel: rows [row[b], row[b+1]) with nnz starting at nnz0[b].
+struct RowBlocks {
+  int32_t count = 0;
+  DeviceBuffer row;   // int32 [count+1] ... stored as pairs (first row, end row) per block
+  DeviceBuffer nnz0;  // unused for now
+};
+
+struct Csr : Object {
+  Csr() : Object(Kind::Csr) {}
+  int32_t n_rows = 0, n_cols = 0, n_local_cols = 0;
+  int64_t nnz = 0;
+  int32_t max_row_len = 0;
+  int32_t threads_per_row = 1;  // chosen from the row-length statistics at create time
+  int32_t nnz_cap = 2048;       // nnz staged in shared memory per block
+  DeviceBuffer rowptr, colind, vals;  // 0-based; colind/vals padded for 16-byte over-reads
+  // row blocks: int4 {row_begin, row_end, nnz_begin, nnz_end}; interior = no remote column
+  DeviceBuffer blocks_interior, blocks_boundary, blocks_all;
+  int32_t n_blocks_interior = 0, n_blocks_boundary = 0, n_blocks_all = 0;
+  // cache of the column-map multivector (A.importMV, src/CSRMatrix.jl:10,772-781); only used when the column
+  // map is not [domain prefix | remote tail] and the fused apply path does not apply
+  std::unique_ptr<MultiVector> import_mv;
+};
+
+struct Plan : Object {
+  Plan() : Object(Kind::Plan) {}
+  Comm* comm = nullptr;
+  int32_t n_src = 0, n_tgt = 0, num_same = 0, n_permute = 0, n_remote = 0, n_export = 0;
+  DeviceBuffer permute_to, permute_from, remote_lids, export_lids;  // 0-based int32
+  std::vector<int32_t> procs_to, procs_from;                        // 1-based PIDs, incl. self
+  std::vector<int64_t> lengths_to, lengths_from, starts_to, starts_from;  // element offsets (0-based)
+  bool remote_is_tail = false;     // remote_lids == num_same + (0..n_remote-1): receives land in place
+  bool export_contiguous = false;  // every send block is a contiguous LID range (k==1 needs no pack)
+  DeviceBuffer sendbuf, recvbuf;   // LID-major, vector-minor (src/MultiVector.jl:335-349)
+  int32_t buf_k = 0;
+  // post/wait state (src/Distributor.jl:24-29)
+  bool posted = false;
+  jp_handle posted_tgt = 0;
+  int32_t posted_k = 0;
+  cudaEvent_t ev_done = nullptr;
+  ~Plan() override {
+    if (ev_done) cudaEventDestroy(ev_done);
+  }
+};
+
+struct Event : Object {
+  Event() : Object(Kind::Event) {}
+  cudaEvent_t ev = nullptr;
+  ~Event() override {
+    if (ev) cudaEventDestroy(ev);
+  }
+};
+
+// ---- cross-file entry points (internal) ---------------------------------------------------------
+// y[r0:r1) rows of A applied to x (+ optional halo) on `stream`
+void launch_spmv(const Csr& A, const DeviceBuffer& blocks, int32_t n_blocks, bool use_halo, const double* x, int64_t ldx,
+                 const double* halo, int32_t halo_k, double* y, int64_t ldy, int32_t k, double alpha, double beta,
+                 cudaStream_t stream);
+void launch_spmv_trans(const Csr& A, const double* x, int64_t ldx, double* y, int64_t ldy, int32_t ny, int32_t k, double alpha,
+                       double beta, cudaStream_t stream);
+void launch_scale_fill(double* y, int64_t n, double beta, cudaStream_t stream);  // y = beta==0 ? 0 : beta*y
+void plan_ensure_buffers(Plan& p, int32_t k);
+void plan_post(Plan& p, const MultiVector& src, MultiVector* tgt, bool halo_only, int32_t combine_mode, bool reverse);
+void plan_unpack(Plan& p, MultiVector& tgt, cudaStream_t stream);
+void comm_allreduce_device(Comm& c, double* buf, int64_t n, cudaStream_t stream);
+void release_host_path_cache();
+void release_reduce_workspace();
+
+}  // namespace jp

@@ -1,0 +1,373 @@
+// jp_mv.cu -- DenseMultiVector storage (src/DenseMultiVector.jl:6-60) and the MultiVector kernels
+// (src/MultiVector.jl:52-161): fill!, scale!, axpby (broadcast copyto!), dot, norm, commReduce.
+//
+// All of these are HBM-bound streaming kernels: coalesced 8-byte loads with 4-way unrolled independent
+// accumulators, one launch per call.  dot/norm are fused block reductions: every block writes one partial per
+// vector, the last block to finish (ticket counter) adds the partials in block order, so the result is
+// deterministic for a given launch geometry; the cross-rank sum is one ncclAllReduce of k doubles.
+// Elementwise arithmetic uses explicit non-fused __dmul_rn/__dadd_rn so results are bit-identical to the
+// reference's scalar loops (Julia does not contract a*x+b*y into an FMA).
+#include "jp_common.h"
+
+namespace jp {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxReduceBlocks = 1024;  // partials per vector
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// MODE 0: dot  sum x*y      (src/MultiVector.jl:99-105)
+// MODE 1: norm2 sum x*x     (src/MultiVector.jl:122-131)
+// MODE 2: normp sum x^p     (src/MultiVector.jl:135-142)
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) reduce_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t n,
+                                                            double p, double* __restrict__ partials,
+                                                            unsigned int* __restrict__ tickets, double* __restrict__ out) {
+  const int vec = blockIdx.y;
+  const double* xv = x + (size_t)vec * n;
+  const double* yv = MODE == 0 ? y + (size_t)vec * n : nullptr;
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    double x0 = xv[i], x1 = xv[i + stride], x2 = xv[i + 2 * stride], x3 = xv[i + 3 * stride];
+    if (MODE == 0) {
+      double y0 = yv[i], y1 = yv[i + stride], y2 = yv[i + 2 * stride], y3 = yv[i + 3 * stride];
+      a0 += x0 * y0; a1 += x1 * y1; a2 += x2 * y2; a3 += x3 * y3;
+    } else if (MODE == 1) {
+      a0 += x0 * x0; a1 += x1 * x1; a2 += x2 * x2; a3 += x3 * x3;
+    } else {
+      a0 += pow(x0, p); a1 += pow(x1, p); a2 += pow(x2, p); a3 += pow(x3, p);
+    }
+  }
+  for (; i < n; i += stride) {
+    double x0 = xv[i];
+    if (MODE == 0) a0 += x0 * yv[i];
+    else if (MODE == 1) a0 += x0 * x0;
+    else a0 += pow(x0, p);
+  }
+  double s = warp_sum((a0 + a1) + (a2 + a3));
+  __shared__ double warp_part[kThreads / 32];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) warp_part[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    double t = lane < kThreads / 32 ? warp_part[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) {
+      partials[(size_t)vec * gridDim.x + blockIdx.x] = t;
+      __threadfence();
+      unsigned int ticket = atomicAdd(&tickets[vec], 1u);
+      is_last = (ticket == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (is_last && warp == 0) {
+    __threadfence();
+    // fixed-order final sum over the blocks of this vector
+    double t = 0.0;
+    const volatile double* pv = partials + (size_t)vec * gridDim.x;
+    for (unsigned int b = lane; b < gridDim.x; b += 32) t += pv[b];
+    t = warp_sum(t);
+    if (lane == 0) {
+      out[vec] = t;
+      tickets[vec] = 0;  // re-arm for the next call
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) fill_kernel(double* __restrict__ y, int64_t n, double v) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) y[i] = v;
+}
+
+// y *= alpha  (rmul!, src/MultiVector.jl:63)
+__global__ void __launch_bounds__(kThreads) scale_kernel(double* __restrict__ y, int64_t n, double alpha) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) y[i] = __dmul_rn(y[i], alpha);
+}
+
+// column v scaled by alpha[v]  (src/MultiVector.jl:72-77)
+__global__ void __launch_bounds__(kThreads) scale_vec_kernel(double* __restrict__ y, int64_t n, const double* __restrict__ alpha) {
+  const double a = alpha[blockIdx.y];
+  double* col = y + (size_t)blockIdx.y * n;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) col[i] = __dmul_rn(col[i], a);
+}
+
+// y = (a*x) + (b*y), unfused  (broadcast copyto!, src/MultiVector.jl:497-502)
+__global__ void __launch_bounds__(kThreads) axpby_kernel(double* __restrict__ y, const double* __restrict__ x, int64_t n, double a,
+                                                           double b) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride)
+    y[i] = __dadd_rn(__dmul_rn(a, x[i]), __dmul_rn(b, y[i]));
+}
+
+int grid_for(int64_t n, int per_thread) {
+  int64_t want = (n + (int64_t)kThreads * per_thread - 1) / ((int64_t)kThreads * per_thread);
+  int64_t cap = (int64_t)ctx().sm_count * 8;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+struct ReduceWorkspace {
+  double* partials;      // [k][blocks]
+  unsigned int* tickets; // [k]
+  double* out;           // [k]
+};
+
+// carve the reduction workspace out of a dedicated device buffer (tickets must stay zero between calls)
+DeviceBuffer g_reduce_buf;
+int32_t g_reduce_k = 0;
+
+ReduceWorkspace reduce_workspace(int32_t k) {
+  if (k > g_reduce_k) {
+    JP_CUDA(cudaStreamSynchronize(ctx().compute));
+    int32_t kk = k < 32 ? 32 : k;
+    size_t bytes = (size_t)kk * kMaxReduceBlocks * 8 + (size_t)kk * 8 + (size_t)kk * 8;
+    g_reduce_buf.alloc(bytes);
+    JP_CUDA(cudaMemsetAsync(g_reduce_buf.p, 0, bytes, ctx().compute));
+    g_reduce_k = kk;
+  }
+  ReduceWorkspace w;
+  char* base = (char*)g_reduce_buf.p;
+  w.partials = (double*)base;
+  w.out = (double*)(base + (size_t)g_reduce_k * kMaxReduceBlocks * 8);
+  w.tickets = (unsigned int*)(base + (size_t)g_reduce_k * kMaxReduceBlocks * 8 + (size_t)g_reduce_k * 8);
+  return w;
+}
+
+// local sums for every vector -> w.out (device), stream-ordered on compute
+template <int MODE>
+double* reduce_local(const MultiVector& x, const MultiVector* y, double p) {
+  ReduceWorkspace w = reduce_workspace(x.k);
+  int blocks = grid_for(x.n, 8);
+  if (blocks > kMaxReduceBlocks) blocks = kMaxReduceBlocks;
+  dim3 grid(blocks, x.k);
+  reduce_kernel<MODE><<<grid, kThreads, 0, ctx().compute>>>(x.d(), y ? y->d() : nullptr, x.n, p, w.partials, w.tickets, w.out);
+  JP_LAUNCH_CHECK();
+  return w.out;
+}
+
+// sumAll of the k local sums + copy to the host (the only synchronising step)
+void finish_reduction(Comm& c, double* dev_out, int32_t k, double* host_out) {
+  Context& x = ctx();
+  comm_allreduce_device(c, dev_out, k, x.compute);
+  double* pinned = (double*)host_scratch((size_t)k * 8);
+  JP_CUDA(cudaMemcpyAsync(pinned, dev_out, (size_t)k * 8, cudaMemcpyDeviceToHost, x.compute));
+  JP_CUDA(cudaStreamSynchronize(x.compute));
+  std::memcpy(host_out, pinned, (size_t)k * 8);
+}
+
+}  // namespace
+
+void release_reduce_workspace() {
+  g_reduce_buf.release();
+  g_reduce_k = 0;
+}
+
+void launch_scale_fill(double* y, int64_t n, double beta, cudaStream_t stream) {
+  if (n == 0) return;
+  if (beta == 0.0) {
+    JP_CUDA(cudaMemsetAsync(y, 0, (size_t)n * 8, stream));
+  } else if (beta != 1.0) {
+    scale_kernel<<<grid_for(n, 4), kThreads, 0, stream>>>(y, n, beta);
+    JP_LAUNCH_CHECK();
+  }
+}
+
+}  // namespace jp
+
+using namespace jp;
+
+extern "C" {
+
+int32_t jp_mv_create(int32_t n_local, int32_t k, jp_handle* out) {
+  return guarded([&] {
+    require_init();
+    JP_REQUIRE(out != nullptr, "jp_mv_create: null output");
+    JP_REQUIRE(n_local >= 0 && k >= 0, "jp_mv_create: negative shape");
+    auto mv = std::make_unique<MultiVector>();
+    mv->n = n_local;
+    mv->k = k;
+    size_t bytes = (size_t)n_local * k * 8;
+    mv->data.alloc(bytes + 64);  // slack: vectorised tails may over-read, never over-write
+    JP_CUDA(cudaMemsetAsync(mv->data.p, 0, bytes + 64, ctx().compute));
+    *out = register_object(std::move(mv));
+  });
+}
+
+int32_t jp_mv_destroy(jp_handle mv) {
+  return guarded([&] { destroy_object(mv, Kind::MultiVector, "multivector"); });
+}
+
+int32_t jp_mv_shape(jp_handle mv, int32_t* n_local, int32_t* k) {
+  return guarded([&] {
+    MultiVector* m = get<MultiVector>(mv, Kind::MultiVector, "multivector");
+    if (n_local) *n_local = m->n;
+    if (k) *k = m->k;
+  });
+}
+
+int32_t jp_mv_upload(jp_handle mv, const double* host) {
+  return guarded([&] {
+    require_init();
+    MultiVector* m = get<MultiVector>(mv, Kind::MultiVector, "multivector");
+    size_t bytes = (size_t)m->n * m->k * 8;
+    if (bytes == 0) return;
+    JP_REQUIRE(host != nullptr, "jp_mv_upload: null host pointer");
+    JP_CUDA(cudaMemcpyAsync(m->d(), host, bytes, cudaMemcpyHostToDevice, ctx().compute));
+    JP_CUDA(cudaStreamSynchronize(ctx().compute));  // the host array is not retained
+  });
+}
+
+int32_t jp_mv_download(jp_handle mv, double* host) {
+  return guarded([&] {
+    require_init();
+    MultiVector* m = get<MultiVector>(mv, Kind::MultiVector, "multivector");
+    size_t bytes = (size_t)m->n * m->k * 8;
+    if (bytes == 0) return;
+    JP_REQUIRE(host != nullptr, "jp_mv_download: null host pointer");
+    JP_CUDA(cudaStreamSynchronize(ctx().comm));
+    JP_CUDA(cudaMemcpyAsync(host, m->d(), bytes, cudaMemcpyDeviceToHost, ctx().compute));
+    JP_CUDA(cudaStreamSynchronize(ctx().compute));
+  });
+}
+
+int32_t jp_mv_copy(jp_handle dst, jp_handle src) {
+  return guarded([&] {
+    require_init();
+    MultiVector* d = get<MultiVector>(dst, Kind::MultiVector, "multivector");
+    MultiVector* s = get<MultiVector>(src, Kind::MultiVector, "multivector");
+    JP_REQUIRE(d->n == s->n && d->k == s->k, "jp_mv_copy: shapes differ");
+    size_t bytes = (size_t)d->n * d->k * 8;
+    if (bytes && d != s) JP_CUDA(cudaMemcpyAsync(d->d(), s->d(), bytes, cudaMemcpyDeviceToDevice, ctx().compute));
+  });
+}
+
+int32_t jp_mv_fill(jp_handle mv, double value) {
+  return guarded([&] {
+    require_init();
+    MultiVector* m = get<MultiVector>(mv, Kind::MultiVector, "multivector");
+    int64_t n = (int64_t)m->n * m->k;
+    if (n == 0) return;
+    if (value == 0.0 && !std::signbit(value)) {
+      JP_CUDA(cudaMemsetAsync(m->d(), 0, (size_t)n * 8, ctx().compute));
+    } else {
+      fill_kernel<<<grid_for(n, 4), kThreads, 0, ctx().compute>>>(m->d(), n, value);
+      JP_LAUNCH_CHECK();
+    }
+  });
+}
+
+int32_t jp_mv_scale(jp_handle mv, double alpha) {
+  return guarded([&] {
+    require_init();
+    MultiVector* m = get<MultiVector>(mv, Kind::MultiVector, "multivector");
+    int64_t n = (int64_t)m->n * m->k;
+    if (n == 0) return;
+    scale_kernel<<<grid_for(n, 4), kThreads, 0, ctx().compute>>>(m->d(), n, alpha);
+    JP_LAUNCH_CHECK();
+  });
+}
+
+int32_t jp_mv_scale_vec(jp_handle mv, const double* alpha_k) {
+  return guarded([&] {
+    require_init();
+    MultiVector* m = get<MultiVector>(mv, Kind::MultiVector, "multivector");
+    if (m->n == 0 || m->k == 0) return;
+    JP_REQUIRE(alpha_k != nullptr, "jp_mv_scale_vec: null alpha");
+    double* pinned = (double*)host_scratch((size_t)m->k * 8);
+    std::memcpy(pinned, alpha_k, (size_t)m->k * 8);
+    double* dev = (double*)scratch((size_t)m->k * 8);
+    JP_CUDA(cudaMemcpyAsync(dev, pinned, (size_t)m->k * 8, cudaMemcpyHostToDevice, ctx().compute));
+    dim3 grid(grid_for(m->n, 4), m->k);
+    scale_vec_kernel<<<grid, kThreads, 0, ctx().compute>>>(m->d(), m->n, dev);
+    JP_LAUNCH_CHECK();
+    JP_CUDA(cudaStreamSynchronize(ctx().compute));  // pinned/scratch staging is shared
+  });
+}
+
+int32_t jp_mv_axpby(jp_handle y, double a, jp_handle x, double b) {
+  return guarded([&] {
+    require_init();
+    MultiVector* my = get<MultiVector>(y, Kind::MultiVector, "multivector");
+    MultiVector* mx = get<MultiVector>(x, Kind::MultiVector, "multivector");
+    JP_REQUIRE(my->n == mx->n && my->k == mx->k, "jp_mv_axpby: shapes differ");
+    int64_t n = (int64_t)my->n * my->k;
+    if (n == 0) return;
+    axpby_kernel<<<grid_for(n, 4), kThreads, 0, ctx().compute>>>(my->d(), mx->d(), n, a, b);
+    JP_LAUNCH_CHECK();
+  });
+}
+
+int32_t jp_mv_dot(jp_handle comm, jp_handle x, jp_handle y, double* out_k) {
+  return guarded([&] {
+    require_init();
+    Comm* c = get<Comm>(comm, Kind::Comm, "comm");
+    MultiVector* mx = get<MultiVector>(x, Kind::MultiVector, "multivector");
+    MultiVector* my = get<MultiVector>(y, Kind::MultiVector, "multivector");
+    // src/MultiVector.jl:88-93
+    JP_REQUIRE(mx->k == my->k, "MultiVectors must have the same number of vectors to take the dot product of them");
+    JP_REQUIRE(mx->n == my->n, "Vectors must have the same length to take the dot product of them");
+    if (mx->k == 0) return;
+    JP_REQUIRE(out_k != nullptr, "jp_mv_dot: null output");
+    double* dev = reduce_local<0>(*mx, my, 0.0);
+    finish_reduction(*c, dev, mx->k, out_k);
+  });
+}
+
+int32_t jp_mv_norm2(jp_handle comm, jp_handle x, double* out_k) {
+  return guarded([&] {
+    require_init();
+    Comm* c = get<Comm>(comm, Kind::Comm, "comm");
+    MultiVector* mx = get<MultiVector>(x, Kind::MultiVector, "multivector");
+    if (mx->k == 0) return;
+    JP_REQUIRE(out_k != nullptr, "jp_mv_norm2: null output");
+    double* dev = reduce_local<1>(*mx, nullptr, 2.0);
+    finish_reduction(*c, dev, mx->k, out_k);
+    for (int v = 0; v < mx->k; ++v) out_k[v] = std::sqrt(out_k[v]);  // sqrt after the allreduce, src/MultiVector.jl:132-133
+  });
+}
+
+int32_t jp_mv_normp(jp_handle comm, jp_handle x, double p, double* out_k) {
+  return guarded([&] {
+    require_init();
+    if (p == 2.0) {
+      int32_t rc = jp_mv_norm2(comm, x, out_k);
+      if (rc != JP_OK) {
+        char buf[512];
+        jp_last_error(buf, sizeof buf);
+        fail(rc, buf);
+      }
+      return;
+    }
+    Comm* c = get<Comm>(comm, Kind::Comm, "comm");
+    MultiVector* mx = get<MultiVector>(x, Kind::MultiVector, "multivector");
+    if (mx->k == 0) return;
+    JP_REQUIRE(out_k != nullptr, "jp_mv_normp: null output");
+    double* dev = reduce_local<2>(*mx, nullptr, p);
+    finish_reduction(*c, dev, mx->k, out_k);
+    for (int v = 0; v < mx->k; ++v) out_k[v] = std::pow(out_k[v], 1.0 / p);  // src/MultiVector.jl:143-144
+  });
+}
+
+int32_t jp_mv_comm_reduce(jp_handle comm, jp_handle mv) {
+  return guarded([&] {
+    require_init();
+    Comm* c = get<Comm>(comm, Kind::Comm, "comm");
+    MultiVector* m = get<MultiVector>(mv, Kind::MultiVector, "multivector");
+    // view .= sumAll(comm, view), src/MultiVector.jl:159-160 (identity on SerialComm)
+    comm_allreduce_device(*c, m->d(), (int64_t)m->n * m->k, ctx().compute);
+  });
+}
+
+}  // extern "C"

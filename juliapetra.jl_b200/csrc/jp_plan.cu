@@ -1,0 +1,412 @@
+// jp_plan.cu -- Import/Export plans on the device, the halo exchange, and apply!.
+//
+// Replaces, for MultiVectors:
+//   doTransfer            src/DistObject.jl:200-258
+//   copyAndPermute        src/MultiVector.jl:308-325   (copy kernel; skipped entirely on the fused apply path)
+//   packAndPrepare        src/MultiVector.jl:327-349   (pack kernel -> LID-major, vector-minor send buffer)
+//   resolvePosts/Waits    src/MPIDistributor.jl:451-590 (one ncclGroup of send/recv per neighbour on the comm
+//                         stream; message sizes are static per plan, so the reference's 4 barriers, 2 size
+//                         handshakes and byte (de)serialisation per exchange disappear)
+//   unpackAndCombine      src/MultiVector.jl:351-371   (unpack kernel; not needed on the fused path because the
+//                         receives land directly in the halo buffer the boundary kernel reads)
+//   apply!                src/RowMatrix.jl:261-357
+//
+// Fused apply (NO_TRANS, plan whose remote LIDs are the contiguous tail of the column map, which is what
+// __makeColMap produces, src/CSRGraphInternalMethods.jl:946-981):
+//   comm stream   : wait(X ready) -> pack -> ncclGroup{recv halo, send boundary rows} -> record(halo ready)
+//   compute stream: interior row blocks (local columns only, read straight from X: the reference's full local
+//                   copy K8 is gone) -> wait(halo ready) -> boundary row blocks (X + halo buffer)
+#include "jp_common.h"
+
+namespace jp {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// sendbuf[i*k + j] = src[lid[i] + j*ld]      (src/MultiVector.jl:339-347)
+__global__ void __launch_bounds__(kThreads) pack_kernel(const double* __restrict__ src, int64_t ld, const int32_t* __restrict__ lids,
+                                                          int32_t n, int32_t k, double* __restrict__ buf) {
+  const int64_t total = (int64_t)n * k;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += stride) {
+    const int32_t j = (int32_t)(t / n), i = (int32_t)(t - (int64_t)j * n);  // consecutive threads: consecutive LIDs
+    buf[(size_t)i * k + j] = __ldg(src + __ldg(lids + i) + (size_t)j * ld);
+  }
+}
+
+// tgt[lid[i] + j*ld] = buf[i*k + j]          (src/MultiVector.jl:363-369; combine mode ignored, as there)
+__global__ void __launch_bounds__(kThreads) unpack_kernel(double* __restrict__ tgt, int64_t ld, const int32_t* __restrict__ lids,
+                                                            int32_t n, int32_t k, const double* __restrict__ buf) {
+  const int64_t total = (int64_t)n * k;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += stride) {
+    const int32_t j = (int32_t)(t / n), i = (int32_t)(t - (int64_t)j * n);
+    tgt[__ldg(lids + i) + (size_t)j * ld] = __ldg(buf + (size_t)i * k + j);
+  }
+}
+
+// tgt[to[i] + j*ldt] = src[from[i] + j*lds]  (src/MultiVector.jl:320-323)
+__global__ void __launch_bounds__(kThreads) permute_kernel(double* __restrict__ tgt, int64_t ldt, const double* __restrict__ src,
+                                                             int64_t lds, const int32_t* __restrict__ to, const int32_t* __restrict__ from,
+                                                             int32_t n, int32_t k) {
+  const int64_t total = (int64_t)n * k;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += stride) {
+    const int32_t j = (int32_t)(t / n), i = (int32_t)(t - (int64_t)j * n);
+    tgt[__ldg(to + i) + (size_t)j * ldt] = __ldg(src + __ldg(from + i) + (size_t)j * lds);
+  }
+}
+
+int grid_for(int64_t n) {
+  int64_t want = (n + kThreads - 1) / kThreads;
+  int64_t cap = (int64_t)ctx().sm_count * 8;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+void upload_lids(DeviceBuffer& buf, const int32_t* host, int32_t n, int32_t base, int32_t limit, const char* what) {
+  std::vector<int32_t> v((size_t)n);
+  for (int32_t i = 0; i < n; ++i) {
+    v[i] = host[i] - base;
+    JP_REQUIRE(v[i] >= 0 && v[i] < limit, std::string("jp_plan_create: ") + what + " out of range");
+  }
+  buf.alloc((size_t)n * 4 + 16);
+  if (n > 0) JP_CUDA(cudaMemcpy(buf.p, v.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+}
+
+// the exchange proper, on the comm stream: sendbuf -> peers' recvbuf
+void exchange(Plan& p, int32_t k, bool reverse, cudaStream_t st) {
+  Comm& c = *p.comm;
+  const std::vector<int32_t>& to = reverse ? p.procs_from : p.procs_to;
+  const std::vector<int64_t>& lto = reverse ? p.lengths_from : p.lengths_to;
+  const std::vector<int64_t>& sto = reverse ? p.starts_from : p.starts_to;
+  const std::vector<int32_t>& from = reverse ? p.procs_to : p.procs_from;
+  const std::vector<int64_t>& lfrom = reverse ? p.lengths_to : p.lengths_from;
+  const std::vector<int64_t>& sfrom = reverse ? p.starts_to : p.starts_from;
+  double* sb = p.sendbuf.as<double>();
+  double* rb = p.recvbuf.as<double>();
+  const int me = c.rank0 + 1;
+  bool any_remote = false;
+  for (size_t i = 0; i < from.size(); ++i) any_remote |= (from[i] != me && lfrom[i] > 0);
+  for (size_t i = 0; i < to.size(); ++i) any_remote |= (to[i] != me && lto[i] > 0);
+  if (any_remote) {
+    JP_REQUIRE_STATE(!c.serial, "plan names remote ranks but its comm is serial");
+    JP_NCCL(ncclGroupStart());
+    for (size_t i = 0; i < from.size(); ++i)
+      if (from[i] != me && lfrom[i] > 0)
+        JP_NCCL(ncclRecv(rb + (size_t)sfrom[i] * k, (size_t)lfrom[i] * k, ncclDouble, from[i] - 1, c.nccl, st));
+    for (size_t i = 0; i < to.size(); ++i)
+      if (to[i] != me && lto[i] > 0)
+        JP_NCCL(ncclSend(sb + (size_t)sto[i] * k, (size_t)lto[i] * k, ncclDouble, to[i] - 1, c.nccl, st));
+    JP_NCCL(ncclGroupEnd());
+  }
+  // self message: aliased in the reference (src/MPIDistributor.jl:559-561), a device copy here
+  for (size_t i = 0; i < to.size(); ++i) {
+    if (to[i] != me || lto[i] == 0) continue;
+    for (size_t r = 0; r < from.size(); ++r)
+      if (from[r] == me)
+        JP_CUDA(cudaMemcpyAsync(rb + (size_t)sfrom[r] * k, sb + (size_t)sto[i] * k, (size_t)lto[i] * k * 8, cudaMemcpyDeviceToDevice, st));
+  }
+}
+
+}  // namespace
+
+void plan_ensure_buffers(Plan& p, int32_t k) {
+  if (k <= p.buf_k) return;
+  JP_CUDA(cudaStreamSynchronize(ctx().comm));
+  JP_CUDA(cudaStreamSynchronize(ctx().compute));
+  int64_t ns = std::max<int64_t>(p.n_export, 0), nr = std::max<int64_t>(p.n_remote, 0);
+  // reverse mode swaps the roles of the two buffers' capacities
+  int64_t cap = std::max(ns, nr);
+  p.sendbuf.alloc((size_t)cap * k * 8 + 64);
+  p.recvbuf.alloc((size_t)cap * k * 8 + 64);
+  p.buf_k = k;
+}
+
+// comm stream: [copyAndPermute] + pack + exchange; records p.ev_done.  halo_only skips copyAndPermute (the fused
+// apply reads the local part from X directly).
+void plan_post(Plan& p, const MultiVector& src, MultiVector* tgt, bool halo_only, int32_t combine_mode, bool reverse) {
+  Context& x = ctx();
+  const int32_t k = src.k;
+  plan_ensure_buffers(p, k);
+  JP_CUDA(cudaEventRecord(x.ev_x_ready, x.compute));
+  JP_CUDA(cudaStreamWaitEvent(x.comm, x.ev_x_ready, 0));
+  if (!halo_only) {
+    // copyAndPermute (src/MultiVector.jl:308-325)
+    if (p.num_same > 0 && k > 0 && tgt->d() != src.d())
+      JP_CUDA(cudaMemcpy2DAsync(tgt->d(), (size_t)tgt->n * 8, src.d(), (size_t)src.n * 8, (size_t)p.num_same * 8, (size_t)k,
+                                cudaMemcpyDeviceToDevice, x.comm));
+    if (p.n_permute > 0 && k > 0) {
+      permute_kernel<<<grid_for((int64_t)p.n_permute * k), kThreads, 0, x.comm>>>(tgt->d(), tgt->n, src.d(), src.n,
+                                                                                 p.permute_to.as<int32_t>(), p.permute_from.as<int32_t>(),
+                                                                                 p.n_permute, k);
+      JP_LAUNCH_CHECK();
+    }
+  }
+  if (combine_mode != JP_ZERO && k > 0) {  // src/DistObject.jl:238
+    if (p.n_export > 0) {
+      pack_kernel<<<grid_for((int64_t)p.n_export * k), kThreads, 0, x.comm>>>(src.d(), src.n, p.export_lids.as<int32_t>(), p.n_export, k,
+                                                                             p.sendbuf.as<double>());
+      JP_LAUNCH_CHECK();
+    }
+    exchange(p, k, reverse, x.comm);
+  }
+  JP_CUDA(cudaEventRecord(p.ev_done, x.comm));
+}
+
+// tgt[remote_lids] = recvbuf on `stream` (must already be ordered after ev_done)
+void plan_unpack(Plan& p, MultiVector& tgt, cudaStream_t stream) {
+  if (p.n_remote == 0 || tgt.k == 0) return;
+  unpack_kernel<<<grid_for((int64_t)p.n_remote * tgt.k), kThreads, 0, stream>>>(tgt.d(), tgt.n, p.remote_lids.as<int32_t>(), p.n_remote, tgt.k,
+                                                                               p.recvbuf.as<double>());
+  JP_LAUNCH_CHECK();
+}
+
+}  // namespace jp
+
+using namespace jp;
+
+namespace {
+
+void check_transfer_args(Plan* p, MultiVector* s, MultiVector* t, int32_t combine_mode, int32_t reverse) {
+  JP_REQUIRE(combine_mode >= JP_ADD && combine_mode <= JP_ZERO, "bad CombineMode");
+  // checkSizes, src/MultiVector.jl:301-306
+  JP_REQUIRE(s->k == t->k, "checkSize() indicates that the destination object is not a legal target for redistribution from the "
+                           "source object: MultiVectors must have the same number of columns");
+  JP_REQUIRE(s->n == p->n_src && t->n == p->n_tgt, "multivector local lengths do not match the plan's source/target maps");
+  if (reverse) {
+    int64_t tot_to = 0, tot_from = 0;
+    for (int64_t l : p->lengths_to) tot_to += l;
+    for (int64_t l : p->lengths_from) tot_from += l;
+    JP_REQUIRE(p->n_export == tot_from && p->n_remote == tot_to,
+               "reverse-mode transfer with non-matching export/remote lists is undefined in the reference "
+               "(src/DistObject.jl:104-157 pass the forward lists unswapped)");
+  }
+}
+
+// apply!'s NO_TRANS body on device objects; X is a domain-map multivector
+void apply_no_trans(Csr* a, Plan* p, MultiVector* y, MultiVector* x, double alpha, double beta) {
+  Context& c = ctx();
+  JP_REQUIRE(y->n == a->n_rows, "apply!: Y must have one row per local matrix row");
+  if (p == nullptr) {
+    // importer === nothing: XColMap = X (src/RowMatrix.jl:290-291)
+    JP_REQUIRE(x->n == a->n_cols, "apply!: X does not match the column map and no importer was given");
+    launch_spmv(*a, a->blocks_all, a->n_blocks_all, false, x->d(), x->n, nullptr, 1, y->d(), y->n, y->k, alpha, beta, c.compute);
+    return;
+  }
+  JP_REQUIRE(x->n == p->n_src, "apply!: X does not match the importer's source map");
+  JP_REQUIRE(p->n_tgt == a->n_cols, "apply!: the importer's target map is not the matrix's column map");
+  const bool fused = p->remote_is_tail && p->n_permute == 0 && p->num_same == a->n_local_cols && p->num_same == x->n &&
+                     p->num_same + p->n_remote == a->n_cols;
+  if (!fused) {
+    // general column map (unused local columns => permutes): import into the cached column-map multivector
+    // exactly as the reference does (src/RowMatrix.jl:294-295), then one launch over all row blocks
+    if (!a->import_mv || a->import_mv->k != x->k) {  // createColumnMapMultiVector, src/RowMatrix.jl:210-233
+      JP_CUDA(cudaStreamSynchronize(c.compute));
+      JP_CUDA(cudaStreamSynchronize(c.comm));
+      a->import_mv = std::make_unique<MultiVector>();
+      a->import_mv->n = a->n_cols;
+      a->import_mv->k = x->k;
+      a->import_mv->data.alloc((size_t)a->n_cols * x->k * 8 + 64);
+      JP_CUDA(cudaMemsetAsync(a->import_mv->d(), 0, (size_t)a->n_cols * x->k * 8 + 64, c.compute));
+    }
+    MultiVector* xc = a->import_mv.get();
+    plan_post(*p, *x, xc, /*halo_only=*/false, JP_INSERT, false);
+    JP_CUDA(cudaStreamWaitEvent(c.compute, p->ev_done, 0));
+    plan_unpack(*p, *xc, c.compute);
+    launch_spmv(*a, a->blocks_all, a->n_blocks_all, false, xc->d(), xc->n, nullptr, 1, y->d(), y->n, y->k, alpha, beta, c.compute);
+    JP_CUDA(cudaEventRecord(c.ev_tmp, c.compute));
+    JP_CUDA(cudaStreamWaitEvent(c.comm, c.ev_tmp, 0));
+    return;
+  }
+  plan_post(*p, *x, nullptr, /*halo_only=*/true, JP_INSERT, false);
+  launch_spmv(*a, a->blocks_interior, a->n_blocks_interior, false, x->d(), x->n, nullptr, 1, y->d(), y->n, y->k, alpha, beta, c.compute);
+  JP_CUDA(cudaStreamWaitEvent(c.compute, p->ev_done, 0));
+  launch_spmv(*a, a->blocks_boundary, a->n_blocks_boundary, true, x->d(), x->n, p->recvbuf.as<double>(), y->k, y->d(), y->n, y->k, alpha,
+              beta, c.compute);
+  // the next post must not overwrite sendbuf/recvbuf before the boundary kernel has read them
+  JP_CUDA(cudaEventRecord(c.ev_tmp, c.compute));
+  JP_CUDA(cudaStreamWaitEvent(c.comm, c.ev_tmp, 0));
+}
+
+void apply_impl(Csr* a, Plan* p, MultiVector* y, MultiVector* x, int32_t mode, double alpha, double beta) {
+  JP_REQUIRE(mode == JP_NO_TRANS || mode == JP_TRANS || mode == JP_CONJ_TRANS, "apply!: bad TransposeMode");
+  JP_REQUIRE(x != y, "apply!: X and Y must be different multivectors");
+  JP_REQUIRE(x->k == y->k, "apply!: X and Y must have the same number of vectors");
+  if (alpha == 0.0) {  // src/RowMatrix.jl:271-278
+    launch_scale_fill(y->d(), (int64_t)y->n * y->k, beta, ctx().compute);
+    return;
+  }
+  if (mode == JP_NO_TRANS) {
+    apply_no_trans(a, p, y, x, alpha, beta);
+  } else {
+    // distributed TRANS needs doExport(..., ADD), which the reference does not implement
+    // (src/RowMatrix.jl:324-352 uses undefined names; ADD ignored at src/MultiVector.jl:359-371)
+    JP_REQUIRE_STATE(p == nullptr, "apply!: transposed apply with a non-trivial importer is non-functional in the reference");
+    JP_REQUIRE(x->n == a->n_rows && y->n == a->n_cols, "apply!: transposed apply needs X on the row map and Y on the column map");
+    launch_spmv_trans(*a, x->d(), x->n, y->d(), y->n, y->n, y->k, alpha, beta, ctx().compute);
+  }
+}
+
+// device staging for jp_apply_host, keyed by shape
+struct HostPathCache {
+  std::unique_ptr<MultiVector> x, y;
+};
+HostPathCache g_host_cache;
+
+MultiVector* cached_mv(std::unique_ptr<MultiVector>& slot, int32_t n, int32_t k) {
+  if (!slot || slot->n != n || slot->k != k) {
+    JP_CUDA(cudaStreamSynchronize(ctx().compute));
+    JP_CUDA(cudaStreamSynchronize(ctx().comm));
+    slot = std::make_unique<MultiVector>();
+    slot->n = n;
+    slot->k = k;
+    slot->data.alloc((size_t)n * k * 8 + 64);
+  }
+  return slot.get();
+}
+
+}  // namespace
+
+namespace jp {
+void release_host_path_cache() {
+  g_host_cache.x.reset();
+  g_host_cache.y.reset();
+}
+}  // namespace jp
+
+extern "C" {
+
+int32_t jp_plan_create(jp_handle comm, int32_t n_src, int32_t n_tgt, int32_t num_same, const int32_t* permute_to,
+                       const int32_t* permute_from, int32_t n_permute, const int32_t* remote_lids, int32_t n_remote,
+                       const int32_t* export_lids, int32_t n_export, const int32_t* procs_to, const int64_t* lengths_to,
+                       int32_t n_sends, const int32_t* procs_from, const int64_t* lengths_from, int32_t n_recvs,
+                       int32_t index_base, jp_handle* out) {
+  return guarded([&] {
+    require_init();
+    JP_REQUIRE(out != nullptr, "jp_plan_create: null output");
+    Comm* c = get<Comm>(comm, Kind::Comm, "comm");
+    JP_REQUIRE(index_base == 0 || index_base == 1, "jp_plan_create: index_base must be 0 or 1");
+    JP_REQUIRE(n_src >= 0 && n_tgt >= 0 && n_permute >= 0 && n_remote >= 0 && n_export >= 0 && n_sends >= 0 && n_recvs >= 0,
+               "jp_plan_create: negative size");
+    JP_REQUIRE(num_same >= 0 && num_same <= n_src && num_same <= n_tgt, "jp_plan_create: numSameIDs out of range");
+    auto p = std::make_unique<Plan>();
+    p->comm = c;
+    p->n_src = n_src;
+    p->n_tgt = n_tgt;
+    p->num_same = num_same;
+    p->n_permute = n_permute;
+    p->n_remote = n_remote;
+    p->n_export = n_export;
+    upload_lids(p->permute_to, permute_to, n_permute, index_base, n_tgt, "permuteToLIDs");
+    upload_lids(p->permute_from, permute_from, n_permute, index_base, n_src, "permuteFromLIDs");
+    upload_lids(p->remote_lids, remote_lids, n_remote, index_base, n_tgt, "remoteLIDs");
+    upload_lids(p->export_lids, export_lids, n_export, index_base, n_src, "exportLIDs");
+    p->remote_is_tail = true;
+    for (int32_t i = 0; i < n_remote; ++i)
+      if (remote_lids[i] - index_base != num_same + i) {
+        p->remote_is_tail = false;
+        break;
+      }
+    int64_t tot_to = 0, tot_from = 0;
+    for (int32_t i = 0; i < n_sends; ++i) {
+      JP_REQUIRE(procs_to[i] >= 1 && procs_to[i] <= c->nproc, "jp_plan_create: procs_to out of range");
+      JP_REQUIRE(lengths_to[i] >= 0, "jp_plan_create: negative send length");
+      p->procs_to.push_back(procs_to[i]);
+      p->lengths_to.push_back(lengths_to[i]);
+      p->starts_to.push_back(tot_to);
+      tot_to += lengths_to[i];
+    }
+    for (int32_t i = 0; i < n_recvs; ++i) {
+      JP_REQUIRE(procs_from[i] >= 1 && procs_from[i] <= c->nproc, "jp_plan_create: procs_from out of range");
+      JP_REQUIRE(lengths_from[i] >= 0, "jp_plan_create: negative receive length");
+      p->procs_from.push_back(procs_from[i]);
+      p->lengths_from.push_back(lengths_from[i]);
+      p->starts_from.push_back(tot_from);
+      tot_from += lengths_from[i];
+    }
+    JP_REQUIRE(tot_to == n_export, "jp_plan_create: sum(lengths_to) must equal the number of export LIDs");
+    JP_REQUIRE(tot_from == n_remote, "jp_plan_create: sum(lengths_from) must equal the number of remote LIDs");
+    JP_CUDA(cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming));
+    *out = register_object(std::move(p));
+  });
+}
+
+int32_t jp_plan_destroy(jp_handle plan) {
+  return guarded([&] { destroy_object(plan, Kind::Plan, "plan"); });
+}
+
+int32_t jp_transfer_post(jp_handle plan, jp_handle src, jp_handle tgt, int32_t combine_mode, int32_t reverse) {
+  return guarded([&] {
+    require_init();
+    Plan* p = get<Plan>(plan, Kind::Plan, "plan");
+    MultiVector* s = get<MultiVector>(src, Kind::MultiVector, "multivector");
+    MultiVector* t = get<MultiVector>(tgt, Kind::MultiVector, "multivector");
+    check_transfer_args(p, s, t, combine_mode, reverse);
+    plan_post(*p, *s, t, false, combine_mode, reverse != 0);
+    p->posted = true;
+    p->posted_tgt = tgt;
+    p->posted_k = combine_mode == JP_ZERO ? 0 : s->k;
+  });
+}
+
+int32_t jp_transfer_wait(jp_handle plan) {
+  return guarded([&] {
+    require_init();
+    Plan* p = get<Plan>(plan, Kind::Plan, "plan");
+    // src/MPIDistributor.jl:574-576 / src/SerialComm.jl:52-54
+    JP_REQUIRE_STATE(p->posted, "Cannot resolve waits when no posts have been made");
+    p->posted = false;
+    MultiVector* t = get<MultiVector>(p->posted_tgt, Kind::MultiVector, "multivector");
+    Context& x = ctx();
+    JP_CUDA(cudaStreamWaitEvent(x.compute, p->ev_done, 0));
+    if (p->posted_k > 0) plan_unpack(*p, *t, x.compute);
+    JP_CUDA(cudaEventRecord(x.ev_tmp, x.compute));
+    JP_CUDA(cudaStreamWaitEvent(x.comm, x.ev_tmp, 0));
+  });
+}
+
+int32_t jp_transfer(jp_handle plan, jp_handle src, jp_handle tgt, int32_t combine_mode, int32_t reverse) {
+  int32_t rc = jp_transfer_post(plan, src, tgt, combine_mode, reverse);
+  if (rc != JP_OK) return rc;
+  return jp_transfer_wait(plan);
+}
+
+int32_t jp_apply(jp_handle comm, jp_handle Y, jp_handle A, jp_handle X, jp_handle plan, int32_t mode, double alpha, double beta) {
+  return guarded([&] {
+    require_init();
+    (void)get<Comm>(comm, Kind::Comm, "comm");
+    Csr* a = get<Csr>(A, Kind::Csr, "csr matrix");
+    MultiVector* y = get<MultiVector>(Y, Kind::MultiVector, "multivector");
+    MultiVector* x = get<MultiVector>(X, Kind::MultiVector, "multivector");
+    Plan* p = plan ? get<Plan>(plan, Kind::Plan, "plan") : nullptr;
+    apply_impl(a, p, y, x, mode, alpha, beta);
+  });
+}
+
+int32_t jp_apply_host(jp_handle comm, jp_handle A, jp_handle plan, const double* x_host, double* y_host, int32_t k, int32_t mode,
+                      double alpha, double beta) {
+  return guarded([&] {
+    require_init();
+    (void)get<Comm>(comm, Kind::Comm, "comm");
+    Csr* a = get<Csr>(A, Kind::Csr, "csr matrix");
+    Plan* p = plan ? get<Plan>(plan, Kind::Plan, "plan") : nullptr;
+    JP_REQUIRE(k >= 0 && x_host && y_host, "jp_apply_host: bad arguments");
+    const bool trans = mode != JP_NO_TRANS;
+    const int32_t nx = trans ? a->n_rows : (p ? p->n_src : a->n_cols);
+    const int32_t ny = trans ? a->n_cols : a->n_rows;
+    MultiVector* x = cached_mv(g_host_cache.x, nx, k);
+    MultiVector* y = cached_mv(g_host_cache.y, ny, k);
+    Context& c = ctx();
+    const size_t xb = (size_t)nx * k * 8, yb = (size_t)ny * k * 8;
+    if (xb) JP_CUDA(cudaMemcpyAsync(x->d(), x_host, xb, cudaMemcpyHostToDevice, c.compute));
+    if (beta != 0.0 && yb) JP_CUDA(cudaMemcpyAsync(y->d(), y_host, yb, cudaMemcpyHostToDevice, c.compute));
+    apply_impl(a, p, y, x, mode, alpha, beta);
+    if (yb) JP_CUDA(cudaMemcpyAsync(y_host, y->d(), yb, cudaMemcpyDeviceToHost, c.compute));
+    JP_CUDA(cudaStreamSynchronize(c.compute));
+  });
+}
+
+}  // extern "C"
