@@ -456,3 +456,19 @@ def norm_raw(a, p=2.0):
     out = np.empty(a.shape[1], dtype=np.float64)
     lib().orc_norm_raw(a.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(a.shape[0]), a.shape[1], C.c_double(p), _p(out, C.c_double))
     return out
+
+
+def time_local_apply_raw(rowptr1, colind1, vals, x, alpha=1.0, beta=0.0, iters=3, warmup=1):
+    """seconds per localApply on ONE core (the SerialComm configuration), timing only the reference loop"""
+    x = np.asfortranarray(x, dtype=np.float64)
+    if x.ndim == 1:
+        x = x.reshape(-1, 1, order="F")
+    rp = np.ascontiguousarray(rowptr1, dtype=np.int32)
+    ci = np.ascontiguousarray(colind1, dtype=np.int32)
+    va = np.ascontiguousarray(vals, dtype=np.float64)
+    y = np.zeros((len(rp) - 1, x.shape[1]), dtype=np.float64, order="F")
+    f = lib().orc_time_local_apply_raw
+    f.restype = C.c_double
+    return float(f(y.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(y.shape[0]), C.c_int32(len(rp) - 1), _p(rp, C.c_int32),
+                   _p(ci, C.c_int32), _p(va, C.c_double), x.ctypes.data_as(C.POINTER(C.c_double)), C.c_int64(x.shape[0]), x.shape[1],
+                   C.c_double(alpha), C.c_double(beta), iters, warmup))

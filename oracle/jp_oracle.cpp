@@ -1957,6 +1957,20 @@ void orc_local_apply_raw(double* y, int64_t ldy, int32_t nrows, const int32_t* r
   L.vals.assign(vals, vals + nnz);
   localApply(y, ldy, L, nrows, x, ldx, k, mode, alpha, beta);
 }
+// seconds per localApply (NO_TRANS) on one core, timing the reference loop only (CPU baseline, SerialComm case)
+double orc_time_local_apply_raw(double* y, int64_t ldy, int32_t nrows, const int32_t* rowptr, const int32_t* colind, const double* vals,
+                                const double* x, int64_t ldx, int k, double alpha, double beta, int iters, int warmup) {
+  LocalMat L;
+  L.ptrs.assign(rowptr, rowptr + nrows + 1);
+  int64_t nnz = rowptr[nrows] - 1;
+  L.inds.assign(colind, colind + nnz);
+  L.vals.assign(vals, vals + nnz);
+  for (int i = 0; i < warmup; ++i) localApply(y, ldy, L, nrows, x, ldx, k, NO_TRANS, alpha, beta);
+  auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < iters; ++i) localApply(y, ldy, L, nrows, x, ldx, k, NO_TRANS, alpha, beta);
+  auto t1 = std::chrono::steady_clock::now();
+  return std::chrono::duration<double>(t1 - t0).count() / (iters > 0 ? iters : 1);
+}
 void orc_dot_raw(const double* a, const double* b, int64_t n, int k, double* out) { dotLocal(a, b, n, k, out); }
 void orc_norm_raw(const double* a, int64_t n, int k, double p, double* out) { normLocal(a, n, k, p, out); }
 // seconds per apply!, P simulated ranks on P threads (CPU baseline)

@@ -14,33 +14,7 @@ from jpetra_b200 import synthetic  # noqa: E402
 import oracle as O  # noqa: E402
 
 
-def problem_rows(kind, N, first, last, **kw):
-    if kind == "powerlaw":
-        return synthetic.powerlaw_rows(N, first, last, kw.get("mean", 16.0), kw.get("max_len", 10000))
-    return synthetic.stencil_rows(kind, N, first, last)
-
-
-def global_rows(kind, N):
-    return N if kind == "powerlaw" else N ** synthetic.STENCILS[kind][0]
-
-
-def oracle_problem(kind, N, P, **kw):
-    """(comm, rowMap, filled OMatrix) in the oracle for P simulated ranks"""
-    c = O.OComm(P)
-    n = global_rows(kind, N)
-    m = O.OMap.uniform(c, n)
-    per_rank = []
-    for pid in range(1, P + 1):
-        info = m.info(pid)
-        rows, rp, cols, vals = problem_rows(kind, N, info["minMyGID"], info["maxMyGID"], **kw) if info["numMyElements"] else (
-            np.zeros(0, np.int64), np.zeros(1, np.int64), np.zeros(0, np.int64), np.zeros(0))
-        per_rank.append((rows, rp, cols, vals))
-    A = O.OMatrix(m, [np.diff(r[1]) for r in per_rank])
-    for pid, (rows, rp, cols, vals) in enumerate(per_rank, start=1):
-        if len(rows):
-            A.insert_rows(pid, rows, rp, cols, vals)
-    A.fill_complete(m, m)
-    return c, m, A
+from oracle.problems import global_rows, oracle_problem, problem_rows  # noqa: E402,F401
 
 
 def free_port():
