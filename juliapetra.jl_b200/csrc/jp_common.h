@@ -178,6 +178,12 @@ struct Csr : Object {
   // cache of the column-map multivector (A.importMV, src/CSRMatrix.jl:10,772-781); only used when the column
   // map is not [domain prefix | remote tail] and the fused apply path does not apply
   std::unique_ptr<MultiVector> import_mv;
+  // CUDA graphs of the fused apply sequence, keyed by the device addresses and scalars it was captured with
+  std::unordered_map<std::string, cudaGraphExec_t> graphs;
+  ~Csr() override {
+    for (auto& kv : graphs)
+      if (kv.second) cudaGraphExecDestroy(kv.second);
+  }
 };
 
 struct Plan : Object {

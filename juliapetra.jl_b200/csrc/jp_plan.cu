@@ -16,6 +16,8 @@
 //   comm stream   : wait(X ready) -> pack -> ncclGroup{recv halo, send boundary rows} -> record(halo ready)
 //   compute stream: interior row blocks (local columns only, read straight from X: the reference's full local
 //                   copy K8 is gone) -> wait(halo ready) -> boundary row blocks (X + halo buffer)
+#include <cstdlib>
+
 #include "jp_common.h"
 
 namespace jp {
@@ -221,14 +223,69 @@ void apply_no_trans(Csr* a, Plan* p, MultiVector* y, MultiVector* x, double alph
     JP_CUDA(cudaStreamWaitEvent(c.comm, c.ev_tmp, 0));
     return;
   }
-  plan_post(*p, *x, nullptr, /*halo_only=*/true, JP_INSERT, false);
-  launch_spmv(*a, a->blocks_interior, a->n_blocks_interior, false, x->d(), x->n, nullptr, 1, y->d(), y->n, y->k, alpha, beta, c.compute);
-  JP_CUDA(cudaStreamWaitEvent(c.compute, p->ev_done, 0));
-  launch_spmv(*a, a->blocks_boundary, a->n_blocks_boundary, true, x->d(), x->n, p->recvbuf.as<double>(), y->k, y->d(), y->n, y->k, alpha,
-              beta, c.compute);
-  // the next post must not overwrite sendbuf/recvbuf before the boundary kernel has read them
-  JP_CUDA(cudaEventRecord(c.ev_tmp, c.compute));
-  JP_CUDA(cudaStreamWaitEvent(c.comm, c.ev_tmp, 0));
+  // Fused path.  The sequence is 2 streams, 3-4 kernels and one NCCL group; at 8 GPUs the device time of one apply
+  // (~35 us for 256^3) is of the order of the host time to enqueue it, so the sequence is captured ONCE per
+  // (X, Y, plan buffers, alpha, beta) into a CUDA graph and replayed with a single cudaGraphLaunch afterwards.
+  plan_ensure_buffers(*p, x->k);
+  auto body = [&](bool capturing) {
+    plan_post(*p, *x, nullptr, /*halo_only=*/true, JP_INSERT, false);
+    launch_spmv(*a, a->blocks_interior, a->n_blocks_interior, false, x->d(), x->n, nullptr, 1, y->d(), y->n, y->k, alpha, beta, c.compute);
+    JP_CUDA(cudaStreamWaitEvent(c.compute, p->ev_done, 0));
+    launch_spmv(*a, a->blocks_boundary, a->n_blocks_boundary, true, x->d(), x->n, p->recvbuf.as<double>(), y->k, y->d(), y->n, y->k,
+                alpha, beta, c.compute);
+    if (!capturing) {
+      // the next post must not overwrite sendbuf/recvbuf before the boundary kernel has read them
+      // (inside a graph the whole sequence is one unit in the compute stream, so replays are already ordered)
+      JP_CUDA(cudaEventRecord(c.ev_tmp, c.compute));
+      JP_CUDA(cudaStreamWaitEvent(c.comm, c.ev_tmp, 0));
+    }
+  };
+  static const bool use_graph = []() {
+    const char* v = std::getenv("JP_APPLY_GRAPH");
+    return !(v && *v == '0');
+  }();
+  if (!use_graph) {
+    body(false);
+    return;
+  }
+  char key[256];
+  std::snprintf(key, sizeof key, "%p|%p|%p|%p|%p|%d|%a|%a", (void*)x->d(), (void*)y->d(), (void*)p, p->sendbuf.p, p->recvbuf.p, (int)x->k,
+                alpha, beta);
+  auto it = a->graphs.find(key);
+  if (it != a->graphs.end()) {
+    if (it->second != nullptr) {
+      JP_CUDA(cudaGraphLaunch(it->second, c.compute));
+      count_launch(3 + (p->n_export > 0 ? 1 : 0));
+      return;
+    }
+    // second call with this key: everything lazy (shared-memory attributes, NCCL connections) was set up by the
+    // first, eager call -> capture now
+    JP_CUDA(cudaStreamSynchronize(c.comm));
+    cudaGraph_t graph = nullptr;
+    JP_CUDA(cudaStreamBeginCapture(c.compute, cudaStreamCaptureModeThreadLocal));
+    try {
+      body(true);
+    } catch (...) {
+      cudaStreamEndCapture(c.compute, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    JP_CUDA(cudaStreamEndCapture(c.compute, &graph));
+    cudaGraphExec_t exec = nullptr;
+    JP_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+    JP_CUDA(cudaGraphDestroy(graph));
+    it->second = exec;
+    JP_CUDA(cudaGraphLaunch(exec, c.compute));
+    return;
+  }
+  if (a->graphs.size() > 64) {  // bound the cache: drop everything (handles change rarely in a solver loop)
+    JP_CUDA(cudaStreamSynchronize(c.compute));
+    for (auto& kv : a->graphs)
+      if (kv.second) cudaGraphExecDestroy(kv.second);
+    a->graphs.clear();
+  }
+  a->graphs.emplace(key, nullptr);
+  body(false);
 }
 
 void apply_impl(Csr* a, Plan* p, MultiVector* y, MultiVector* x, int32_t mode, double alpha, double beta) {

@@ -428,12 +428,11 @@ def test_csrmatrix_mpi_layout_appendix_b():
     """Column map / Import lists / CSR of the 4-rank matrix.  Not asserted by the reference's tests (only the
     final Y is); derived by hand from the reference code in SURVEY.md Appendix B."""
     c, m, A = _mpi_laplacian()
-    exp = {
-        1: dict(col=[1, 2, 3], remote=[3], exportL=[2], exportP=[2], rp=[1, 3, 6], ci=[1, 2, 1, 2, 3], va=[2, -1, -1, 2, -1]),
-        2: dict(col=[3, 4, 2, 5], remote=[3, 4], exportL=[1, 2], exportP=[1, 3], rp=[1, 4, 7], ci=[1, 2, 3, 1, 2, 4], va=[2, -1, -1, -1, 2, -1]),
-        3: dict(col=[5, 6, 4, 7], remote=[3, 4], exportL=[1, 2], exportP=[2, 4], rp=[1, 4, 7], ci=[1, 2, 3, 1, 2, 4], va=[2, -1, -1, -1, 2, -1]),
-        4: dict(col=[7, 8, 6], remote=[3], exportL=[1], exportP=[3], rp=[1, 4, 6], ci=[1, 2, 3, 2, 3], va=[2, -1, -1, 2, -1]),
-    }
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "appendix_b.json")))["ranks"]
+    exp = {int(p): dict(col=g["colMap"], remote=g["remoteLIDs"], exportL=g["exportLIDs"], exportP=g["exportPIDs"], rp=g["rowptr"], ci=g["colind"],
+                        va=g["vals"]) for p, g in gold.items()}
     imp = A.importer
     assert imp is not None and A.exporter is None
     for pid, e in exp.items():
