@@ -178,6 +178,10 @@ struct Csr : Object {
   // cache of the column-map multivector (A.importMV, src/CSRMatrix.jl:10,772-781); only used when the column
   // map is not [domain prefix | remote tail] and the fused apply path does not apply
   std::unique_ptr<MultiVector> import_mv;
+  // host-buffer path (jp_apply_host): the all-blocks list cut into chunks; chunk c covers blocks
+  // [chunk_block[c], chunk_block[c+1]) = rows [chunk_row[c], chunk_row[c+1]) and reads columns <= chunk_maxcol[c]
+  // (prefix maximum), so its kernel can start as soon as that much of X has been uploaded
+  std::vector<int32_t> chunk_block, chunk_row, chunk_maxcol;
   // CUDA graphs of the fused apply sequence, keyed by the device addresses and scalars it was captured with
   std::unordered_map<std::string, cudaGraphExec_t> graphs;
   ~Csr() override {
@@ -217,6 +221,9 @@ struct Event : Object {
 
 // ---- cross-file entry points (internal) ---------------------------------------------------------
 // y[r0:r1) rows of A applied to x (+ optional halo) on `stream`
+void launch_spmv_blocks(const Csr& A, const void* blocks_int4, int32_t n_blocks, bool use_halo, const double* x, int64_t ldx,
+                        const double* halo, int32_t halo_k, double* y, int64_t ldy, int32_t k, double alpha, double beta,
+                        cudaStream_t stream);
 void launch_spmv(const Csr& A, const DeviceBuffer& blocks, int32_t n_blocks, bool use_halo, const double* x, int64_t ldx,
                  const double* halo, int32_t halo_k, double* y, int64_t ldy, int32_t k, double alpha, double beta,
                  cudaStream_t stream);

@@ -419,9 +419,15 @@ void launch_spmm_impl(const Csr& A, const int4* b, int32_t n_blocks, size_t smem
 void launch_spmv(const Csr& A, const DeviceBuffer& blocks, int32_t n_blocks, bool use_halo, const double* x, int64_t ldx,
                  const double* halo, int32_t halo_k, double* y, int64_t ldy, int32_t k, double alpha, double beta,
                  cudaStream_t stream) {
+  launch_spmv_blocks(A, blocks.p, n_blocks, use_halo, x, ldx, halo, halo_k, y, ldy, k, alpha, beta, stream);
+}
+
+void launch_spmv_blocks(const Csr& A, const void* blocks_int4, int32_t n_blocks, bool use_halo, const double* x, int64_t ldx,
+                        const double* halo, int32_t halo_k, double* y, int64_t ldy, int32_t k, double alpha, double beta,
+                        cudaStream_t stream) {
   if (n_blocks == 0 || k == 0) return;
   const size_t smem = stage_smem_bytes(A.nnz_cap);
-  const int4* b = blocks.as<int4>();
+  const int4* b = static_cast<const int4*>(blocks_int4);
   static const int tma = env_int("JP_SPMV_TMA", 1);  // 0: cp.async staging (kept for A/B measurements)
   if (k == 1) {
     if (use_halo) {
@@ -493,6 +499,7 @@ int32_t jp_csr_create(int32_t n_rows, int32_t n_cols, int32_t n_local_cols, int6
     }
     JP_REQUIRE(rp[n_rows] == nnz, "jp_csr_create: rowptr[last] does not match nnz");
     std::vector<uint8_t> cls((size_t)n_rows, 0);
+    std::vector<int32_t> rowmax((size_t)n_rows, -1);
     int32_t maxlen = 0;
     for (int32_t r = 0; r < n_rows; ++r) {
       int32_t mx = -1;
@@ -502,6 +509,7 @@ int32_t jp_csr_create(int32_t n_rows, int32_t n_cols, int32_t n_local_cols, int6
         mx = c > mx ? c : mx;
       }
       cls[r] = mx >= n_local_cols;
+      rowmax[r] = mx;
       maxlen = std::max(maxlen, rp[r + 1] - rp[r]);
     }
     A->max_row_len = maxlen;
@@ -522,6 +530,19 @@ int32_t jp_csr_create(int32_t n_rows, int32_t n_cols, int32_t n_local_cols, int6
     upload_blocks(bi, A->blocks_interior, A->n_blocks_interior);
     upload_blocks(bb, A->blocks_boundary, A->n_blocks_boundary);
     upload_blocks(ba, A->blocks_all, A->n_blocks_all);
+    {  // chunks of the all-blocks list for the pipelined host-buffer path
+      const int nchunks = std::max(1, std::min<int>(env_int("JP_HOST_CHUNKS", 16), (int)ba.size()));
+      int32_t run = -1;
+      for (int c = 0; c <= nchunks; ++c) {
+        const int32_t bidx = (int32_t)((int64_t)ba.size() * c / nchunks);
+        A->chunk_block.push_back(bidx);
+        A->chunk_row.push_back(bidx < (int32_t)ba.size() ? ba[bidx].x : n_rows);
+      }
+      for (int c = 0; c < nchunks; ++c) {
+        for (int32_t r = A->chunk_row[c]; r < A->chunk_row[c + 1]; ++r) run = std::max(run, rowmax[r]);
+        A->chunk_maxcol.push_back(run);
+      }
+    }
     // device arrays; 64 elements of zeroed slack so the 16-byte staging may over-read past nnz
     A->rowptr.alloc(((size_t)n_rows + 1 + 16) * 4);  // slack: row pointers are staged in aligned groups of 4
     JP_CUDA(cudaMemset(A->rowptr.p, 0, ((size_t)n_rows + 1 + 16) * 4));

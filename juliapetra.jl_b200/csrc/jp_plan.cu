@@ -13,9 +13,10 @@
 //
 // Fused apply (NO_TRANS, plan whose remote LIDs are the contiguous tail of the column map, which is what
 // __makeColMap produces, src/CSRGraphInternalMethods.jl:946-981):
-//   comm stream   : wait(X ready) -> pack -> ncclGroup{recv halo, send boundary rows} -> record(halo ready)
+//   comm stream   : wait(X ready) -> pack -> ncclGroup{recv halo, send boundary rows} -> boundary row blocks
+//                   (X + halo buffer) -> record(done)
 //   compute stream: interior row blocks (local columns only, read straight from X: the reference's full local
-//                   copy K8 is gone) -> wait(halo ready) -> boundary row blocks (X + halo buffer)
+//                   copy K8 is gone), concurrently -> wait(done)
 #include <cstdlib>
 
 #include "jp_common.h"
@@ -228,21 +229,20 @@ void apply_no_trans(Csr* a, Plan* p, MultiVector* y, MultiVector* x, double alph
   // (X, Y, plan buffers, alpha, beta) into a CUDA graph and replayed with a single cudaGraphLaunch afterwards.
   plan_ensure_buffers(*p, x->k);
   auto body = [&](bool capturing) {
+    // comm stream (high priority): pack -> exchange -> BOUNDARY rows; compute stream: INTERIOR rows, concurrently.
+    // The two launches write disjoint rows of Y; the compute stream joins on the comm stream at the end, so there
+    // is no serial boundary-kernel latency after the interior kernel's tail.
     plan_post(*p, *x, nullptr, /*halo_only=*/true, JP_INSERT, false);
+    launch_spmv(*a, a->blocks_boundary, a->n_blocks_boundary, true, x->d(), x->n, p->recvbuf.as<double>(), y->k, y->d(), y->n, y->k,
+                alpha, beta, c.comm);
+    JP_CUDA(cudaEventRecord(p->ev_done, c.comm));
     launch_spmv(*a, a->blocks_interior, a->n_blocks_interior, false, x->d(), x->n, nullptr, 1, y->d(), y->n, y->k, alpha, beta, c.compute);
     JP_CUDA(cudaStreamWaitEvent(c.compute, p->ev_done, 0));
-    launch_spmv(*a, a->blocks_boundary, a->n_blocks_boundary, true, x->d(), x->n, p->recvbuf.as<double>(), y->k, y->d(), y->n, y->k,
-                alpha, beta, c.compute);
-    if (!capturing) {
-      // the next post must not overwrite sendbuf/recvbuf before the boundary kernel has read them
-      // (inside a graph the whole sequence is one unit in the compute stream, so replays are already ordered)
-      JP_CUDA(cudaEventRecord(c.ev_tmp, c.compute));
-      JP_CUDA(cudaStreamWaitEvent(c.comm, c.ev_tmp, 0));
-    }
+    (void)capturing;
   };
   static const bool use_graph = []() {
-    const char* v = std::getenv("JP_APPLY_GRAPH");
-    return !(v && *v == '0');
+    const char* v = std::getenv("JP_APPLY_GRAPH");  // opt-in: replay the sequence as one CUDA graph
+    return v && *v == '1';
   }();
   if (!use_graph) {
     body(false);
@@ -312,6 +312,7 @@ struct HostPathCache {
   std::unique_ptr<MultiVector> x, y;
 };
 HostPathCache g_host_cache;
+std::vector<cudaEvent_t> g_host_events;
 
 MultiVector* cached_mv(std::unique_ptr<MultiVector>& slot, int32_t n, int32_t k) {
   if (!slot || slot->n != n || slot->k != k) {
@@ -331,6 +332,8 @@ namespace jp {
 void release_host_path_cache() {
   g_host_cache.x.reset();
   g_host_cache.y.reset();
+  for (cudaEvent_t e : g_host_events) cudaEventDestroy(e);
+  g_host_events.clear();
 }
 }  // namespace jp
 
@@ -458,11 +461,62 @@ int32_t jp_apply_host(jp_handle comm, jp_handle A, jp_handle plan, const double*
     MultiVector* y = cached_mv(g_host_cache.y, ny, k);
     Context& c = ctx();
     const size_t xb = (size_t)nx * k * 8, yb = (size_t)ny * k * 8;
-    if (xb) JP_CUDA(cudaMemcpyAsync(x->d(), x_host, xb, cudaMemcpyHostToDevice, c.compute));
-    if (beta != 0.0 && yb) JP_CUDA(cudaMemcpyAsync(y->d(), y_host, yb, cudaMemcpyHostToDevice, c.compute));
-    apply_impl(a, p, y, x, mode, alpha, beta);
-    if (yb) JP_CUDA(cudaMemcpyAsync(y_host, y->d(), yb, cudaMemcpyDeviceToHost, c.compute));
-    JP_CUDA(cudaStreamSynchronize(c.compute));
+    const int nch = (int)a->chunk_maxcol.size();
+    static const bool pipeline_enabled = []() {
+      const char* v = std::getenv("JP_HOST_PIPELINE");
+      return !(v && *v == '0');
+    }();
+    const bool pipelined = pipeline_enabled && !trans && p == nullptr && beta == 0.0 && alpha != 0.0 && nch > 1 && xb >= ((size_t)4 << 20) &&
+                           nx == a->n_cols && ny == a->n_rows;
+    if (!pipelined) {
+      if (xb) JP_CUDA(cudaMemcpyAsync(x->d(), x_host, xb, cudaMemcpyHostToDevice, c.compute));
+      if (beta != 0.0 && yb) JP_CUDA(cudaMemcpyAsync(y->d(), y_host, yb, cudaMemcpyHostToDevice, c.compute));
+      apply_impl(a, p, y, x, mode, alpha, beta);
+      if (yb) JP_CUDA(cudaMemcpyAsync(y_host, y->d(), yb, cudaMemcpyDeviceToHost, c.compute));
+      JP_CUDA(cudaStreamSynchronize(c.compute));
+      return;
+    }
+    // Pipelined single-GPU path: PCIe is full duplex, so X goes up in row chunks on one stream, each chunk of row
+    // blocks runs as soon as the columns it reads have arrived (prefix maximum of the block's column indices), and
+    // its slice of Y goes down on a third stream while the next pieces of X are still uploading.
+    while ((int)g_host_events.size() < 2 * nch) {
+      cudaEvent_t e;
+      JP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      g_host_events.push_back(e);
+    }
+    cudaStream_t h2d = c.comm, comp = c.compute, d2h = c.copy;
+    JP_CUDA(cudaEventRecord(c.ev_tmp, comp));  // order after whatever the compute stream was doing
+    JP_CUDA(cudaStreamWaitEvent(h2d, c.ev_tmp, 0));
+    std::vector<int32_t> xr(nch + 1);
+    for (int i = 0; i <= nch; ++i) xr[i] = (int32_t)((int64_t)nx * i / nch);
+    for (int i = 0; i < nch; ++i) {
+      const size_t w = (size_t)(xr[i + 1] - xr[i]) * 8;
+      if (w)
+        JP_CUDA(cudaMemcpy2DAsync(x->d() + xr[i], (size_t)nx * 8, x_host + xr[i], (size_t)nx * 8, w, (size_t)k, cudaMemcpyHostToDevice, h2d));
+      JP_CUDA(cudaEventRecord(g_host_events[i], h2d));
+    }
+    const char* blocks = static_cast<const char*>(a->blocks_all.p);
+    int uploaded_chunk = -1;  // highest X chunk the compute stream already waits for
+    for (int ch = 0; ch < nch; ++ch) {
+      const int32_t need = a->chunk_maxcol[ch];
+      int want = 0;
+      while (want < nch - 1 && xr[want + 1] <= need) ++want;
+      if (want > uploaded_chunk) {
+        JP_CUDA(cudaStreamWaitEvent(comp, g_host_events[want], 0));
+        uploaded_chunk = want;
+      }
+      const int32_t b0 = a->chunk_block[ch], b1 = a->chunk_block[ch + 1];
+      launch_spmv_blocks(*a, blocks + (size_t)b0 * 16, b1 - b0, false, x->d(), nx, nullptr, 1, y->d(), ny, k, alpha, beta, comp);
+      JP_CUDA(cudaEventRecord(g_host_events[nch + ch], comp));
+      JP_CUDA(cudaStreamWaitEvent(d2h, g_host_events[nch + ch], 0));
+      const int32_t r0 = a->chunk_row[ch], r1 = a->chunk_row[ch + 1];
+      if (r1 > r0)
+        JP_CUDA(cudaMemcpy2DAsync(y_host + r0, (size_t)ny * 8, y->d() + r0, (size_t)ny * 8, (size_t)(r1 - r0) * 8, (size_t)k,
+                                  cudaMemcpyDeviceToHost, d2h));
+    }
+    JP_CUDA(cudaStreamSynchronize(d2h));
+    JP_CUDA(cudaStreamSynchronize(comp));
+    JP_CUDA(cudaStreamSynchronize(h2d));
   });
 }
 
