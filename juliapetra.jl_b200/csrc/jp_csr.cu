@@ -243,9 +243,21 @@ spmv_kernel(const int4* __restrict__ blocks, const int32_t* __restrict__ rowptr,
       *yp = combine(beta == 0.0 ? 0.0 : *yp, sum, alpha, beta);
     }
   } else {
+    // WARPROW: the block holds at least one long row.  Short rows still go thread-per-row (sequential sum, the
+    // reference's order); only rows longer than kLongRowLen are summed by a whole warp.
+    for (int r = tid; r < b.nrows; r += kSpmvThreads) {
+      const int s = rp[r] - b.a0, e = rp[r + 1] - b.a0;
+      if (e - s <= kLongRowLen) {
+        double sum = 0.0;
+        for (int i = s; i < e; ++i) sum = __dadd_rn(sum, sv.s_val[i]);
+        double* yp = y + b.row0 + r;
+        *yp = combine(beta == 0.0 ? 0.0 : *yp, sum, alpha, beta);
+      }
+    }
     const int lane = tid & 31, warp = tid >> 5;
     for (int r = warp; r < b.nrows; r += kSpmvThreads / 32) {
       const int s = rp[r] - b.a0, e = rp[r + 1] - b.a0;
+      if (e - s <= kLongRowLen) continue;  // warp-uniform
       double sum = 0.0;
       for (int i = s + lane; i < e; i += 32) sum += sv.s_val[i];
       sum = warp_sum(sum);

@@ -354,6 +354,28 @@ def test_host_buffer_apply_matches_device_apply():
     assert np.array_equal(A.apply_host(x), O.local_apply_raw(np.zeros((n, 1)), A.rowOffsets, A.localIndices1D, A.values, x))
 
 
+@pytest.mark.parametrize("kind,N,k", [("7pt", 96, 1), ("5pt", 900, 2), ("powerlaw", 700000, 1)])
+def test_pipelined_host_buffer_apply(kind, N, k):
+    """large enough (>= 4 MB of X) for jp_apply_host to take its pipelined path: chunked H2D of X, row-block chunks
+    launched as soon as the columns they read are on the device, chunked D2H of Y; must equal the device path"""
+    c, m, A = serial_matrix(kind, N, max_len=500)
+    n = m.numMyElements()
+    assert n * k * 8 >= 4 << 20
+    x = synthetic.vector_block(1, n, k, seed=1)
+    X, Y = jp.DenseMultiVector(m, x), jp.DenseMultiVector(m, k)
+    A.apply_(Y, X)
+    want = Y.data
+    for _ in range(2):
+        yh = np.full((n, k), np.nan, order="F")
+        A.apply_host(x, yh)
+        assert np.array_equal(yh, want)
+    # beta != 0 takes the unpipelined path and must still agree
+    y0 = synthetic.vector_block(1, n, k, seed=2)
+    Y2 = jp.DenseMultiVector(m, y0)
+    A.apply_(Y2, X, jp.NO_TRANS, 3.0, 0.5)
+    assert np.array_equal(A.apply_host(x, np.array(y0, order="F", copy=True), jp.NO_TRANS, 3.0, 0.5), Y2.data)
+
+
 def test_invalid_handles_and_arguments():
     lib = _lib.lib()
     with pytest.raises(jp.InvalidArgumentError):
