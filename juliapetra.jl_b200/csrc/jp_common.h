@@ -206,9 +206,21 @@ struct Plan : Object {
   jp_handle posted_tgt = 0;
   int32_t posted_k = 0;
   cudaEvent_t ev_done = nullptr;
-  ~Plan() override {
-    if (ev_done) cudaEventDestroy(ev_done);
-  }
+  // ---- peer-to-peer halo (fused apply): every rank exposes an ARENA through CUDA IPC:
+  //      [ready flags: uint64 per source rank | ack flags: uint64 per destination rank | recv buffer 0 | recv buffer 1]
+  //      senders store packed rows straight into the receiver's buffer over NVLink and publish `ready = epoch`;
+  //      receivers publish `ack = epoch` into the sender's arena when the boundary rows have consumed the halo.
+  int p2p_state = 0;            // 0 = not tried, 1 = active, -1 = unavailable (NCCL send/recv is used)
+  int32_t p2p_k = 0;
+  DeviceBuffer arena;
+  size_t arena_buf_bytes = 0;   // bytes of ONE of my recv buffers
+  std::vector<void*> peer_arena;   // per rank: mapped base of its arena (own rank: arena.p; non-neighbours: nullptr)
+  DeviceBuffer send_table;      // P2PSend per send block
+  DeviceBuffer wait_table;      // per source: {const uint64* ready flag (mine)}, {uint64* ack flag (in the source's arena)}
+  int32_t n_send_blocks = 0, n_sources = 0;
+  DeviceBuffer p2p_tickets;     // uint32 counters
+  uint64_t epoch = 0;
+  ~Plan() override;
 };
 
 struct Event : Object {
@@ -233,6 +245,8 @@ void launch_scale_fill(double* y, int64_t n, double beta, cudaStream_t stream); 
 void plan_ensure_buffers(Plan& p, int32_t k);
 void plan_post(Plan& p, const MultiVector& src, MultiVector* tgt, bool halo_only, int32_t combine_mode, bool reverse);
 void plan_unpack(Plan& p, MultiVector& tgt, cudaStream_t stream);
+const double* plan_post_p2p(Plan& p, const MultiVector& src);
+void plan_p2p_ack(Plan& p);
 void comm_allreduce_device(Comm& c, double* buf, int64_t n, cudaStream_t stream);
 void release_host_path_cache();
 void release_reduce_workspace();

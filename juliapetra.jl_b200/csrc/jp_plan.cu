@@ -114,6 +114,214 @@ void exchange(Plan& p, int32_t k, bool reverse, cudaStream_t st) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Peer-to-peer halo for the fused apply.  The halo of one apply is a few hundred KiB per neighbour (512 KiB for
+// 256^3 slabs), so its cost is latency, not bandwidth: an NCCL send/recv group costs ~25 us per exchange, the same
+// order as the whole interior SpMV at 8 GPUs.  Here the pack kernel IS the send: it gathers the exported rows of X
+// and stores them straight into the receiver's halo buffer through an IPC-mapped peer pointer (NVLink stores), then
+// publishes an epoch flag; the receiver's comm stream waits on the flag in a one-warp kernel right before the
+// boundary-row kernel.  Buffers are double-buffered by epoch parity and guarded by an ack flag, so a sender can
+// never overwrite a halo that is still being read.
+// ---------------------------------------------------------------------------------------------------------------
+struct P2PSend {
+  int32_t start, count;        // slice of the export list (elements)
+  double* dst[2];              // where it lands in the receiver's recv buffer 0 / 1 (peer or local pointer)
+  uint64_t* ready_flag;        // receiver's ready[me]
+  const uint64_t* ack_flag;    // my ack[receiver]
+};
+struct P2PSource {
+  const uint64_t* ready_flag;  // my ready[source]
+  uint64_t* ack_flag;          // source's ack[me]
+};
+
+constexpr int kArenaFlagBytes = 4096;  // ready flags at [0, 2048), ack flags at [2048, 4096): 256 ranks max
+constexpr long long kSpinLimit = 1ll << 23;  // a few seconds; a peer that never shows up must not hang the GPU
+
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+
+// fused pack + send: dst[(i - start)*k + j] = src[lid[i] + j*ld] for every export entry i, into the receivers' buffers
+__global__ void __launch_bounds__(kThreads) pack_p2p_kernel(const double* __restrict__ src, int64_t ld, const int32_t* __restrict__ lids,
+                                                              int32_t n, int32_t k, const P2PSend* __restrict__ table, int32_t n_blocks,
+                                                              uint64_t epoch, unsigned int* __restrict__ ticket) {
+  const int parity = (int)(epoch & 1);
+  // back-pressure: the buffer of this parity was last used at epoch-2; its reader must have acknowledged it
+  if (threadIdx.x < n_blocks && epoch > 2) {
+    long long spins = 0;
+    while (ld_acquire_sys(table[threadIdx.x].ack_flag) + 2 < epoch && ++spins < kSpinLimit) {
+    }
+  }
+  __syncthreads();
+  const int64_t total = (int64_t)n * k;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += stride) {
+    const int32_t j = (int32_t)(t / n), i = (int32_t)(t - (int64_t)j * n);
+    int b = 0;
+    while (b + 1 < n_blocks && i >= table[b].start + table[b].count) ++b;
+    table[b].dst[parity][(size_t)(i - table[b].start) * k + j] = __ldg(src + __ldg(lids + i) + (size_t)j * ld);
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last) {
+    __threadfence_system();
+    if (threadIdx.x < n_blocks) st_release_sys(table[threadIdx.x].ready_flag, epoch);
+    if (threadIdx.x == 0) *ticket = 0;
+  }
+}
+
+// one warp: wait until every source has published this epoch's halo
+__global__ void halo_wait_kernel(const P2PSource* __restrict__ sources, int32_t n_sources, uint64_t epoch) {
+  if ((int)threadIdx.x < n_sources) {
+    long long spins = 0;
+    while (ld_acquire_sys(sources[threadIdx.x].ready_flag) < epoch && ++spins < kSpinLimit) {
+    }
+  }
+}
+
+// one warp: tell every source that this epoch's halo has been consumed
+__global__ void halo_ack_kernel(const P2PSource* __restrict__ sources, int32_t n_sources, uint64_t epoch) {
+  if ((int)threadIdx.x < n_sources) st_release_sys(sources[threadIdx.x].ack_flag, epoch);
+}
+
+// all-gather of `bytes` host bytes per rank (setup only)
+void allgather_host_bytes(Comm& c, const void* in, size_t bytes, void* out) {
+  Context& x = ctx();
+  char* buf = (char*)scratch(bytes * (c.nproc + 1));
+  JP_CUDA(cudaMemcpyAsync(buf, in, bytes, cudaMemcpyHostToDevice, x.comm));
+  JP_NCCL(ncclAllGather(buf, buf + bytes, bytes, ncclChar, c.nccl, x.comm));
+  JP_CUDA(cudaMemcpyAsync(out, buf + bytes, bytes * c.nproc, cudaMemcpyDeviceToHost, x.comm));
+  JP_CUDA(cudaStreamSynchronize(x.comm));
+}
+
+// Collective over the plan's comm: build the arenas, exchange IPC handles and recv offsets, map the neighbours.
+// Returns false (on every rank) when peer mapping is unavailable; the caller then uses NCCL send/recv.
+bool p2p_setup(Plan& p, int32_t k) {
+  Comm& c = *p.comm;
+  Context& x = ctx();
+  if (c.serial) return false;
+  static const bool disabled = []() {
+    const char* v = std::getenv("JP_HALO");
+    return v && std::string(v) == "nccl";
+  }();
+  if (disabled) return false;
+  JP_REQUIRE(c.nproc <= 256, "peer-to-peer halo supports up to 256 ranks");
+  JP_CUDA(cudaStreamSynchronize(x.comm));
+  JP_CUDA(cudaStreamSynchronize(x.compute));
+  const int P = c.nproc, me = c.rank0;
+  // close a previous mapping (k changed)
+  for (int q = 0; q < (int)p.peer_arena.size(); ++q)
+    if (p.peer_arena[q] && q != me) cudaIpcCloseMemHandle(p.peer_arena[q]);
+  p.peer_arena.assign(P, nullptr);
+  p.arena_buf_bytes = (((size_t)std::max(p.n_remote, 1) * k * 8) + 255) & ~(size_t)255;
+  p.arena.alloc(kArenaFlagBytes + 2 * p.arena_buf_bytes);
+  JP_CUDA(cudaMemset(p.arena.p, 0, kArenaFlagBytes + 2 * p.arena_buf_bytes));
+  p.p2p_tickets.alloc(64);
+  JP_CUDA(cudaMemset(p.p2p_tickets.p, 0, 64));
+  p.epoch = 0;
+  // what every rank publishes: IPC handle, buffer size, and for each source rank the element offset of its data
+  struct Info {
+    cudaIpcMemHandle_t handle;
+    uint64_t buf_bytes;
+    int64_t recv_off[256];
+  };
+  std::vector<Info> all(P);
+  Info mine;
+  std::memset(&mine, 0, sizeof mine);
+  int ok = 1;
+  if (cudaIpcGetMemHandle(&mine.handle, p.arena.p) != cudaSuccess) {
+    cudaGetLastError();
+    ok = 0;
+  }
+  mine.buf_bytes = p.arena_buf_bytes;
+  for (int q = 0; q < 256; ++q) mine.recv_off[q] = -1;
+  for (size_t i = 0; i < p.procs_from.size(); ++i) mine.recv_off[p.procs_from[i] - 1] = p.starts_from[i];
+  allgather_host_bytes(c, &mine, sizeof(Info), all.data());
+  // map every neighbour (ranks I send to or receive from)
+  std::vector<char> need(P, 0);
+  for (int32_t q : p.procs_to) need[q - 1] = 1;
+  for (int32_t q : p.procs_from) need[q - 1] = 1;
+  p.peer_arena[me] = p.arena.p;
+  for (int q = 0; q < P && ok; ++q) {
+    if (!need[q] || q == me) continue;
+    void* ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, all[q].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0;
+      break;
+    }
+    p.peer_arena[q] = ptr;
+  }
+  // everybody or nobody
+  int64_t okv = ok, okmin = 0;
+  {
+    int64_t* buf = (int64_t*)scratch(16);
+    JP_CUDA(cudaMemcpyAsync(buf, &okv, 8, cudaMemcpyHostToDevice, x.comm));
+    JP_NCCL(ncclAllReduce(buf, buf, 1, ncclInt64, ncclMin, c.nccl, x.comm));
+    JP_CUDA(cudaMemcpyAsync(&okmin, buf, 8, cudaMemcpyDeviceToHost, x.comm));
+    JP_CUDA(cudaStreamSynchronize(x.comm));
+  }
+  if (!okmin) {
+    for (int q = 0; q < P; ++q)
+      if (p.peer_arena[q] && q != me) cudaIpcCloseMemHandle(p.peer_arena[q]);
+    p.peer_arena.assign(P, nullptr);
+    p.arena.release();
+    return false;
+  }
+  // device tables
+  std::vector<P2PSend> sends;
+  for (size_t i = 0; i < p.procs_to.size(); ++i) {
+    if (p.lengths_to[i] == 0) continue;
+    const int q = p.procs_to[i] - 1;
+    const int64_t off = all[q].recv_off[me];
+    JP_REQUIRE_STATE(off >= 0, "peer-to-peer halo: the receiver does not expect data from this rank");
+    char* base = (char*)p.peer_arena[q];
+    P2PSend s;
+    s.start = (int32_t)p.starts_to[i];
+    s.count = (int32_t)p.lengths_to[i];
+    s.dst[0] = (double*)(base + kArenaFlagBytes) + (size_t)off * k;
+    s.dst[1] = (double*)(base + kArenaFlagBytes + all[q].buf_bytes) + (size_t)off * k;
+    s.ready_flag = (uint64_t*)base + me;
+    s.ack_flag = (const uint64_t*)((char*)p.arena.p + 2048) + q;
+    sends.push_back(s);
+  }
+  JP_REQUIRE(sends.size() <= (size_t)kThreads, "peer-to-peer halo: too many destinations");
+  std::vector<P2PSource> sources;
+  for (size_t i = 0; i < p.procs_from.size(); ++i) {
+    if (p.lengths_from[i] == 0) continue;
+    const int q = p.procs_from[i] - 1;
+    P2PSource s;
+    s.ready_flag = (const uint64_t*)p.arena.p + q;
+    s.ack_flag = (uint64_t*)((char*)p.peer_arena[q] + 2048) + me;
+    sources.push_back(s);
+  }
+  JP_REQUIRE(sources.size() <= 32, "peer-to-peer halo: more than 32 sources per rank");
+  p.n_send_blocks = (int32_t)sends.size();
+  p.n_sources = (int32_t)sources.size();
+  p.send_table.alloc(sends.size() * sizeof(P2PSend) + 16);
+  p.wait_table.alloc(sources.size() * sizeof(P2PSource) + 16);
+  if (!sends.empty()) JP_CUDA(cudaMemcpy(p.send_table.p, sends.data(), sends.size() * sizeof(P2PSend), cudaMemcpyHostToDevice));
+  if (!sources.empty()) JP_CUDA(cudaMemcpy(p.wait_table.p, sources.data(), sources.size() * sizeof(P2PSource), cudaMemcpyHostToDevice));
+  // nobody may publish into an arena that is not mapped everywhere yet
+  {
+    double* buf = (double*)scratch(8);
+    JP_CUDA(cudaMemsetAsync(buf, 0, 8, x.comm));
+    JP_NCCL(ncclAllReduce(buf, buf, 1, ncclDouble, ncclSum, c.nccl, x.comm));
+    JP_CUDA(cudaStreamSynchronize(x.comm));
+  }
+  p.p2p_k = k;
+  return true;
+}
+
 }  // namespace
 
 void plan_ensure_buffers(Plan& p, int32_t k) {
@@ -165,6 +373,45 @@ void plan_unpack(Plan& p, MultiVector& tgt, cudaStream_t stream) {
   unpack_kernel<<<grid_for((int64_t)p.n_remote * tgt.k), kThreads, 0, stream>>>(tgt.d(), tgt.n, p.remote_lids.as<int32_t>(), p.n_remote, tgt.k,
                                                                                p.recvbuf.as<double>());
   JP_LAUNCH_CHECK();
+}
+
+Plan::~Plan() {
+  if (ev_done) cudaEventDestroy(ev_done);
+  const int me = comm ? comm->rank0 : -1;
+  for (int q = 0; q < (int)peer_arena.size(); ++q)
+    if (peer_arena[q] && q != me) cudaIpcCloseMemHandle(peer_arena[q]);
+}
+
+// Fused-apply halo over peer memory: returns the halo buffer of this epoch, or nullptr when the plan has to use
+// the NCCL path.  Enqueues pack+send and the wait on the comm stream; the caller launches the boundary rows on
+// the comm stream and then calls plan_p2p_ack().
+const double* plan_post_p2p(Plan& p, const MultiVector& src) {
+  Context& x = ctx();
+  const int32_t k = src.k;
+  if (p.p2p_state == 0 || (p.p2p_state == 1 && p.p2p_k != k)) p.p2p_state = p2p_setup(p, k) ? 1 : -1;
+  if (p.p2p_state != 1) return nullptr;
+  p.epoch += 1;
+  JP_CUDA(cudaEventRecord(x.ev_x_ready, x.compute));
+  JP_CUDA(cudaStreamWaitEvent(x.comm, x.ev_x_ready, 0));
+  if (p.n_export > 0 && p.n_send_blocks > 0) {
+    pack_p2p_kernel<<<grid_for((int64_t)p.n_export * k), kThreads, 0, x.comm>>>(src.d(), src.n, p.export_lids.as<int32_t>(), p.n_export, k,
+                                                                               p.send_table.as<P2PSend>(), p.n_send_blocks, p.epoch,
+                                                                               p.p2p_tickets.as<unsigned int>());
+    JP_LAUNCH_CHECK();
+  }
+  if (p.n_sources > 0) {
+    halo_wait_kernel<<<1, 32, 0, x.comm>>>(p.wait_table.as<P2PSource>(), p.n_sources, p.epoch);
+    JP_LAUNCH_CHECK();
+  }
+  return reinterpret_cast<const double*>((const char*)p.arena.p + kArenaFlagBytes + (p.epoch & 1) * p.arena_buf_bytes);
+}
+
+void plan_p2p_ack(Plan& p) {
+  Context& x = ctx();
+  if (p.n_sources > 0) {
+    halo_ack_kernel<<<1, 32, 0, x.comm>>>(p.wait_table.as<P2PSource>(), p.n_sources, p.epoch);
+    JP_LAUNCH_CHECK();
+  }
 }
 
 }  // namespace jp
@@ -232,9 +479,14 @@ void apply_no_trans(Csr* a, Plan* p, MultiVector* y, MultiVector* x, double alph
     // comm stream (high priority): pack -> exchange -> BOUNDARY rows; compute stream: INTERIOR rows, concurrently.
     // The two launches write disjoint rows of Y; the compute stream joins on the comm stream at the end, so there
     // is no serial boundary-kernel latency after the interior kernel's tail.
-    plan_post(*p, *x, nullptr, /*halo_only=*/true, JP_INSERT, false);
-    launch_spmv(*a, a->blocks_boundary, a->n_blocks_boundary, true, x->d(), x->n, p->recvbuf.as<double>(), y->k, y->d(), y->n, y->k,
-                alpha, beta, c.comm);
+    const double* halo = capturing ? nullptr : plan_post_p2p(*p, *x);  // peer-memory halo (epochs cannot be replayed from a graph)
+    const bool p2p = halo != nullptr;
+    if (!p2p) {
+      plan_post(*p, *x, nullptr, /*halo_only=*/true, JP_INSERT, false);
+      halo = p->recvbuf.as<double>();
+    }
+    launch_spmv(*a, a->blocks_boundary, a->n_blocks_boundary, true, x->d(), x->n, halo, y->k, y->d(), y->n, y->k, alpha, beta, c.comm);
+    if (p2p) plan_p2p_ack(*p);
     JP_CUDA(cudaEventRecord(p->ev_done, c.comm));
     launch_spmv(*a, a->blocks_interior, a->n_blocks_interior, false, x->d(), x->n, nullptr, 1, y->d(), y->n, y->k, alpha, beta, c.compute);
     JP_CUDA(cudaStreamWaitEvent(c.compute, p->ev_done, 0));
