@@ -157,12 +157,16 @@ struct MultiVector : Object {
   double* d() const { return data.as<double>(); }
 };
 
-// One launch list of the row-block SpMV kernel: rows [row[b], row[b+1]) with nnz starting at nnz0[b].
-struct RowBlocks {
-  int32_t count = 0;
-  DeviceBuffer row;   // int32 [count+1] ... stored as pairs (first row, end row) per block
-  DeviceBuffer nnz0;  // unused for now
+// One row block of the SpMV/SpMM kernels (32 bytes, read as two int4)
+struct alignas(16) BlockDesc {
+  int32_t row0;         // first row
+  int32_t nrows_kind;   // nrows | kind << 16
+  int32_t p0, p1;       // nonzero range [p0, p1)
+  int32_t ucol0;        // SpMM tile path: offset of the block's unique-column list in Csr::ucols (multiple of 4)
+  int32_t ucount;       // number of unique columns of the block
+  int32_t pad0, pad1;
 };
+constexpr size_t kBlockDescBytes = sizeof(BlockDesc);
 
 struct Csr : Object {
   Csr() : Object(Kind::Csr) {}
@@ -172,9 +176,15 @@ struct Csr : Object {
   int32_t threads_per_row = 1;  // chosen from the row-length statistics at create time
   int32_t nnz_cap = 2048;       // nnz staged in shared memory per block
   DeviceBuffer rowptr, colind, vals;  // 0-based; colind/vals padded for 16-byte over-reads
-  // row blocks: int4 {row_begin, row_end, nnz_begin, nnz_end}; interior = no remote column
+  // row blocks (BlockDesc); interior = no remote column
   DeviceBuffer blocks_interior, blocks_boundary, blocks_all;
   int32_t n_blocks_interior = 0, n_blocks_boundary = 0, n_blocks_all = 0;
+  std::vector<BlockDesc> h_blocks_interior, h_blocks_boundary, h_blocks_all;  // host copies (the tile builder patches them)
+  // SpMM tile path (built lazily at the first k > 1 apply): per block the sorted unique columns it references and,
+  // per nonzero, the uint16 position of its column in that list, so the block's X tile can be staged in shared memory
+  int tile_state = 0;        // 0 = not built, 1 = active, -1 = not beneficial for this matrix
+  int32_t tile_umax = 0;     // largest unique-column count of a block
+  DeviceBuffer ucols, lidx;
   // cache of the column-map multivector (A.importMV, src/CSRMatrix.jl:10,772-781); only used when the column
   // map is not [domain prefix | remote tail] and the fused apply path does not apply
   std::unique_ptr<MultiVector> import_mv;

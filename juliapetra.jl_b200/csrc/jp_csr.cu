@@ -24,7 +24,9 @@
 // read from HBM once for all k (the reference re-streams it per vector).
 // No tensor cores: this is not a dense contraction.  No atomics in NO_TRANS: results are deterministic.
 #include <algorithm>
+#include <climits>
 #include <cstdlib>
+#include <thread>
 
 #include "jp_common.h"
 
@@ -37,7 +39,6 @@ constexpr int kMaxRowsPerBlock = 512;   // rows staged per block (row pointers i
 constexpr int kLongRowLen = 64;         // blocks holding a row longer than this reduce warp-per-row
 
 enum BlockKind : int { KIND_DIRECT = 0, KIND_TWOPHASE = 1, KIND_WARPROW = 2, KIND_LONGROW = 3 };
-// block descriptor int4: x = first row, y = nrows | kind << 16, z = nnz begin, w = nnz end
 
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -117,7 +118,8 @@ struct BlockRange {
   int rpo;  // shared index of row r's pointer is rpo + r
 };
 
-__device__ __forceinline__ BlockRange decode_block(const int4 blk) {
+__device__ __forceinline__ BlockRange decode_block(const BlockDesc* __restrict__ blocks, int idx) {
+  const int4 blk = __ldg(reinterpret_cast<const int4*>(blocks + idx));
   BlockRange b;
   b.row0 = blk.x;
   b.nrows = blk.y & 0xffff;
@@ -193,14 +195,14 @@ __device__ void long_row(const int32_t* __restrict__ colind, const double* __res
 
 template <bool HALO, int TMA>
 __global__ void __launch_bounds__(kSpmvThreads)
-spmv_kernel(const int4* __restrict__ blocks, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+spmv_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
             const double* __restrict__ vals, const double* __restrict__ x, const double* __restrict__ halo, int32_t nloc,
             double* __restrict__ y, int32_t cap, double alpha, double beta) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double s_red[kSpmvThreads / 32];
   __shared__ __align__(8) uint64_t s_bar;
   const StageView sv = stage_view(smem_raw, cap);
-  const BlockRange b = decode_block(blocks[blockIdx.x]);
+  const BlockRange b = decode_block(blocks, blockIdx.x);
   const int tid = threadIdx.x;
   if (b.kind == KIND_LONGROW) {
     long_row<HALO>(colind, vals, x, 0, halo, 1, nloc, y, 0, 1, b.row0, b.p0, b.p1, alpha, beta, s_red);
@@ -271,7 +273,7 @@ spmv_kernel(const int4* __restrict__ blocks, const int32_t* __restrict__ rowptr,
 
 template <int KT, bool HALO, int TMA>
 __global__ void __launch_bounds__(kSpmvThreads)
-spmm_kernel(const int4* __restrict__ blocks, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+spmm_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
             const double* __restrict__ vals, const double* __restrict__ x, int64_t ldx, const double* __restrict__ halo,
             int32_t halo_k, int32_t nloc, double* __restrict__ y, int64_t ldy, int32_t k, int32_t cap, int32_t T, double alpha,
             double beta) {
@@ -279,7 +281,7 @@ spmm_kernel(const int4* __restrict__ blocks, const int32_t* __restrict__ rowptr,
   __shared__ double s_red[kSpmvThreads / 32];
   __shared__ __align__(8) uint64_t s_bar;
   const StageView sv = stage_view(smem_raw, cap);
-  const BlockRange b = decode_block(blocks[blockIdx.x]);
+  const BlockRange b = decode_block(blocks, blockIdx.x);
   const int tid = threadIdx.x;
   if (b.kind == KIND_LONGROW) {
     long_row<HALO>(colind, vals, x, ldx, halo, halo_k, nloc, y, ldy, k, b.row0, b.p0, b.p1, alpha, beta, s_red);
@@ -329,6 +331,123 @@ spmm_kernel(const int4* __restrict__ blocks, const int32_t* __restrict__ rowptr,
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// SpMM with the multivector tile staged in shared memory (banded / stencil-like matrices).
+// A k-vector apply gathers nnz*k doubles of X; with X only in L1/L2 that traffic (12 GB for 27-pt 192^3, k = 8) is
+// several times the matrix stream and the L1 that is left beside the staged matrix (~20 KB) cannot hold a block's
+// working set.  At build time every row block gets the sorted list of the UNIQUE columns it references (ucols) and
+// every nonzero the uint16 position of its column in that list (lidx).  The kernel stages vals, lidx, row pointers
+// and ucols with TMA bulk copies, gathers the block's X tile [KT vectors] x [unique columns] ONCE into shared
+// memory (coalesced along the column runs of a banded matrix; a column referenced by 3 neighbouring rows is
+// fetched once, not 3 times), then runs thread-per-row out of shared memory.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kTileThreads = 256;
+
+struct TileStage {
+  double* s_val;    // [cap + 8]
+  double* xs;       // [KT][upad]
+  int32_t* s_rp;    // [kMaxRowsPerBlock + 8]
+  int32_t* s_ucol;  // [upad]
+  uint16_t* s_lidx; // [cap + 16]
+};
+__host__ __device__ inline size_t tile_smem_bytes(int cap, int upad, int KT) {
+  return (size_t)(cap + 8) * 8 + (size_t)KT * upad * 8 + (size_t)(kMaxRowsPerBlock + 8) * 4 + (size_t)upad * 4 + (size_t)(cap + 16) * 2;
+}
+
+template <int KT, bool HALO>
+__global__ void __launch_bounds__(kTileThreads)
+spmm_tile_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                 const double* __restrict__ vals, const uint16_t* __restrict__ lidx, const int32_t* __restrict__ ucols,
+                 const double* __restrict__ x, int64_t ldx, const double* __restrict__ halo, int32_t halo_k, int32_t nloc,
+                 double* __restrict__ y, int64_t ldy, int32_t k, int32_t cap, int32_t upad, double alpha, double beta) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ double s_red[kTileThreads / 32];
+  __shared__ __align__(8) uint64_t s_bar;
+  TileStage t;
+  t.s_val = reinterpret_cast<double*>(smem_raw);
+  t.xs = t.s_val + cap + 8;
+  t.s_rp = reinterpret_cast<int32_t*>(t.xs + (size_t)KT * upad);
+  t.s_ucol = t.s_rp + kMaxRowsPerBlock + 8;
+  t.s_lidx = reinterpret_cast<uint16_t*>(t.s_ucol + upad);
+  const BlockRange b = decode_block(blocks, blockIdx.x);
+  const int4 aux = __ldg(reinterpret_cast<const int4*>(blocks + blockIdx.x) + 1);
+  const int ucol0 = aux.x, U = aux.y;
+  const int tid = threadIdx.x;
+  if (b.kind == KIND_LONGROW) {
+    long_row<HALO>(colind, vals, x, ldx, halo, halo_k, nloc, y, ldy, k, b.row0, b.p0, b.p1, alpha, beta, s_red);
+    return;
+  }
+  // stage: vals, lidx, row pointers, unique columns (four TMA bulk copies)
+  const int ngrp = (b.p1 - b.a0 + 3) >> 2;
+  const int al0 = b.p0 & ~7;                       // 16-byte aligned first staged lidx
+  const int nl8 = (b.p1 - al0 + 7) & ~7;           // lidx staged (multiple of 8)
+  const int ra0 = b.row0 & ~3;
+  const int nrp = (b.row0 + b.nrows + 1 - ra0 + 3) & ~3;
+  const int nu4 = (U + 3) & ~3;
+  if (tid == 0) mbar_init(&s_bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    const uint64_t pol = policy_evict_first();
+    mbar_expect_tx(&s_bar, (unsigned)(ngrp * 32 + nl8 * 2 + nrp * 4 + nu4 * 4));
+    if (ngrp > 0) bulk_g2s(t.s_val, vals + b.a0, (unsigned)ngrp * 32, &s_bar, pol);
+    if (nl8 > 0) bulk_g2s(t.s_lidx, lidx + al0, (unsigned)nl8 * 2, &s_bar, pol);
+    bulk_g2s(t.s_rp, rowptr + ra0, (unsigned)nrp * 4, &s_bar, pol);
+    if (nu4 > 0) bulk_g2s(t.s_ucol, ucols + ucol0, (unsigned)nu4 * 4, &s_bar, pol);
+  }
+  mbar_wait(&s_bar, 0);
+  const int32_t* rp = t.s_rp + b.rpo;
+  // lanes per row: as many as keep every thread busy, at most 4 (warp-uniform, power of two)
+  int T = 1;
+  while (T < 4 && b.nrows * (T << 1) <= kTileThreads) T <<= 1;
+  const int lane_t = tid & (T - 1), group = tid / T, ngroups = kTileThreads / T;
+  for (int v0 = 0; v0 < k; v0 += KT) {
+    // X tile: xs[j][u] = X[ucol[u], v0 + j]
+    for (int u = tid; u < U; u += kTileThreads) {
+      const int c = t.s_ucol[u];
+      if (HALO && c >= nloc) {
+        const double* h = halo + (size_t)(c - nloc) * halo_k + v0;
+#pragma unroll
+        for (int j = 0; j < KT; ++j)
+          if (v0 + j < k) t.xs[(size_t)j * upad + u] = h[j];
+      } else {
+        const double* xc = x + c + (size_t)v0 * ldx;
+#pragma unroll
+        for (int j = 0; j < KT; ++j)
+          if (v0 + j < k) t.xs[(size_t)j * upad + u] = __ldg(xc + (size_t)j * ldx);
+      }
+    }
+    __syncthreads();
+    for (int rbase = 0; rbase < b.nrows; rbase += ngroups) {  // warp-uniform trip count (shuffles below)
+      const int r = rbase + group;
+      const bool valid = r < b.nrows;
+      const int s = valid ? rp[r] : 0, e = valid ? rp[r + 1] : 0;
+      double acc[KT];
+#pragma unroll
+      for (int j = 0; j < KT; ++j) acc[j] = 0.0;
+      for (int i = s + lane_t; i < e; i += T) {
+        const int li = t.s_lidx[i - al0];
+        const double v = t.s_val[i - b.a0];
+#pragma unroll
+        for (int j = 0; j < KT; ++j) acc[j] = __dadd_rn(acc[j], __dmul_rn(v, t.xs[(size_t)j * upad + li]));
+      }
+      for (int o = T >> 1; o > 0; o >>= 1) {
+#pragma unroll
+        for (int j = 0; j < KT; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+      }
+      if (valid && lane_t == 0) {
+#pragma unroll
+        for (int j = 0; j < KT; ++j)
+          if (v0 + j < k) {
+            double* yp = y + b.row0 + r + (size_t)(v0 + j) * ldy;
+            *yp = combine(beta == 0.0 ? 0.0 : *yp, acc[j], alpha, beta);
+          }
+      }
+    }
+    __syncthreads();  // the next vector tile overwrites xs
+  }
+}
+
 // TRANS / CONJ_TRANS (src/CSRMatrix.jl:1147-1160): Y[ind, v] += (alpha * X[row, v]) * val, after Y *= beta.
 // Scatter with fp64 atomics (RED.ADD.F64): the summation order differs from the reference's row sweep, within
 // the 1e-12 contract.  Warp per row, lanes over the row's entries.
@@ -361,7 +480,7 @@ size_t stage_smem_bytes(int cap) { return (size_t)(cap + 8) * 12 + (size_t)(kMax
 
 // cut rows into blocks; cls[r] = 1 when the row touches a remote column
 void build_blocks(const std::vector<int32_t>& rp, const std::vector<uint8_t>& cls, int32_t cap, int32_t max_rows, bool allow_direct,
-                  std::vector<int4>& interior, std::vector<int4>& boundary, std::vector<int4>& all) {
+                  std::vector<BlockDesc>& interior, std::vector<BlockDesc>& boundary, std::vector<BlockDesc>& all) {
   const int32_t n = (int32_t)rp.size() - 1;
   int32_t r = 0;
   while (r < n) {
@@ -382,20 +501,21 @@ void build_blocks(const std::vector<int32_t>& rp, const std::vector<uint8_t>& cl
       if (allow_direct && maxlen <= 32 && (int64_t)maxlen * nrows <= 2 * nnzb + 32) kind = KIND_DIRECT;
       else kind = maxlen > kLongRowLen ? KIND_WARPROW : KIND_TWOPHASE;
     }
-    int4 b;
-    b.x = start;
-    b.y = (r - start) | (kind << 16);
-    b.z = nnz0;
-    b.w = rp[r];
+    BlockDesc b;
+    b.row0 = start;
+    b.nrows_kind = (r - start) | (kind << 16);
+    b.p0 = nnz0;
+    b.p1 = rp[r];
+    b.ucol0 = b.ucount = b.pad0 = b.pad1 = 0;
     (c ? boundary : interior).push_back(b);
     all.push_back(b);
   }
 }
 
-void upload_blocks(const std::vector<int4>& v, DeviceBuffer& buf, int32_t& count) {
+void upload_blocks(const std::vector<BlockDesc>& v, DeviceBuffer& buf, int32_t& count) {
   count = (int32_t)v.size();
-  buf.alloc(v.size() * sizeof(int4) + 16);
-  if (!v.empty()) JP_CUDA(cudaMemcpy(buf.p, v.data(), v.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  if (buf.bytes < v.size() * sizeof(BlockDesc) + 16) buf.alloc(v.size() * sizeof(BlockDesc) + 16);
+  if (!v.empty()) JP_CUDA(cudaMemcpy(buf.p, v.data(), v.size() * sizeof(BlockDesc), cudaMemcpyHostToDevice));
 }
 
 // opt a kernel in to its dynamic shared-memory size once per size (the attribute call is not free)
@@ -408,7 +528,7 @@ void set_smem_attr(K kernel, size_t bytes) {
 }
 
 template <bool HALO, int TMA>
-void launch_spmv_impl(const Csr& A, const int4* b, int32_t n_blocks, size_t smem, const double* x, const double* halo, double* y,
+void launch_spmv_impl(const Csr& A, const BlockDesc* b, int32_t n_blocks, size_t smem, const double* x, const double* halo, double* y,
                       double alpha, double beta, cudaStream_t stream) {
   set_smem_attr(spmv_kernel<HALO, TMA>, smem);
   spmv_kernel<HALO, TMA><<<n_blocks, kSpmvThreads, smem, stream>>>(b, A.rowptr.as<int32_t>(), A.colind.as<int32_t>(), A.vals.as<double>(), x,
@@ -416,7 +536,7 @@ void launch_spmv_impl(const Csr& A, const int4* b, int32_t n_blocks, size_t smem
 }
 
 template <bool HALO, int TMA>
-void launch_spmm_impl(const Csr& A, const int4* b, int32_t n_blocks, size_t smem, const double* x, int64_t ldx, const double* halo,
+void launch_spmm_impl(const Csr& A, const BlockDesc* b, int32_t n_blocks, size_t smem, const double* x, int64_t ldx, const double* halo,
                       int32_t halo_k, double* y, int64_t ldy, int32_t k, double alpha, double beta, cudaStream_t stream) {
   constexpr int KT = 8;
   set_smem_attr(spmm_kernel<KT, HALO, TMA>, smem);
@@ -424,6 +544,96 @@ void launch_spmm_impl(const Csr& A, const int4* b, int32_t n_blocks, size_t smem
                                                                         A.vals.as<double>(), x, ldx, halo, halo_k,
                                                                         HALO ? A.n_local_cols : A.n_cols, y, ldy, k, A.nnz_cap,
                                                                         A.threads_per_row, alpha, beta);
+}
+
+
+// Build the SpMM tile tables (lazily, at the first k > 1 apply): per block the sorted unique columns, per nonzero the
+// position of its column in that list.  Host threads over blocks; one-time cost.
+void build_tiles(Csr& A) {
+  constexpr int KT = 8;
+  const size_t nb = A.h_blocks_all.size();
+  if (A.nnz == 0 || nb == 0 || env_int("JP_SPMM_TILE", 1) == 0) {
+    A.tile_state = -1;
+    return;
+  }
+  std::vector<int32_t> ci((size_t)A.nnz);
+  JP_CUDA(cudaStreamSynchronize(ctx().compute));
+  JP_CUDA(cudaMemcpy(ci.data(), A.colind.p, (size_t)A.nnz * 4, cudaMemcpyDeviceToHost));
+  std::vector<int32_t> ubuf((size_t)A.nnz);       // block b's unique list is built in place at [p0, p0 + ucount)
+  std::vector<uint16_t> lidx((size_t)A.nnz + 64, 0);
+  std::vector<BlockDesc>& all = A.h_blocks_all;
+  const int nthreads = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  auto worker = [&](int tix) {
+    for (size_t bi = tix; bi < nb; bi += nthreads) {
+      BlockDesc& b = all[bi];
+      b.ucount = 0;
+      if ((b.nrows_kind >> 16) == KIND_LONGROW) continue;
+      int32_t* u = ubuf.data() + b.p0;
+      const int32_t n = b.p1 - b.p0;
+      std::copy(ci.begin() + b.p0, ci.begin() + b.p1, u);
+      std::sort(u, u + n);
+      const int32_t uc = (int32_t)(std::unique(u, u + n) - u);
+      b.ucount = uc;
+      for (int32_t i = b.p0; i < b.p1; ++i) lidx[i] = (uint16_t)(std::lower_bound(u, u + uc, ci[i]) - u);
+    }
+  };
+  {
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t) th.emplace_back(worker, t);
+    worker(0);
+    for (auto& t : th) t.join();
+  }
+  int64_t sum_u = 0, sum_nnz = 0, off = 0;
+  int32_t umax = 0;
+  for (BlockDesc& b : all) {
+    b.ucol0 = (int32_t)off;
+    off += (b.ucount + 3) & ~3;
+    umax = std::max(umax, b.ucount);
+    if (b.ucount) {
+      sum_u += b.ucount;
+      sum_nnz += b.p1 - b.p0;
+    }
+  }
+  const int upad = (umax + 3) & ~3;
+  // worth it only when columns are shared between the rows of a block, and the tile has to fit beside the stage
+  if (sum_nnz == 0 || (double)sum_u > 0.7 * (double)sum_nnz || tile_smem_bytes(A.nnz_cap, upad, KT) > 200 * 1024 || off > INT32_MAX - 64) {
+    A.tile_state = -1;
+    return;
+  }
+  std::vector<int32_t> ucols((size_t)off + 64, 0);
+  for (const BlockDesc& b : all) std::copy(ubuf.begin() + b.p0, ubuf.begin() + b.p0 + b.ucount, ucols.begin() + b.ucol0);
+  // the interior / boundary lists are subsequences of the all-list: copy the patched fields over
+  auto patch = [&](std::vector<BlockDesc>& lst) {
+    size_t j = 0;
+    for (BlockDesc& d : lst) {
+      while (all[j].row0 != d.row0) ++j;
+      d.ucol0 = all[j].ucol0;
+      d.ucount = all[j].ucount;
+    }
+  };
+  patch(A.h_blocks_interior);
+  patch(A.h_blocks_boundary);
+  A.ucols.alloc(ucols.size() * 4);
+  A.lidx.alloc(lidx.size() * 2);
+  JP_CUDA(cudaMemcpy(A.ucols.p, ucols.data(), ucols.size() * 4, cudaMemcpyHostToDevice));
+  JP_CUDA(cudaMemcpy(A.lidx.p, lidx.data(), lidx.size() * 2, cudaMemcpyHostToDevice));
+  upload_blocks(A.h_blocks_interior, A.blocks_interior, A.n_blocks_interior);
+  upload_blocks(A.h_blocks_boundary, A.blocks_boundary, A.n_blocks_boundary);
+  upload_blocks(A.h_blocks_all, A.blocks_all, A.n_blocks_all);
+  A.tile_umax = umax;
+  A.tile_state = 1;
+}
+
+template <bool HALO>
+void launch_spmm_tile(const Csr& A, const BlockDesc* b, int32_t n_blocks, const double* x, int64_t ldx, const double* halo, int32_t halo_k,
+                      double* y, int64_t ldy, int32_t k, double alpha, double beta, cudaStream_t stream) {
+  constexpr int KT = 8;
+  const int upad = (A.tile_umax + 3) & ~3;
+  const size_t smem = tile_smem_bytes(A.nnz_cap, upad, KT);
+  set_smem_attr(spmm_tile_kernel<KT, HALO>, smem);
+  spmm_tile_kernel<KT, HALO><<<n_blocks, kTileThreads, smem, stream>>>(b, A.rowptr.as<int32_t>(), A.colind.as<int32_t>(), A.vals.as<double>(),
+                                                                        A.lidx.as<uint16_t>(), A.ucols.as<int32_t>(), x, ldx, halo, halo_k,
+                                                                        HALO ? A.n_local_cols : A.n_cols, y, ldy, k, A.nnz_cap, upad, alpha, beta);
 }
 
 }  // namespace
@@ -438,8 +648,12 @@ void launch_spmv_blocks(const Csr& A, const void* blocks_int4, int32_t n_blocks,
                         const double* halo, int32_t halo_k, double* y, int64_t ldy, int32_t k, double alpha, double beta,
                         cudaStream_t stream) {
   if (n_blocks == 0 || k == 0) return;
+  if (k > 1 && A.tile_state == 0) {
+    // lazily build the SpMM tile tables; the block lists are re-uploaded in place (same buffers, same order)
+    build_tiles(const_cast<Csr&>(A));
+  }
   const size_t smem = stage_smem_bytes(A.nnz_cap);
-  const int4* b = static_cast<const int4*>(blocks_int4);
+  const BlockDesc* b = static_cast<const BlockDesc*>(blocks_int4);
   static const int tma = env_int("JP_SPMV_TMA", 1);  // 0: cp.async staging (kept for A/B measurements)
   if (k == 1) {
     if (use_halo) {
@@ -449,6 +663,9 @@ void launch_spmv_blocks(const Csr& A, const void* blocks_int4, int32_t n_blocks,
       if (tma) launch_spmv_impl<false, 1>(A, b, n_blocks, smem, x, nullptr, y, alpha, beta, stream);
       else launch_spmv_impl<false, 0>(A, b, n_blocks, smem, x, nullptr, y, alpha, beta, stream);
     }
+  } else if (A.tile_state == 1) {
+    if (use_halo) launch_spmm_tile<true>(A, b, n_blocks, x, ldx, halo, halo_k, y, ldy, k, alpha, beta, stream);
+    else launch_spmm_tile<false>(A, b, n_blocks, x, ldx, nullptr, 1, y, ldy, k, alpha, beta, stream);
   } else {
     if (use_halo) {
       if (tma) launch_spmm_impl<true, 1>(A, b, n_blocks, smem, x, ldx, halo, halo_k, y, ldy, k, alpha, beta, stream);
@@ -537,7 +754,7 @@ int32_t jp_csr_create(int32_t n_rows, int32_t n_cols, int32_t n_local_cols, int6
     A->nnz_cap = cap;
     int max_rows = env_int("JP_SPMV_ROWS", kSpmvThreads);
     JP_REQUIRE(max_rows >= 1 && max_rows <= kMaxRowsPerBlock, "JP_SPMV_ROWS must be in [1,512]");
-    std::vector<int4> bi, bb, ba;
+    std::vector<BlockDesc>&bi = A->h_blocks_interior, &bb = A->h_blocks_boundary, &ba = A->h_blocks_all;
     build_blocks(rp, cls, cap, max_rows, env_int("JP_SPMV_DIRECT", 1) != 0, bi, bb, ba);
     upload_blocks(bi, A->blocks_interior, A->n_blocks_interior);
     upload_blocks(bb, A->blocks_boundary, A->n_blocks_boundary);
@@ -548,7 +765,7 @@ int32_t jp_csr_create(int32_t n_rows, int32_t n_cols, int32_t n_local_cols, int6
       for (int c = 0; c <= nchunks; ++c) {
         const int32_t bidx = (int32_t)((int64_t)ba.size() * c / nchunks);
         A->chunk_block.push_back(bidx);
-        A->chunk_row.push_back(bidx < (int32_t)ba.size() ? ba[bidx].x : n_rows);
+        A->chunk_row.push_back(bidx < (int32_t)ba.size() ? ba[bidx].row0 : n_rows);
       }
       for (int c = 0; c < nchunks; ++c) {
         for (int32_t r = A->chunk_row[c]; r < A->chunk_row[c + 1]; ++r) run = std::max(run, rowmax[r]);

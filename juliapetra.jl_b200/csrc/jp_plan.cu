@@ -758,7 +758,7 @@ int32_t jp_apply_host(jp_handle comm, jp_handle A, jp_handle plan, const double*
         uploaded_chunk = want;
       }
       const int32_t b0 = a->chunk_block[ch], b1 = a->chunk_block[ch + 1];
-      launch_spmv_blocks(*a, blocks + (size_t)b0 * 16, b1 - b0, false, x->d(), nx, nullptr, 1, y->d(), ny, k, alpha, beta, comp);
+      launch_spmv_blocks(*a, blocks + (size_t)b0 * kBlockDescBytes, b1 - b0, false, x->d(), nx, nullptr, 1, y->d(), ny, k, alpha, beta, comp);
       JP_CUDA(cudaEventRecord(g_host_events[nch + ch], comp));
       JP_CUDA(cudaStreamWaitEvent(d2h, g_host_events[nch + ch], 0));
       const int32_t r0 = a->chunk_row[ch], r1 = a->chunk_row[ch + 1];
