@@ -250,10 +250,13 @@ def main():
     bytes_rank_est = algorithmic_bytes(n_my, nnz_my, k)
     flush = bytes_rank_est < 1.5 * 126e6
     ms = C.c_double()
+    host_enqueue_ms = None
     if not flush:
         _lib.check(lib.jp_event_record(ev0.value))
+        t_h = time.perf_counter()
         for _ in range(args.steps):
             step()
+        host_enqueue_ms = (time.perf_counter() - t_h) * 1e3 / args.steps  # CPU time to enqueue one step (no sync inside)
         _lib.check(lib.jp_event_record(ev1.value))
         _lib.check(lib.jp_event_elapsed_ms(ev0.value, ev1.value, C.byref(ms)))
         total_ms = ms.value
@@ -295,6 +298,13 @@ def main():
             clocks = sampler.stop()
             clocks_window = "same apply! loop repeated for ~1.5 s right after the timed region (timed region shorter than the sampling period)"
     launches = int(sum_over_ranks(float(cnt1.value - cnt0.value)))
+    # pure CPU cost of enqueueing one step: a short burst into idle streams (well below the launch-queue depth)
+    barrier()
+    t_h = time.perf_counter()
+    for _ in range(64):
+        step()
+    host_burst_ms = (time.perf_counter() - t_h) * 1e3 / 64
+    barrier()
 
     flops_step = 2.0 * nnz * k + (6.0 * n * k if cg else 0.0)  # + dot, norm2, axpy: 2*n*k each
     value = flops_step / (ms_per_step * 1e-3) / 1e9
@@ -343,7 +353,7 @@ def main():
                        "l2": (f"L2 flushed (256 MB memset) between timed iterations, each iteration on its own event pair; {bytes_rank / 1e6:.0f} MB per GPU per apply"
                               if flush else f"inputs larger than L2: {bytes_rank / 1e6:.0f} MB streamed per GPU per apply vs 126 MB L2; no flush needed"),
                        "setup_s": round(setup_s, 1)},
-            "hbm_gbs": bytes_apply / (ms_per_step * 1e-3) / 1e9,
+            "hbm_gbs": bytes_apply / (ms_per_step * 1e-3) / 1e9, "host_enqueue_ms_per_step": host_enqueue_ms, "host_enqueue_burst_ms_per_step": host_burst_ms,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
                          "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0, "bytes_per_launch": bytes_rank,
                          "kernel": "spmv_kernel (one launch per apply at N=1; interior+boundary launches at N>1)"},

@@ -229,7 +229,6 @@ struct Plan : Object {
   DeviceBuffer wait_table;      // per source: {const uint64* ready flag (mine)}, {uint64* ack flag (in the source's arena)}
   int32_t n_send_blocks = 0, n_sources = 0;
   DeviceBuffer p2p_tickets;     // uint32 counters
-  uint64_t epoch = 0;
   ~Plan() override;
 };
 
@@ -257,6 +256,7 @@ void plan_post(Plan& p, const MultiVector& src, MultiVector* tgt, bool halo_only
 void plan_unpack(Plan& p, MultiVector& tgt, cudaStream_t stream);
 const double* plan_post_p2p(Plan& p, const MultiVector& src);
 void plan_p2p_ack(Plan& p);
+bool p2p_setup_public(Plan& p, int32_t k);
 void comm_allreduce_device(Comm& c, double* buf, int64_t n, cudaStream_t stream);
 void release_host_path_cache();
 void release_reduce_workspace();

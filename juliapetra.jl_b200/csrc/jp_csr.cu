@@ -97,6 +97,18 @@ __device__ __forceinline__ double combine(double yold, double sum, double alpha,
   return beta == 0.0 ? s : __dadd_rn(__dmul_rn(yold, beta), s);
 }
 
+// left-to-right sum of s_val[s..e) (the reference's order); four shared loads are issued ahead of the adds
+__device__ __forceinline__ double row_sum_sequential(const double* s_val, int s, int e) {
+  double sum = 0.0;
+  int i = s;
+  for (; i + 4 <= e; i += 4) {
+    const double a0 = s_val[i], a1 = s_val[i + 1], a2 = s_val[i + 2], a3 = s_val[i + 3];
+    sum = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(sum, a0), a1), a2), a3);
+  }
+  for (; i < e; ++i) sum = __dadd_rn(sum, s_val[i]);
+  return sum;
+}
+
 // shared-memory stage: vals [cap+8] | colind [cap+8] | row pointers [kMaxRowsPerBlock+8]
 struct StageView {
   double* s_val;
@@ -226,23 +238,33 @@ spmv_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ ro
     }
     return;
   }
-  // phase A: products, thread-per-nonzero (every gather of the block is independent of row structure)
+  // phase A: products, thread-per-nonzero (every gather of the block is independent of row structure);
+  // 8 nonzeros per thread per pass so 8 gathers are in flight before the first product is needed
   const int s0 = b.p0 - b.a0, s1 = b.p1 - b.a0;
-#pragma unroll 4
-  for (int i = s0 + tid; i < s1; i += kSpmvThreads) {
-    const int c = sv.s_col[i];
-    const double xv = (HALO && c >= nloc) ? halo[c - nloc] : __ldg(x + c);
-    sv.s_val[i] = __dmul_rn(sv.s_val[i], xv);
+  for (int base = s0 + tid; base < s1; base += 8 * kSpmvThreads) {
+    int c[8];
+    double xv[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int i = base + q * kSpmvThreads;
+      c[q] = i < s1 ? sv.s_col[i] : -1;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      xv[q] = c[q] < 0 ? 0.0 : ((HALO && c[q] >= nloc) ? halo[c[q] - nloc] : __ldg(x + c[q]));
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int i = base + q * kSpmvThreads;
+      if (i < s1) sv.s_val[i] = __dmul_rn(sv.s_val[i], xv[q]);
+    }
   }
   __syncthreads();
   // phase B: row sums
   if (b.kind == KIND_TWOPHASE) {
     for (int r = tid; r < b.nrows; r += kSpmvThreads) {
       const int s = rp[r] - b.a0, e = rp[r + 1] - b.a0;
-      double sum = 0.0;
-      for (int i = s; i < e; ++i) sum = __dadd_rn(sum, sv.s_val[i]);
       double* yp = y + b.row0 + r;
-      *yp = combine(beta == 0.0 ? 0.0 : *yp, sum, alpha, beta);
+      *yp = combine(beta == 0.0 ? 0.0 : *yp, row_sum_sequential(sv.s_val, s, e), alpha, beta);
     }
   } else {
     // WARPROW: the block holds at least one long row.  Short rows still go thread-per-row (sequential sum, the
@@ -250,10 +272,8 @@ spmv_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ ro
     for (int r = tid; r < b.nrows; r += kSpmvThreads) {
       const int s = rp[r] - b.a0, e = rp[r + 1] - b.a0;
       if (e - s <= kLongRowLen) {
-        double sum = 0.0;
-        for (int i = s; i < e; ++i) sum = __dadd_rn(sum, sv.s_val[i]);
         double* yp = y + b.row0 + r;
-        *yp = combine(beta == 0.0 ? 0.0 : *yp, sum, alpha, beta);
+        *yp = combine(beta == 0.0 ? 0.0 : *yp, row_sum_sequential(sv.s_val, s, e), alpha, beta);
       }
     }
     const int lane = tid & 31, warp = tid >> 5;
@@ -293,6 +313,8 @@ spmm_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ ro
   const int Tb = b.kind == KIND_WARPROW ? 32 : T;
   const int lane_t = tid & (Tb - 1), group = tid / Tb, ngroups = kSpmvThreads / Tb;
   for (int v0 = 0; v0 < k; v0 += KT) {
+    const int kt = k - v0 < KT ? k - v0 : KT;  // warp-uniform
+    const double* xt = x + (size_t)v0 * ldx;
     for (int rbase = 0; rbase < b.nrows; rbase += ngroups) {  // warp-uniform trip count (shuffles below)
       const int r = rbase + group;
       const bool valid = r < b.nrows;
@@ -300,19 +322,35 @@ spmm_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ ro
       double acc[KT];
 #pragma unroll
       for (int j = 0; j < KT; ++j) acc[j] = 0.0;
-      for (int i = s + lane_t; i < e; i += Tb) {
-        const int c = sv.s_col[i];
-        const double v = sv.s_val[i];
-        if (HALO && c >= nloc) {
-          const double* h = halo + (size_t)(c - nloc) * halo_k + v0;
+      if (kt == KT) {
+        for (int i = s + lane_t; i < e; i += Tb) {
+          const int c = sv.s_col[i];
+          const double v = sv.s_val[i];
+          if (HALO && c >= nloc) {
+            const double* h = halo + (size_t)(c - nloc) * halo_k + v0;
 #pragma unroll
-          for (int j = 0; j < KT; ++j)
-            if (v0 + j < k) acc[j] = __dadd_rn(acc[j], __dmul_rn(v, h[j]));
-        } else {
-          const double* xc = x + c + (size_t)v0 * ldx;
+            for (int j = 0; j < KT; ++j) acc[j] = fma(v, h[j], acc[j]);
+          } else {
+            const double* xc = xt + c;
 #pragma unroll
-          for (int j = 0; j < KT; ++j)
-            if (v0 + j < k) acc[j] = __dadd_rn(acc[j], __dmul_rn(v, __ldg(xc + (size_t)j * ldx)));
+            for (int j = 0; j < KT; ++j) acc[j] = fma(v, __ldg(xc + (size_t)j * ldx), acc[j]);
+          }
+        }
+      } else {
+        for (int i = s + lane_t; i < e; i += Tb) {
+          const int c = sv.s_col[i];
+          const double v = sv.s_val[i];
+          if (HALO && c >= nloc) {
+            const double* h = halo + (size_t)(c - nloc) * halo_k + v0;
+#pragma unroll
+            for (int j = 0; j < KT; ++j)
+              if (j < kt) acc[j] = fma(v, h[j], acc[j]);
+          } else {
+            const double* xc = xt + c;
+#pragma unroll
+            for (int j = 0; j < KT; ++j)
+              if (j < kt) acc[j] = fma(v, __ldg(xc + (size_t)j * ldx), acc[j]);
+          }
         }
       }
       for (int o = Tb >> 1; o > 0; o >>= 1) {
@@ -322,7 +360,7 @@ spmm_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ ro
       if (valid && lane_t == 0) {
 #pragma unroll
         for (int j = 0; j < KT; ++j)
-          if (v0 + j < k) {
+          if (j < kt) {
             double* yp = y + b.row0 + r + (size_t)(v0 + j) * ldy;
             *yp = combine(beta == 0.0 ? 0.0 : *yp, acc[j], alpha, beta);
           }
@@ -330,7 +368,6 @@ spmm_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ ro
     }
   }
 }
-
 
 // ---------------------------------------------------------------------------------------------------------------
 // SpMM with the multivector tile staged in shared memory (banded / stencil-like matrices).
@@ -429,7 +466,7 @@ spmm_tile_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict
         const int li = t.s_lidx[i - al0];
         const double v = t.s_val[i - b.a0];
 #pragma unroll
-        for (int j = 0; j < KT; ++j) acc[j] = __dadd_rn(acc[j], __dmul_rn(v, t.xs[(size_t)j * upad + li]));
+        for (int j = 0; j < KT; ++j) acc[j] = fma(v, t.xs[(size_t)j * upad + li], acc[j]);
       }
       for (int o = T >> 1; o > 0; o >>= 1) {
 #pragma unroll

@@ -126,7 +126,7 @@ void exchange(Plan& p, int32_t k, bool reverse, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------------------------
 struct P2PSend {
   int32_t start, count;        // slice of the export list (elements)
-  double* dst[2];              // where it lands in the receiver's recv buffer 0 / 1 (peer or local pointer)
+  double* dst;                 // where it lands in the receiver's halo buffer (peer or local pointer)
   uint64_t* ready_flag;        // receiver's ready[me]
   const uint64_t* ack_flag;    // my ack[receiver]
 };
@@ -147,15 +147,20 @@ __device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
 }
 
-// fused pack + send: dst[(i - start)*k + j] = src[lid[i] + j*ld] for every export entry i, into the receivers' buffers
+// fused pack + send: dst[(i - start)*k + j] = src[lid[i] + j*ld] for every export entry i, into the receivers' buffers.
+// The epoch lives in device memory (this kernel advances it), so the whole apply sequence is a static CUDA graph.
 __global__ void __launch_bounds__(kThreads) pack_p2p_kernel(const double* __restrict__ src, int64_t ld, const int32_t* __restrict__ lids,
                                                               int32_t n, int32_t k, const P2PSend* __restrict__ table, int32_t n_blocks,
-                                                              uint64_t epoch, unsigned int* __restrict__ ticket) {
-  const int parity = (int)(epoch & 1);
-  // back-pressure: the buffer of this parity was last used at epoch-2; its reader must have acknowledged it
-  if (threadIdx.x < n_blocks && epoch > 2) {
+                                                              uint64_t* __restrict__ epoch_dev, unsigned int* __restrict__ ticket) {
+  __shared__ uint64_t s_epoch;
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile uint64_t*>(epoch_dev) + 1;
+  __syncthreads();
+  const uint64_t epoch = s_epoch;
+  // back-pressure: the receiver must have consumed the previous halo before its buffer is overwritten
+  if (threadIdx.x < n_blocks && epoch > 1) {
     long long spins = 0;
-    while (ld_acquire_sys(table[threadIdx.x].ack_flag) + 2 < epoch && ++spins < kSpinLimit) {
+    while (ld_acquire_sys(table[threadIdx.x].ack_flag) + 1 < epoch && ++spins < kSpinLimit) {
     }
   }
   __syncthreads();
@@ -165,22 +170,25 @@ __global__ void __launch_bounds__(kThreads) pack_p2p_kernel(const double* __rest
     const int32_t j = (int32_t)(t / n), i = (int32_t)(t - (int64_t)j * n);
     int b = 0;
     while (b + 1 < n_blocks && i >= table[b].start + table[b].count) ++b;
-    table[b].dst[parity][(size_t)(i - table[b].start) * k + j] = __ldg(src + __ldg(lids + i) + (size_t)j * ld);
+    table[b].dst[(size_t)(i - table[b].start) * k + j] = __ldg(src + __ldg(lids + i) + (size_t)j * ld);
   }
   __threadfence_system();
   __syncthreads();
-  __shared__ bool is_last;
   if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
   __syncthreads();
   if (is_last) {
     __threadfence_system();
+    if (threadIdx.x == 0) {
+      *reinterpret_cast<volatile uint64_t*>(epoch_dev) = epoch;
+      *ticket = 0;
+    }
     if (threadIdx.x < n_blocks) st_release_sys(table[threadIdx.x].ready_flag, epoch);
-    if (threadIdx.x == 0) *ticket = 0;
   }
 }
 
 // one warp: wait until every source has published this epoch's halo
-__global__ void halo_wait_kernel(const P2PSource* __restrict__ sources, int32_t n_sources, uint64_t epoch) {
+__global__ void halo_wait_kernel(const P2PSource* __restrict__ sources, int32_t n_sources, const uint64_t* __restrict__ epoch_dev) {
+  const uint64_t epoch = *reinterpret_cast<const volatile uint64_t*>(epoch_dev);
   if ((int)threadIdx.x < n_sources) {
     long long spins = 0;
     while (ld_acquire_sys(sources[threadIdx.x].ready_flag) < epoch && ++spins < kSpinLimit) {
@@ -189,7 +197,8 @@ __global__ void halo_wait_kernel(const P2PSource* __restrict__ sources, int32_t 
 }
 
 // one warp: tell every source that this epoch's halo has been consumed
-__global__ void halo_ack_kernel(const P2PSource* __restrict__ sources, int32_t n_sources, uint64_t epoch) {
+__global__ void halo_ack_kernel(const P2PSource* __restrict__ sources, int32_t n_sources, const uint64_t* __restrict__ epoch_dev) {
+  const uint64_t epoch = *reinterpret_cast<const volatile uint64_t*>(epoch_dev);
   if ((int)threadIdx.x < n_sources) st_release_sys(sources[threadIdx.x].ack_flag, epoch);
 }
 
@@ -223,11 +232,10 @@ bool p2p_setup(Plan& p, int32_t k) {
     if (p.peer_arena[q] && q != me) cudaIpcCloseMemHandle(p.peer_arena[q]);
   p.peer_arena.assign(P, nullptr);
   p.arena_buf_bytes = (((size_t)std::max(p.n_remote, 1) * k * 8) + 255) & ~(size_t)255;
-  p.arena.alloc(kArenaFlagBytes + 2 * p.arena_buf_bytes);
-  JP_CUDA(cudaMemset(p.arena.p, 0, kArenaFlagBytes + 2 * p.arena_buf_bytes));
-  p.p2p_tickets.alloc(64);
+  p.arena.alloc(kArenaFlagBytes + p.arena_buf_bytes);
+  JP_CUDA(cudaMemset(p.arena.p, 0, kArenaFlagBytes + p.arena_buf_bytes));
+  p.p2p_tickets.alloc(64);  // [0] ticket of the pack kernel (uint32), [8..16) the epoch (uint64)
   JP_CUDA(cudaMemset(p.p2p_tickets.p, 0, 64));
-  p.epoch = 0;
   // what every rank publishes: IPC handle, buffer size, and for each source rank the element offset of its data
   struct Info {
     cudaIpcMemHandle_t handle;
@@ -288,8 +296,7 @@ bool p2p_setup(Plan& p, int32_t k) {
     P2PSend s;
     s.start = (int32_t)p.starts_to[i];
     s.count = (int32_t)p.lengths_to[i];
-    s.dst[0] = (double*)(base + kArenaFlagBytes) + (size_t)off * k;
-    s.dst[1] = (double*)(base + kArenaFlagBytes + all[q].buf_bytes) + (size_t)off * k;
+    s.dst = (double*)(base + kArenaFlagBytes) + (size_t)off * k;
     s.ready_flag = (uint64_t*)base + me;
     s.ack_flag = (const uint64_t*)((char*)p.arena.p + 2048) + q;
     sends.push_back(s);
@@ -375,6 +382,8 @@ void plan_unpack(Plan& p, MultiVector& tgt, cudaStream_t stream) {
   JP_LAUNCH_CHECK();
 }
 
+bool p2p_setup_public(Plan& p, int32_t k) { return p2p_setup(p, k); }
+
 Plan::~Plan() {
   if (ev_done) cudaEventDestroy(ev_done);
   const int me = comm ? comm->rank0 : -1;
@@ -390,26 +399,26 @@ const double* plan_post_p2p(Plan& p, const MultiVector& src) {
   const int32_t k = src.k;
   if (p.p2p_state == 0 || (p.p2p_state == 1 && p.p2p_k != k)) p.p2p_state = p2p_setup(p, k) ? 1 : -1;
   if (p.p2p_state != 1) return nullptr;
-  p.epoch += 1;
+  uint64_t* epoch_dev = reinterpret_cast<uint64_t*>(static_cast<char*>(p.p2p_tickets.p) + 8);
   JP_CUDA(cudaEventRecord(x.ev_x_ready, x.compute));
   JP_CUDA(cudaStreamWaitEvent(x.comm, x.ev_x_ready, 0));
-  if (p.n_export > 0 && p.n_send_blocks > 0) {
-    pack_p2p_kernel<<<grid_for((int64_t)p.n_export * k), kThreads, 0, x.comm>>>(src.d(), src.n, p.export_lids.as<int32_t>(), p.n_export, k,
-                                                                               p.send_table.as<P2PSend>(), p.n_send_blocks, p.epoch,
-                                                                               p.p2p_tickets.as<unsigned int>());
-    JP_LAUNCH_CHECK();
-  }
+  // always launched: it also advances the epoch
+  pack_p2p_kernel<<<grid_for((int64_t)p.n_export * k), kThreads, 0, x.comm>>>(src.d(), src.n, p.export_lids.as<int32_t>(), p.n_export, k,
+                                                                             p.send_table.as<P2PSend>(), p.n_send_blocks, epoch_dev,
+                                                                             p.p2p_tickets.as<unsigned int>());
+  JP_LAUNCH_CHECK();
   if (p.n_sources > 0) {
-    halo_wait_kernel<<<1, 32, 0, x.comm>>>(p.wait_table.as<P2PSource>(), p.n_sources, p.epoch);
+    halo_wait_kernel<<<1, 32, 0, x.comm>>>(p.wait_table.as<P2PSource>(), p.n_sources, epoch_dev);
     JP_LAUNCH_CHECK();
   }
-  return reinterpret_cast<const double*>((const char*)p.arena.p + kArenaFlagBytes + (p.epoch & 1) * p.arena_buf_bytes);
+  return reinterpret_cast<const double*>((const char*)p.arena.p + kArenaFlagBytes);
 }
 
 void plan_p2p_ack(Plan& p) {
   Context& x = ctx();
   if (p.n_sources > 0) {
-    halo_ack_kernel<<<1, 32, 0, x.comm>>>(p.wait_table.as<P2PSource>(), p.n_sources, p.epoch);
+    const uint64_t* epoch_dev = reinterpret_cast<const uint64_t*>(static_cast<char*>(p.p2p_tickets.p) + 8);
+    halo_ack_kernel<<<1, 32, 0, x.comm>>>(p.wait_table.as<P2PSource>(), p.n_sources, epoch_dev);
     JP_LAUNCH_CHECK();
   }
 }
@@ -479,7 +488,7 @@ void apply_no_trans(Csr* a, Plan* p, MultiVector* y, MultiVector* x, double alph
     // comm stream (high priority): pack -> exchange -> BOUNDARY rows; compute stream: INTERIOR rows, concurrently.
     // The two launches write disjoint rows of Y; the compute stream joins on the comm stream at the end, so there
     // is no serial boundary-kernel latency after the interior kernel's tail.
-    const double* halo = capturing ? nullptr : plan_post_p2p(*p, *x);  // peer-memory halo (epochs cannot be replayed from a graph)
+    const double* halo = plan_post_p2p(*p, *x);  // peer-memory halo; nullptr -> NCCL send/recv
     const bool p2p = halo != nullptr;
     if (!p2p) {
       plan_post(*p, *x, nullptr, /*halo_only=*/true, JP_INSERT, false);
@@ -492,22 +501,29 @@ void apply_no_trans(Csr* a, Plan* p, MultiVector* y, MultiVector* x, double alph
     JP_CUDA(cudaStreamWaitEvent(c.compute, p->ev_done, 0));
     (void)capturing;
   };
-  static const bool use_graph = []() {
-    const char* v = std::getenv("JP_APPLY_GRAPH");  // opt-in: replay the sequence as one CUDA graph
-    return v && *v == '1';
+  // Graph replay pays off when the sequence is kernels only (peer-memory halo); with NCCL send/recv inside, replay
+  // measured slower than eager enqueue.  JP_APPLY_GRAPH=0/1 forces it off/on.
+  static const int graph_env = []() {
+    const char* v = std::getenv("JP_APPLY_GRAPH");
+    return (v && *v) ? (*v == '1' ? 1 : 0) : -1;
   }();
+  if (p->p2p_state == 0 && graph_env != 0) {  // decide the halo transport (collective) before choosing the replay mode
+    JP_CUDA(cudaStreamSynchronize(c.compute));
+    p->p2p_state = p2p_setup_public(*p, x->k) ? 1 : -1;
+  }
+  const bool use_graph = graph_env == 1 || (graph_env == -1 && p->p2p_state == 1 && p->p2p_k == x->k);
   if (!use_graph) {
     body(false);
     return;
   }
   char key[256];
-  std::snprintf(key, sizeof key, "%p|%p|%p|%p|%p|%d|%a|%a", (void*)x->d(), (void*)y->d(), (void*)p, p->sendbuf.p, p->recvbuf.p, (int)x->k,
-                alpha, beta);
+  std::snprintf(key, sizeof key, "%p|%p|%p|%p|%p|%p|%d|%a|%a", (void*)x->d(), (void*)y->d(), (void*)p, p->sendbuf.p, p->recvbuf.p,
+                p->arena.p, (int)x->k, alpha, beta);
   auto it = a->graphs.find(key);
   if (it != a->graphs.end()) {
     if (it->second != nullptr) {
       JP_CUDA(cudaGraphLaunch(it->second, c.compute));
-      count_launch(3 + (p->n_export > 0 ? 1 : 0));
+      count_launch(p->p2p_state == 1 ? 3 + (p->n_sources > 0 ? 2 : 0) : 3 + (p->n_export > 0 ? 1 : 0));
       return;
     }
     // second call with this key: everything lazy (shared-memory attributes, NCCL connections) was set up by the
