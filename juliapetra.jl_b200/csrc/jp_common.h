@@ -254,6 +254,9 @@ void launch_scale_fill(double* y, int64_t n, double beta, cudaStream_t stream); 
 void plan_ensure_buffers(Plan& p, int32_t k);
 void plan_post(Plan& p, const MultiVector& src, MultiVector* tgt, bool halo_only, int32_t combine_mode, bool reverse);
 void plan_unpack(Plan& p, MultiVector& tgt, cudaStream_t stream);
+struct FusedHalo;
+void launch_spmv_fused(const Csr& A, const FusedHalo& h, const double* x, const double* halo, double* y, double alpha, double beta,
+                       cudaStream_t stream);
 const double* plan_post_p2p(Plan& p, const MultiVector& src);
 void plan_p2p_ack(Plan& p);
 bool p2p_setup_public(Plan& p, int32_t k);

@@ -29,6 +29,7 @@
 #include <thread>
 
 #include "jp_common.h"
+#include "jp_p2p.cuh"
 
 namespace jp {
 
@@ -205,22 +206,18 @@ __device__ void long_row(const int32_t* __restrict__ colind, const double* __res
   }
 }
 
+// one row block of y = beta*y + alpha*A*x (k = 1); called by every thread of the CTA
 template <bool HALO, int TMA>
-__global__ void __launch_bounds__(kSpmvThreads)
-spmv_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
-            const double* __restrict__ vals, const double* __restrict__ x, const double* __restrict__ halo, int32_t nloc,
-            double* __restrict__ y, int32_t cap, double alpha, double beta) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ double s_red[kSpmvThreads / 32];
-  __shared__ __align__(8) uint64_t s_bar;
-  const StageView sv = stage_view(smem_raw, cap);
-  const BlockRange b = decode_block(blocks, blockIdx.x);
+__device__ __forceinline__ void spmv_block(const BlockRange& b, const StageView& sv, uint64_t* s_bar_p, double* s_red,
+                                           const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                                           const double* __restrict__ vals, const double* __restrict__ x,
+                                           const double* __restrict__ halo, int32_t nloc, double* __restrict__ y, double alpha, double beta) {
   const int tid = threadIdx.x;
   if (b.kind == KIND_LONGROW) {
     long_row<HALO>(colind, vals, x, 0, halo, 1, nloc, y, 0, 1, b.row0, b.p0, b.p1, alpha, beta, s_red);
     return;
   }
-  stage_block<TMA>(sv, &s_bar, rowptr, colind, vals, b);
+  stage_block<TMA>(sv, s_bar_p, rowptr, colind, vals, b);
   const int32_t* rp = sv.s_rp + b.rpo;  // rp[r] is a global nonzero index; shared index = rp[r] - a0
   if (b.kind == KIND_DIRECT) {
     // thread-per-row straight from the stage; lanes = consecutive rows
@@ -287,6 +284,111 @@ spmv_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ ro
         double* yp = y + b.row0 + r;
         *yp = combine(beta == 0.0 ? 0.0 : *yp, sum, alpha, beta);
       }
+    }
+  }
+}
+
+template <bool HALO, int TMA>
+__global__ void __launch_bounds__(kSpmvThreads)
+spmv_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+            const double* __restrict__ vals, const double* __restrict__ x, const double* __restrict__ halo, int32_t nloc,
+            double* __restrict__ y, int32_t cap, double alpha, double beta) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ double s_red[kSpmvThreads / 32];
+  __shared__ __align__(8) uint64_t s_bar;
+  const StageView sv = stage_view(smem_raw, cap);
+  const BlockRange b = decode_block(blocks, blockIdx.x);
+  spmv_block<HALO, TMA>(b, sv, &s_bar, s_red, rowptr, colind, vals, x, halo, nloc, y, alpha, beta);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// apply! with the halo exchange INSIDE the SpMV kernel (k = 1, peer-memory halo): one launch per apply, no stream
+// events, no NCCL call.  The grid is [pack CTAs | interior row blocks | boundary row blocks]:
+//   pack CTAs      gather the exported rows of x and store them straight into the neighbours' halo buffers over
+//                  NVLink (IPC-mapped peer pointers), then publish ready = epoch with a system-scope release;
+//   interior CTAs  the ordinary row-block SpMV on local columns (they are the bulk of the grid and hide the exchange);
+//   boundary CTAs  come last in the grid: they acquire the neighbours' ready flags (set ~30 us earlier by the peers'
+//                  pack CTAs, which never wait on this GPU's current kernel), run the row-block SpMV on x + halo, and
+//                  the last one publishes ack = epoch so the senders may overwrite the halo buffer next time.
+// CTAs are dispatched in index order, so pack CTAs run first and a waiting boundary CTA never holds a slot that a
+// pack or interior CTA still needs.
+// ---------------------------------------------------------------------------------------------------------------
+struct FusedSpmvArgs {
+  const BlockDesc* interior;
+  const BlockDesc* boundary;
+  int32_t n_pack, n_interior, n_boundary;
+  const int32_t* rowptr;
+  const int32_t* colind;
+  const double* vals;
+  const double* x;
+  const double* halo;
+  int32_t nloc;
+  double* y;
+  int32_t cap;
+  double alpha, beta;
+  FusedHalo h;
+};
+
+__global__ void __launch_bounds__(kSpmvThreads) spmv_fused_halo_kernel(const FusedSpmvArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ double s_red[kSpmvThreads / 32];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ bool s_last;
+  const int tid = threadIdx.x;
+  const int bid = blockIdx.x;
+  const uint64_t epoch = *reinterpret_cast<const volatile uint64_t*>(a.h.epoch_dev) + 1;  // constant during this kernel
+  if (bid < a.n_pack) {
+    // ---- pack + send ----
+    if (tid < a.h.n_sends && epoch > 1) {  // back-pressure: the receiver consumed the previous halo
+      long long spins = 0;
+      while (ld_acquire_sys(a.h.sends[tid].ack_flag) + 1 < epoch && ++spins < kSpinLimit) {
+      }
+    }
+    __syncthreads();
+    const int64_t stride = (int64_t)a.n_pack * kSpmvThreads;
+    for (int64_t i = (int64_t)bid * kSpmvThreads + tid; i < a.h.n_export; i += stride) {
+      int sb = 0;
+      while (sb + 1 < a.h.n_sends && i >= a.h.sends[sb].start + a.h.sends[sb].count) ++sb;
+      a.h.sends[sb].dst[i - a.h.sends[sb].start] = __ldg(a.x + __ldg(a.h.lids + i));
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(a.h.tickets + 0, 1u) == (unsigned)a.n_pack - 1);
+    __syncthreads();
+    if (s_last) {
+      __threadfence_system();
+      if (tid < a.h.n_sends) st_release_sys(a.h.sends[tid].ready_flag, epoch);
+    }
+  } else if (bid < a.n_pack + a.n_interior) {
+    const StageView sv = stage_view(smem_raw, a.cap);
+    const BlockRange b = decode_block(a.interior, bid - a.n_pack);
+    spmv_block<false, 1>(b, sv, &s_bar, s_red, a.rowptr, a.colind, a.vals, a.x, nullptr, a.nloc, a.y, a.alpha, a.beta);
+  } else {
+    // ---- boundary rows: wait for the neighbours' halos first ----
+    if (tid < a.h.n_sources) {
+      long long spins = 0;
+      while (ld_acquire_sys(a.h.sources[tid].ready_flag) < epoch && ++spins < kSpinLimit) {
+      }
+    }
+    __syncthreads();
+    const StageView sv = stage_view(smem_raw, a.cap);
+    const BlockRange b = decode_block(a.boundary, bid - a.n_pack - a.n_interior);
+    spmv_block<true, 1>(b, sv, &s_bar, s_red, a.rowptr, a.colind, a.vals, a.x, a.halo, a.nloc, a.y, a.alpha, a.beta);
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(a.h.tickets + 1, 1u) == (unsigned)a.n_boundary - 1);
+    __syncthreads();
+    if (s_last && tid < a.h.n_sources) st_release_sys(a.h.sources[tid].ack_flag, epoch);
+  }
+  // the last CTA of the whole grid closes the epoch and re-arms the tickets
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(a.h.tickets + 2, 1u) == gridDim.x - 1) {
+      a.h.tickets[0] = 0;
+      a.h.tickets[1] = 0;
+      a.h.tickets[2] = 0;
+      *reinterpret_cast<volatile uint64_t*>(a.h.epoch_dev) = epoch;
+      __threadfence();
     }
   }
 }
@@ -674,6 +776,32 @@ void launch_spmm_tile(const Csr& A, const BlockDesc* b, int32_t n_blocks, const 
 }
 
 }  // namespace
+
+void launch_spmv_fused(const Csr& A, const FusedHalo& h, const double* x, const double* halo, double* y, double alpha, double beta,
+                       cudaStream_t stream) {
+  FusedSpmvArgs a;
+  a.interior = A.blocks_interior.as<BlockDesc>();
+  a.boundary = A.blocks_boundary.as<BlockDesc>();
+  a.n_interior = A.n_blocks_interior;
+  a.n_boundary = A.n_blocks_boundary;
+  a.n_pack = std::max(1, std::min(64, (h.n_export + 1023) / 1024));
+  a.rowptr = A.rowptr.as<int32_t>();
+  a.colind = A.colind.as<int32_t>();
+  a.vals = A.vals.as<double>();
+  a.x = x;
+  a.halo = halo;
+  a.nloc = A.n_local_cols;
+  a.y = y;
+  a.cap = A.nnz_cap;
+  a.alpha = alpha;
+  a.beta = beta;
+  a.h = h;
+  const size_t smem = stage_smem_bytes(A.nnz_cap);
+  set_smem_attr(spmv_fused_halo_kernel, smem);
+  const int grid = a.n_pack + a.n_interior + a.n_boundary;
+  spmv_fused_halo_kernel<<<grid, kSpmvThreads, smem, stream>>>(a);
+  JP_LAUNCH_CHECK();
+}
 
 void launch_spmv(const Csr& A, const DeviceBuffer& blocks, int32_t n_blocks, bool use_halo, const double* x, int64_t ldx,
                  const double* halo, int32_t halo_k, double* y, int64_t ldy, int32_t k, double alpha, double beta,

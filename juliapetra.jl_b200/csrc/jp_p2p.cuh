@@ -1,0 +1,42 @@
+// jp_p2p.cuh -- peer-to-peer halo protocol shared by jp_plan.cu (setup, two-stream path) and jp_csr.cu (fused kernel)
+#pragma once
+#include <cstdint>
+
+namespace jp {
+
+struct P2PSend {
+  int32_t start, count;        // slice of the export list (elements)
+  double* dst;                 // where it lands in the receiver's halo buffer (peer or local pointer)
+  uint64_t* ready_flag;        // receiver's ready[me]
+  const uint64_t* ack_flag;    // my ack[receiver]
+};
+struct P2PSource {
+  const uint64_t* ready_flag;  // my ready[source]
+  uint64_t* ack_flag;          // source's ack[me]
+};
+
+constexpr int kArenaFlagBytes = 4096;        // ready flags at [0, 2048), ack flags at [2048, 4096): 256 ranks max
+constexpr long long kSpinLimit = 1ll << 23;  // a few seconds; a peer that never shows up must not hang the GPU
+
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+
+// everything the fused apply kernel needs besides the SpMV arguments
+struct FusedHalo {
+  const int32_t* lids;      // export LIDs in send order
+  int32_t n_export;
+  const P2PSend* sends;
+  int32_t n_sends;
+  const P2PSource* sources;
+  int32_t n_sources;
+  uint64_t* epoch_dev;      // completed epochs; this apply is epoch *epoch_dev + 1
+  unsigned int* tickets;    // [0] pack blocks done, [1] boundary blocks done, [2] all blocks done
+};
+
+}  // namespace jp

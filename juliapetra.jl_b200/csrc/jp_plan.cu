@@ -20,6 +20,7 @@
 #include <cstdlib>
 
 #include "jp_common.h"
+#include "jp_p2p.cuh"
 
 namespace jp {
 
@@ -124,29 +125,6 @@ void exchange(Plan& p, int32_t k, bool reverse, cudaStream_t st) {
 // boundary-row kernel.  Buffers are double-buffered by epoch parity and guarded by an ack flag, so a sender can
 // never overwrite a halo that is still being read.
 // ---------------------------------------------------------------------------------------------------------------
-struct P2PSend {
-  int32_t start, count;        // slice of the export list (elements)
-  double* dst;                 // where it lands in the receiver's halo buffer (peer or local pointer)
-  uint64_t* ready_flag;        // receiver's ready[me]
-  const uint64_t* ack_flag;    // my ack[receiver]
-};
-struct P2PSource {
-  const uint64_t* ready_flag;  // my ready[source]
-  uint64_t* ack_flag;          // source's ack[me]
-};
-
-constexpr int kArenaFlagBytes = 4096;  // ready flags at [0, 2048), ack flags at [2048, 4096): 256 ranks max
-constexpr long long kSpinLimit = 1ll << 23;  // a few seconds; a peer that never shows up must not hang the GPU
-
-__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
-  uint64_t v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
-}
-
 // fused pack + send: dst[(i - start)*k + j] = src[lid[i] + j*ld] for every export entry i, into the receivers' buffers.
 // The epoch lives in device memory (this kernel advances it), so the whole apply sequence is a static CUDA graph.
 __global__ void __launch_bounds__(kThreads) pack_p2p_kernel(const double* __restrict__ src, int64_t ld, const int32_t* __restrict__ lids,
@@ -234,7 +212,7 @@ bool p2p_setup(Plan& p, int32_t k) {
   p.arena_buf_bytes = (((size_t)std::max(p.n_remote, 1) * k * 8) + 255) & ~(size_t)255;
   p.arena.alloc(kArenaFlagBytes + p.arena_buf_bytes);
   JP_CUDA(cudaMemset(p.arena.p, 0, kArenaFlagBytes + p.arena_buf_bytes));
-  p.p2p_tickets.alloc(64);  // [0] ticket of the pack kernel (uint32), [8..16) the epoch (uint64)
+  p.p2p_tickets.alloc(64);  // uint32 tickets at bytes 0/4/8, the epoch (uint64) at byte 16
   JP_CUDA(cudaMemset(p.p2p_tickets.p, 0, 64));
   // what every rank publishes: IPC handle, buffer size, and for each source rank the element offset of its data
   struct Info {
@@ -399,7 +377,7 @@ const double* plan_post_p2p(Plan& p, const MultiVector& src) {
   const int32_t k = src.k;
   if (p.p2p_state == 0 || (p.p2p_state == 1 && p.p2p_k != k)) p.p2p_state = p2p_setup(p, k) ? 1 : -1;
   if (p.p2p_state != 1) return nullptr;
-  uint64_t* epoch_dev = reinterpret_cast<uint64_t*>(static_cast<char*>(p.p2p_tickets.p) + 8);
+  uint64_t* epoch_dev = reinterpret_cast<uint64_t*>(static_cast<char*>(p.p2p_tickets.p) + 16);
   JP_CUDA(cudaEventRecord(x.ev_x_ready, x.compute));
   JP_CUDA(cudaStreamWaitEvent(x.comm, x.ev_x_ready, 0));
   // always launched: it also advances the epoch
@@ -417,7 +395,7 @@ const double* plan_post_p2p(Plan& p, const MultiVector& src) {
 void plan_p2p_ack(Plan& p) {
   Context& x = ctx();
   if (p.n_sources > 0) {
-    const uint64_t* epoch_dev = reinterpret_cast<const uint64_t*>(static_cast<char*>(p.p2p_tickets.p) + 8);
+    const uint64_t* epoch_dev = reinterpret_cast<const uint64_t*>(static_cast<char*>(p.p2p_tickets.p) + 16);
     halo_ack_kernel<<<1, 32, 0, x.comm>>>(p.wait_table.as<P2PSource>(), p.n_sources, epoch_dev);
     JP_LAUNCH_CHECK();
   }
@@ -480,7 +458,33 @@ void apply_no_trans(Csr* a, Plan* p, MultiVector* y, MultiVector* x, double alph
     JP_CUDA(cudaStreamWaitEvent(c.comm, c.ev_tmp, 0));
     return;
   }
-  // Fused path.  The sequence is 2 streams, 3-4 kernels and one NCCL group; at 8 GPUs the device time of one apply
+  // k == 1 with a peer-memory halo: ONE kernel does pack + send + interior rows + wait + boundary rows + ack
+  // (spmv_fused_halo_kernel, csrc/jp_csr.cu).  JP_FUSED=0 falls back to the two-stream sequence below.
+  static const bool fused_kernel_enabled = []() {
+    const char* v = std::getenv("JP_FUSED");
+    return !(v && *v == '0');
+  }();
+  if (fused_kernel_enabled && x->k == 1) {
+    if (p->p2p_state == 0 || (p->p2p_state == 1 && p->p2p_k != 1)) {  // collective, once
+      JP_CUDA(cudaStreamSynchronize(c.compute));
+      p->p2p_state = p2p_setup_public(*p, 1) ? 1 : -1;
+    }
+    if (p->p2p_state == 1 && p->p2p_k == 1) {
+      FusedHalo h;
+      h.lids = p->export_lids.as<int32_t>();
+      h.n_export = p->n_export;
+      h.sends = p->send_table.as<P2PSend>();
+      h.n_sends = p->n_send_blocks;
+      h.sources = p->wait_table.as<P2PSource>();
+      h.n_sources = p->n_sources;
+      h.epoch_dev = reinterpret_cast<uint64_t*>(static_cast<char*>(p->p2p_tickets.p) + 16);
+      h.tickets = p->p2p_tickets.as<unsigned int>();
+      const double* halo = reinterpret_cast<const double*>(static_cast<const char*>(p->arena.p) + kArenaFlagBytes);
+      launch_spmv_fused(*a, h, x->d(), halo, y->d(), alpha, beta, c.compute);
+      return;
+    }
+  }
+  // Two-stream path.  The sequence is 2 streams, 3-4 kernels and one NCCL group; at 8 GPUs the device time of one apply
   // (~35 us for 256^3) is of the order of the host time to enqueue it, so the sequence is captured ONCE per
   // (X, Y, plan buffers, alpha, beta) into a CUDA graph and replayed with a single cudaGraphLaunch afterwards.
   plan_ensure_buffers(*p, x->k);
@@ -507,11 +511,7 @@ void apply_no_trans(Csr* a, Plan* p, MultiVector* y, MultiVector* x, double alph
     const char* v = std::getenv("JP_APPLY_GRAPH");
     return (v && *v) ? (*v == '1' ? 1 : 0) : -1;
   }();
-  if (p->p2p_state == 0 && graph_env != 0) {  // decide the halo transport (collective) before choosing the replay mode
-    JP_CUDA(cudaStreamSynchronize(c.compute));
-    p->p2p_state = p2p_setup_public(*p, x->k) ? 1 : -1;
-  }
-  const bool use_graph = graph_env == 1 || (graph_env == -1 && p->p2p_state == 1 && p->p2p_k == x->k);
+  const bool use_graph = graph_env == 1;  // measured slower than eager enqueue at 2 and 8 GPUs (profiles/): opt-in only
   if (!use_graph) {
     body(false);
     return;
