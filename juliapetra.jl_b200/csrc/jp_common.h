@@ -229,6 +229,7 @@ struct Plan : Object {
   DeviceBuffer wait_table;      // per source: {const uint64* ready flag (mine)}, {uint64* ack flag (in the source's arena)}
   int32_t n_send_blocks = 0, n_sources = 0;
   DeviceBuffer p2p_tickets;     // uint32 counters
+  uint64_t epoch = 0;           // applies done through the peer-memory halo (identical on every rank)
   ~Plan() override;
 };
 

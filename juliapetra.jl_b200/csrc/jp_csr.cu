@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_fused_halo_kernel(const Fus
   __shared__ bool s_last;
   const int tid = threadIdx.x;
   const int bid = blockIdx.x;
-  const uint64_t epoch = *reinterpret_cast<const volatile uint64_t*>(a.h.epoch_dev) + 1;  // constant during this kernel
+  const uint64_t epoch = a.h.epoch;
   if (bid < a.n_pack) {
     // ---- pack + send ----
     if (tid < a.h.n_sends && epoch > 1) {  // back-pressure: the receiver consumed the previous halo
@@ -358,6 +358,7 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_fused_halo_kernel(const Fus
     if (s_last) {
       __threadfence_system();
       if (tid < a.h.n_sends) st_release_sys(a.h.sends[tid].ready_flag, epoch);
+      if (tid == 0) a.h.tickets[0] = 0;  // re-arm for the next apply (stream-ordered after this kernel)
     }
   } else if (bid < a.n_pack + a.n_interior) {
     const StageView sv = stage_view(smem_raw, a.cap);
@@ -377,18 +378,9 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_fused_halo_kernel(const Fus
     __syncthreads();
     if (tid == 0) s_last = (atomicAdd(a.h.tickets + 1, 1u) == (unsigned)a.n_boundary - 1);
     __syncthreads();
-    if (s_last && tid < a.h.n_sources) st_release_sys(a.h.sources[tid].ack_flag, epoch);
-  }
-  // the last CTA of the whole grid closes the epoch and re-arms the tickets
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    if (atomicAdd(a.h.tickets + 2, 1u) == gridDim.x - 1) {
-      a.h.tickets[0] = 0;
-      a.h.tickets[1] = 0;
-      a.h.tickets[2] = 0;
-      *reinterpret_cast<volatile uint64_t*>(a.h.epoch_dev) = epoch;
-      __threadfence();
+    if (s_last) {
+      if (tid < a.h.n_sources) st_release_sys(a.h.sources[tid].ack_flag, epoch);
+      if (tid == 0) a.h.tickets[1] = 0;
     }
   }
 }

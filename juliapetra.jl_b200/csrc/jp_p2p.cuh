@@ -35,8 +35,8 @@ struct FusedHalo {
   int32_t n_sends;
   const P2PSource* sources;
   int32_t n_sources;
-  uint64_t* epoch_dev;      // completed epochs; this apply is epoch *epoch_dev + 1
-  unsigned int* tickets;    // [0] pack blocks done, [1] boundary blocks done, [2] all blocks done
+  uint64_t epoch;           // this apply's epoch (host counter of the plan: applies are collective and in order)
+  unsigned int* tickets;    // [0] pack blocks done, [1] boundary blocks done (each re-armed by its last block)
 };
 
 }  // namespace jp

@@ -126,15 +126,10 @@ void exchange(Plan& p, int32_t k, bool reverse, cudaStream_t st) {
 // never overwrite a halo that is still being read.
 // ---------------------------------------------------------------------------------------------------------------
 // fused pack + send: dst[(i - start)*k + j] = src[lid[i] + j*ld] for every export entry i, into the receivers' buffers.
-// The epoch lives in device memory (this kernel advances it), so the whole apply sequence is a static CUDA graph.
 __global__ void __launch_bounds__(kThreads) pack_p2p_kernel(const double* __restrict__ src, int64_t ld, const int32_t* __restrict__ lids,
                                                               int32_t n, int32_t k, const P2PSend* __restrict__ table, int32_t n_blocks,
-                                                              uint64_t* __restrict__ epoch_dev, unsigned int* __restrict__ ticket) {
-  __shared__ uint64_t s_epoch;
+                                                              uint64_t epoch, unsigned int* __restrict__ ticket) {
   __shared__ bool is_last;
-  if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile uint64_t*>(epoch_dev) + 1;
-  __syncthreads();
-  const uint64_t epoch = s_epoch;
   // back-pressure: the receiver must have consumed the previous halo before its buffer is overwritten
   if (threadIdx.x < n_blocks && epoch > 1) {
     long long spins = 0;
@@ -156,17 +151,13 @@ __global__ void __launch_bounds__(kThreads) pack_p2p_kernel(const double* __rest
   __syncthreads();
   if (is_last) {
     __threadfence_system();
-    if (threadIdx.x == 0) {
-      *reinterpret_cast<volatile uint64_t*>(epoch_dev) = epoch;
-      *ticket = 0;
-    }
+    if (threadIdx.x == 0) *ticket = 0;
     if (threadIdx.x < n_blocks) st_release_sys(table[threadIdx.x].ready_flag, epoch);
   }
 }
 
 // one warp: wait until every source has published this epoch's halo
-__global__ void halo_wait_kernel(const P2PSource* __restrict__ sources, int32_t n_sources, const uint64_t* __restrict__ epoch_dev) {
-  const uint64_t epoch = *reinterpret_cast<const volatile uint64_t*>(epoch_dev);
+__global__ void halo_wait_kernel(const P2PSource* __restrict__ sources, int32_t n_sources, uint64_t epoch) {
   if ((int)threadIdx.x < n_sources) {
     long long spins = 0;
     while (ld_acquire_sys(sources[threadIdx.x].ready_flag) < epoch && ++spins < kSpinLimit) {
@@ -175,8 +166,7 @@ __global__ void halo_wait_kernel(const P2PSource* __restrict__ sources, int32_t 
 }
 
 // one warp: tell every source that this epoch's halo has been consumed
-__global__ void halo_ack_kernel(const P2PSource* __restrict__ sources, int32_t n_sources, const uint64_t* __restrict__ epoch_dev) {
-  const uint64_t epoch = *reinterpret_cast<const volatile uint64_t*>(epoch_dev);
+__global__ void halo_ack_kernel(const P2PSource* __restrict__ sources, int32_t n_sources, uint64_t epoch) {
   if ((int)threadIdx.x < n_sources) st_release_sys(sources[threadIdx.x].ack_flag, epoch);
 }
 
@@ -212,8 +202,9 @@ bool p2p_setup(Plan& p, int32_t k) {
   p.arena_buf_bytes = (((size_t)std::max(p.n_remote, 1) * k * 8) + 255) & ~(size_t)255;
   p.arena.alloc(kArenaFlagBytes + p.arena_buf_bytes);
   JP_CUDA(cudaMemset(p.arena.p, 0, kArenaFlagBytes + p.arena_buf_bytes));
-  p.p2p_tickets.alloc(64);  // uint32 tickets at bytes 0/4/8, the epoch (uint64) at byte 16
+  p.p2p_tickets.alloc(64);  // uint32 tickets: [0] pack blocks, [1] boundary blocks
   JP_CUDA(cudaMemset(p.p2p_tickets.p, 0, 64));
+  p.epoch = 0;
   // what every rank publishes: IPC handle, buffer size, and for each source rank the element offset of its data
   struct Info {
     cudaIpcMemHandle_t handle;
@@ -377,16 +368,16 @@ const double* plan_post_p2p(Plan& p, const MultiVector& src) {
   const int32_t k = src.k;
   if (p.p2p_state == 0 || (p.p2p_state == 1 && p.p2p_k != k)) p.p2p_state = p2p_setup(p, k) ? 1 : -1;
   if (p.p2p_state != 1) return nullptr;
-  uint64_t* epoch_dev = reinterpret_cast<uint64_t*>(static_cast<char*>(p.p2p_tickets.p) + 16);
+  p.epoch += 1;
   JP_CUDA(cudaEventRecord(x.ev_x_ready, x.compute));
   JP_CUDA(cudaStreamWaitEvent(x.comm, x.ev_x_ready, 0));
   // always launched: it also advances the epoch
   pack_p2p_kernel<<<grid_for((int64_t)p.n_export * k), kThreads, 0, x.comm>>>(src.d(), src.n, p.export_lids.as<int32_t>(), p.n_export, k,
-                                                                             p.send_table.as<P2PSend>(), p.n_send_blocks, epoch_dev,
+                                                                             p.send_table.as<P2PSend>(), p.n_send_blocks, p.epoch,
                                                                              p.p2p_tickets.as<unsigned int>());
   JP_LAUNCH_CHECK();
   if (p.n_sources > 0) {
-    halo_wait_kernel<<<1, 32, 0, x.comm>>>(p.wait_table.as<P2PSource>(), p.n_sources, epoch_dev);
+    halo_wait_kernel<<<1, 32, 0, x.comm>>>(p.wait_table.as<P2PSource>(), p.n_sources, p.epoch);
     JP_LAUNCH_CHECK();
   }
   return reinterpret_cast<const double*>((const char*)p.arena.p + kArenaFlagBytes);
@@ -395,8 +386,7 @@ const double* plan_post_p2p(Plan& p, const MultiVector& src) {
 void plan_p2p_ack(Plan& p) {
   Context& x = ctx();
   if (p.n_sources > 0) {
-    const uint64_t* epoch_dev = reinterpret_cast<const uint64_t*>(static_cast<char*>(p.p2p_tickets.p) + 16);
-    halo_ack_kernel<<<1, 32, 0, x.comm>>>(p.wait_table.as<P2PSource>(), p.n_sources, epoch_dev);
+    halo_ack_kernel<<<1, 32, 0, x.comm>>>(p.wait_table.as<P2PSource>(), p.n_sources, p.epoch);
     JP_LAUNCH_CHECK();
   }
 }
@@ -477,7 +467,7 @@ void apply_no_trans(Csr* a, Plan* p, MultiVector* y, MultiVector* x, double alph
       h.n_sends = p->n_send_blocks;
       h.sources = p->wait_table.as<P2PSource>();
       h.n_sources = p->n_sources;
-      h.epoch_dev = reinterpret_cast<uint64_t*>(static_cast<char*>(p->p2p_tickets.p) + 16);
+      h.epoch = ++p->epoch;
       h.tickets = p->p2p_tickets.as<unsigned int>();
       const double* halo = reinterpret_cast<const double*>(static_cast<const char*>(p->arena.p) + kArenaFlagBytes);
       launch_spmv_fused(*a, h, x->d(), halo, y->d(), alpha, beta, c.compute);
@@ -492,7 +482,8 @@ void apply_no_trans(Csr* a, Plan* p, MultiVector* y, MultiVector* x, double alph
     // comm stream (high priority): pack -> exchange -> BOUNDARY rows; compute stream: INTERIOR rows, concurrently.
     // The two launches write disjoint rows of Y; the compute stream joins on the comm stream at the end, so there
     // is no serial boundary-kernel latency after the interior kernel's tail.
-    const double* halo = plan_post_p2p(*p, *x);  // peer-memory halo; nullptr -> NCCL send/recv
+    // peer-memory halo (epochs are host-counted, so a captured graph falls back to NCCL send/recv); nullptr -> NCCL
+    const double* halo = capturing ? nullptr : plan_post_p2p(*p, *x);
     const bool p2p = halo != nullptr;
     if (!p2p) {
       plan_post(*p, *x, nullptr, /*halo_only=*/true, JP_INSERT, false);
