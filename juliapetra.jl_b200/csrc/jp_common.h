@@ -261,6 +261,7 @@ void launch_spmv_fused(const Csr& A, const FusedHalo& h, const double* x, const 
 const double* plan_post_p2p(Plan& p, const MultiVector& src);
 void plan_p2p_ack(Plan& p);
 bool p2p_setup_public(Plan& p, int32_t k);
+void apply_trans_distributed(Csr* a, Plan* p, MultiVector* y, MultiVector* x, double alpha, double beta);
 void comm_allreduce_device(Comm& c, double* buf, int64_t n, cudaStream_t stream);
 void release_host_path_cache();
 void release_reduce_workspace();

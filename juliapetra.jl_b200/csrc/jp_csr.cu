@@ -683,7 +683,7 @@ void launch_spmm_impl(const Csr& A, const BlockDesc* b, int32_t n_blocks, size_t
 void build_tiles(Csr& A) {
   constexpr int KT = 8;
   const size_t nb = A.h_blocks_all.size();
-  if (A.nnz == 0 || nb == 0 || env_int("JP_SPMM_TILE", 1) == 0) {
+  if (A.nnz == 0 || nb == 0 || env_int("JP_SPMM_TILE", 0) == 0) {  // opt-in: measured slower than the gather kernel (profiles/)
     A.tile_state = -1;
     return;
   }

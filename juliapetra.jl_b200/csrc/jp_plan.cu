@@ -298,7 +298,86 @@ bool p2p_setup(Plan& p, int32_t k) {
   return true;
 }
 
+// Distributed TRANS / CONJ_TRANS: src/RowMatrix.jl:324-352 with the semantics of
+// Tpetra::CrsMatrix::applyTranspose (the reference's own lines cannot run: undefined names, ADD ignored):
+//   YColMap = alpha * A_local^T * X  (scatter kernel into the cached column-map multivector, beta = 0)
+//   Y = beta * Y;  doExport(YColMap, Y, importer, ADD) in reverse mode: local columns are added in place, every
+//   remote column's partial sum travels back to its owner (the halo exchange run backwards) and is added there.
+__global__ void __launch_bounds__(kThreads) add_rows_kernel(double* __restrict__ y, int64_t ldy, const double* __restrict__ yc, int64_t ldc,
+                                                              int32_t n, int32_t k) {
+  const int64_t total = (int64_t)n * k, stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += stride) {
+    const int32_t j = (int32_t)(t / n), i = (int32_t)(t - (int64_t)j * n);
+    y[i + (size_t)j * ldy] += yc[i + (size_t)j * ldc];
+  }
+}
+__global__ void __launch_bounds__(kThreads) add_permute_kernel(double* __restrict__ y, int64_t ldy, const double* __restrict__ yc, int64_t ldc,
+                                                                 const int32_t* __restrict__ dom_lids, const int32_t* __restrict__ col_lids,
+                                                                 int32_t n, int32_t k) {
+  const int64_t total = (int64_t)n * k, stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += stride) {
+    const int32_t j = (int32_t)(t / n), i = (int32_t)(t - (int64_t)j * n);
+    y[dom_lids[i] + (size_t)j * ldy] += yc[col_lids[i] + (size_t)j * ldc];
+  }
+}
+// y[lid[i] + j*ld] += buf[i*k + j]; a row exported to several ranks appears several times in lids -> atomics
+__global__ void __launch_bounds__(kThreads) scatter_add_kernel(double* __restrict__ y, int64_t ld, const int32_t* __restrict__ lids, int32_t n,
+                                                                 int32_t k, const double* __restrict__ buf) {
+  const int64_t total = (int64_t)n * k, stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += stride) {
+    const int32_t j = (int32_t)(t / n), i = (int32_t)(t - (int64_t)j * n);
+    atomicAdd(y + lids[i] + (size_t)j * ld, buf[(size_t)i * k + j]);
+  }
+}
+
 }  // namespace
+
+void apply_trans_distributed(Csr* a, Plan* p, MultiVector* y, MultiVector* x, double alpha, double beta) {
+  Context& c = ctx();
+  const int32_t k = x->k;
+  JP_REQUIRE(x->n == a->n_rows, "apply!: transposed apply needs X on the row map");
+  JP_REQUIRE(y->n == p->n_src && p->n_tgt == a->n_cols, "apply!: transposed apply needs Y on the domain map of the importer");
+  if (!a->import_mv || a->import_mv->k != k) {
+    JP_CUDA(cudaStreamSynchronize(c.compute));
+    JP_CUDA(cudaStreamSynchronize(c.comm));
+    a->import_mv = std::make_unique<MultiVector>();
+    a->import_mv->n = a->n_cols;
+    a->import_mv->k = k;
+    a->import_mv->data.alloc((size_t)a->n_cols * k * 8 + 64);
+  }
+  MultiVector* yc = a->import_mv.get();
+  plan_ensure_buffers(*p, k);
+  launch_spmv_trans(*a, x->d(), x->n, yc->d(), yc->n, yc->n, k, alpha, 0.0, c.compute);
+  launch_scale_fill(y->d(), (int64_t)y->n * k, beta, c.compute);
+  if (p->num_same > 0 && k > 0) {
+    add_rows_kernel<<<grid_for((int64_t)p->num_same * k), kThreads, 0, c.compute>>>(y->d(), y->n, yc->d(), yc->n, p->num_same, k);
+    JP_LAUNCH_CHECK();
+  }
+  if (p->n_permute > 0 && k > 0) {
+    add_permute_kernel<<<grid_for((int64_t)p->n_permute * k), kThreads, 0, c.compute>>>(y->d(), y->n, yc->d(), yc->n, p->permute_from.as<int32_t>(),
+                                                                                       p->permute_to.as<int32_t>(), p->n_permute, k);
+    JP_LAUNCH_CHECK();
+  }
+  // the halo exchange run backwards: what was imported forward (remote LIDs) is exported now, on the comm stream
+  JP_CUDA(cudaEventRecord(c.ev_x_ready, c.compute));
+  JP_CUDA(cudaStreamWaitEvent(c.comm, c.ev_x_ready, 0));
+  if (p->n_remote > 0 && k > 0) {
+    pack_kernel<<<grid_for((int64_t)p->n_remote * k), kThreads, 0, c.comm>>>(yc->d(), yc->n, p->remote_lids.as<int32_t>(), p->n_remote, k,
+                                                                            p->sendbuf.as<double>());
+    JP_LAUNCH_CHECK();
+  }
+  exchange(*p, k, /*reverse=*/true, c.comm);
+  JP_CUDA(cudaEventRecord(p->ev_done, c.comm));
+  JP_CUDA(cudaStreamWaitEvent(c.compute, p->ev_done, 0));
+  if (p->n_export > 0 && k > 0) {
+    scatter_add_kernel<<<grid_for((int64_t)p->n_export * k), kThreads, 0, c.compute>>>(y->d(), y->n, p->export_lids.as<int32_t>(), p->n_export,
+                                                                                      k, p->recvbuf.as<double>());
+    JP_LAUNCH_CHECK();
+  }
+  JP_CUDA(cudaEventRecord(c.ev_tmp, c.compute));
+  JP_CUDA(cudaStreamWaitEvent(c.comm, c.ev_tmp, 0));
+}
+
 
 void plan_ensure_buffers(Plan& p, int32_t k) {
   if (k <= p.buf_k) return;
@@ -558,11 +637,12 @@ void apply_impl(Csr* a, Plan* p, MultiVector* y, MultiVector* x, int32_t mode, d
   if (mode == JP_NO_TRANS) {
     apply_no_trans(a, p, y, x, alpha, beta);
   } else {
-    // distributed TRANS needs doExport(..., ADD), which the reference does not implement
-    // (src/RowMatrix.jl:324-352 uses undefined names; ADD ignored at src/MultiVector.jl:359-371)
-    JP_REQUIRE_STATE(p == nullptr, "apply!: transposed apply with a non-trivial importer is non-functional in the reference");
-    JP_REQUIRE(x->n == a->n_rows && y->n == a->n_cols, "apply!: transposed apply needs X on the row map and Y on the column map");
-    launch_spmv_trans(*a, x->d(), x->n, y->d(), y->n, y->n, y->k, alpha, beta, ctx().compute);
+    if (p == nullptr) {
+      JP_REQUIRE(x->n == a->n_rows && y->n == a->n_cols, "apply!: transposed apply needs X on the row map and Y on the column map");
+      launch_spmv_trans(*a, x->d(), x->n, y->d(), y->n, y->n, y->k, alpha, beta, ctx().compute);
+    } else {
+      apply_trans_distributed(a, p, y, x, alpha, beta);
+    }
   }
 }
 

@@ -1497,12 +1497,55 @@ void applyMatrix(MultiVec* Y, Matrix* A, MultiVec* X, int mode, double alpha, do
       localApply(Y->data[p].data(), Y->n(p), A->d[p], A->rowMap->d[p].numMyElements, XColMap->data[p].data(), XColMap->n(p), Y->k, mode, alpha, b);
     }
   } else {
-    if (A->importer != nullptr || A->exporter != nullptr)
-      throwState("apply!: distributed TRANS is non-functional in the reference (out of scope)");
+    if (A->exporter != nullptr) throwState("apply!: rangeMap != rowMap is non-functional in the reference (out of scope)");
     if (X == Y) throwState("apply!: X and Y must differ");
-    for (int p = 0; p < P; ++p) {
-      double b = (YIsReplicated && p + 1 != 1) ? 0.0 : beta;
-      localApply(Y->data[p].data(), Y->n(p), A->d[p], A->rowMap->d[p].numMyElements, X->data[p].data(), X->n(p), Y->k, mode, alpha, b);
+    if (A->importer == nullptr) {
+      for (int p = 0; p < P; ++p) {
+        double b = (YIsReplicated && p + 1 != 1) ? 0.0 : beta;
+        localApply(Y->data[p].data(), Y->n(p), A->d[p], A->rowMap->d[p].numMyElements, X->data[p].data(), X->n(p), Y->k, mode, alpha, b);
+      }
+    } else {
+      // Distributed TRANS / CONJ_TRANS.  src/RowMatrix.jl:324-352 spells the algorithm
+      //   YColMap = createColumnMapMultiVector; localApply(YColMap, A, X, mode, alpha, ZERO);
+      //   Y = beta*Y (or 0);  doExport(YColMap, Y, importer, ADD)
+      // but cannot run in the reference (undefined `mat` :328,334; `YIsOverwritten` :337; ADD ignored by
+      // unpackAndCombine, src/MultiVector.jl:359-371; reverse mode passes the forward lists unswapped,
+      // src/DistObject.jl:147-157).  Restated with the semantics of Tpetra::CrsMatrix::applyTranspose, which
+      // those lines transcribe: the reverse-mode export ADDS -- local columns (same + permuted LIDs) into Y, and
+      // every remote column's partial sum is sent back to its owner and added at the owner's export LID.
+      // NOT pinned by any reference test; tests/test_oracle_golden.py checks it against a dense A^T X.
+      const int k = Y->k;
+      MultiVec* YColMap = createColumnMapMultiVector(A, Y);  // k columns on the column map
+      TransferPlan* imp = A->importer;
+      PerRank<std::vector<uint8_t>> exports(P);
+      for (int p = 0; p < P; ++p) {
+        const int64_t ncol = YColMap->n(p), ny = Y->n(p);
+        double* yc = YColMap->data[p].data();
+        localApply(yc, ncol, A->d[p], A->rowMap->d[p].numMyElements, X->data[p].data(), X->n(p), k, mode, alpha, 0.0);
+        double b = (YIsReplicated && p + 1 != 1) ? 0.0 : beta;
+        double* y = Y->data[p].data();
+        for (size_t i = 0; i < Y->data[p].size(); ++i) y[i] = (b == 0.0) ? 0.0 : y[i] * b;
+        const PlanData& d = imp->d[p];
+        for (int v = 0; v < k; ++v) {
+          for (LID i = 1; i <= d.numSameIDs; ++i) y[(size_t)v * ny + i - 1] += yc[(size_t)v * ncol + i - 1];
+          for (size_t i = 0; i < d.permuteToLIDs.size(); ++i)
+            y[(size_t)v * ny + d.permuteFromLIDs[i] - 1] += yc[(size_t)v * ncol + d.permuteToLIDs[i] - 1];
+        }
+        std::vector<double> ex;
+        packAndPrepare(yc, ncol, k, d.remoteLIDs, ex);  // what was imported forward is exported in reverse
+        exports[p].resize(ex.size() * sizeof(double));
+        if (!ex.empty()) std::memcpy(exports[p].data(), ex.data(), exports[p].size());
+      }
+      PerRank<std::vector<uint8_t>> imports = distResolve(imp->dist, exports, sizeof(double) * k, /*reverse=*/true);
+      for (int p = 0; p < P; ++p) {
+        const PlanData& d = imp->d[p];
+        const int64_t ny = Y->n(p);
+        if (imports[p].size() != d.exportLIDs.size() * sizeof(double) * k) throwState("reverse transfer: received length does not match exportLIDs");
+        const double* in = reinterpret_cast<const double*>(imports[p].data());
+        double* y = Y->data[p].data();
+        for (size_t i = 0; i < d.exportLIDs.size(); ++i)
+          for (int v = 0; v < k; ++v) y[(size_t)v * ny + d.exportLIDs[i] - 1] += in[i * k + v];  // ADD, in export order
+      }
     }
   }
   if (YIsReplicated) commReduce(Y);  // identity on SerialComm

@@ -134,6 +134,24 @@ def main():
             OXC = O.OMV(OA.col_map, k)
             O.do_transfer(OX, OXC, OA.importer, False, O.INSERT)
             assert np.array_equal(XC.data, OXC.get(pid)), (kind, pid)
+    # ---- distributed TRANS (Tpetra semantics, see oracle/jp_oracle.cpp applyMatrix) ----
+    for kind, size, k in (("7pt", 12, 2), ("powerlaw", 6000, 1), ("27pt", 8, 3)):
+        rm = jp.BlockMap(global_rows(kind, size), comm)
+        Aj = synthetic.build_matrix(jp, rm, kind, size, max_len=500)
+        oc, om, OA = oracle_problem(kind, size, P, max_len=500)
+        xs = [synthetic.vector_block(om.info(p)["minMyGID"], om.info(p)["numMyElements"], k, seed=1) for p in everyone]
+        ys = [synthetic.vector_block(om.info(p)["minMyGID"], om.info(p)["numMyElements"], k, seed=2) for p in everyone]
+        OX, OY = O.OMV.from_arrays(om, xs), O.OMV.from_arrays(om, ys)
+        OA.apply(OY, OX, O.TRANS, 3.0, 0.5)
+        Xj, Yj = jp.DenseMultiVector(rm, xs[rank]), jp.DenseMultiVector(rm, ys[rank])
+        Aj.apply_(Yj, Xj, jp.TRANS, 3.0, 0.5)
+        ref = OY.get(pid)
+        # bound: |beta||y| + |alpha| |A|^T |x| through the oracle on absolute values
+        OAabs_x = O.OMV.from_arrays(om, [np.abs(x) for x in xs])
+        OAabs_y = O.OMV.from_arrays(om, [np.abs(y) for y in ys])
+        # (A's values are not all positive: use a generous norm-wise bound instead)
+        scale = np.abs(ref).max() + 1.0
+        assert np.abs(Yj.data - ref).max() <= 200 * TOL * scale, (kind, pid, np.abs(Yj.data - ref).max())
     # commReduce on a replicated map (test/DenseMultiVectorTests.jl:96-99)
     rep = jp.BlockMap(6, 6, comm)
     v = jp.DenseMultiVector(rep, (10.0 ** pid) * np.ones((6, 3)))

@@ -392,3 +392,33 @@ def test_invalid_handles_and_arguments():
     n = C.c_int64()
     _lib.check(lib.jp_launch_count(C.byref(n)))
     assert n.value > 0
+
+
+def test_transposed_apply_with_importer_serial():
+    """TRANS through an importer (a column map with permutes, one rank): the reverse-mode ADD path of
+    apply_trans_distributed, against a dense A^T X and against the oracle"""
+    c = jp.SerialComm()
+    m = jp.BlockMap(6, c)
+    rows = {1: ([3, 1, 2], [1.0, 2.0, 4.0]), 2: ([2], [5.0]), 3: ([6, 5], [1.0, 2.0]), 4: ([1], [9.0]), 5: ([1, 2, 3], [1.0, 1.5, 1.25]),
+            6: ([6, 1], [7.0, 8.0])}
+    A = jp.CSRMatrix(m, [3, 1, 2, 1, 3, 2], jp.STATIC_PROFILE)
+    oc = O.OComm(1)
+    om = O.OMap.uniform(oc, 6)
+    OA = O.OMatrix(om, [[3, 1, 2, 1, 3, 2]])
+    dense = np.zeros((6, 6))
+    for g, (ci, va) in rows.items():
+        A.insertGlobalValues(g, ci, va)
+        OA.insert(1, g, ci, va)
+        for cc, vv in zip(ci, va):
+            dense[g - 1, cc - 1] += vv
+    A.fillComplete(m, m)
+    OA.fill_complete(om, om)
+    assert A.importer is not None
+    x = np.arange(1.0, 13.0).reshape((6, 2), order="F")
+    y0 = np.linspace(-1, 1, 12).reshape((6, 2), order="F")
+    X, Y = jp.DenseMultiVector(m, x), jp.DenseMultiVector(m, y0)
+    A.apply_(Y, X, jp.TRANS, 3.0, 0.5)
+    OX, OY = O.OMV.from_arrays(om, [x]), O.OMV.from_arrays(om, [y0])
+    OA.apply(OY, OX, O.TRANS, 3.0, 0.5)
+    ref = 0.5 * y0 + 3.0 * (dense.T @ x)
+    assert np.allclose(Y.data, ref, rtol=1e-13, atol=1e-13) and np.allclose(OY.get(1), ref, rtol=1e-13, atol=1e-13)

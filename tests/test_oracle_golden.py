@@ -461,3 +461,33 @@ def test_timed_apply_matches_apply():
     assert A.time_apply(Y2, X, 1.0, 0.0, iters=2, warmup=1) > 0
     for pid in range(1, P + 1):
         assert np.array_equal(Y1.get(pid), Y2.get(pid))
+
+
+# ---- distributed TRANS: not functional in the reference, restated with Tpetra semantics --------
+@pytest.mark.parametrize("kind,N,P,k", [("7pt", 6, 4, 2), ("powerlaw", 400, 4, 3), ("5pt", 9, 2, 1), ("powerlaw", 300, 1, 2)])
+def test_distributed_trans_matches_dense(kind, N, P, k):
+    from oracle.problems import oracle_problem
+    c, m, A = oracle_problem(kind, N, P, max_len=60)
+    n = m.info(1)["numGlobalElements"]
+    dense = np.zeros((n, n))
+    for pid in range(1, P + 1):
+        rp, ci, va = A.csr(pid)
+        cols = A.col_map.my_gids(pid)
+        rows = m.my_gids(pid)
+        for r in range(len(rows)):
+            for i in range(rp[r] - 1, rp[r + 1] - 1):
+                dense[rows[r] - 1, cols[ci[i] - 1] - 1] += va[i]
+    rng = np.random.default_rng(7)
+    xg, yg = rng.standard_normal((n, k)), rng.standard_normal((n, k))
+    split = lambda g: [g[m.info(p)["minMyGID"] - 1: m.info(p)["maxMyGID"], :] for p in range(1, P + 1)]
+    X, Y = O.OMV.from_arrays(m, split(xg)), O.OMV.from_arrays(m, split(yg))
+    A.apply(Y, X, O.TRANS, 3.0, 0.5)
+    ref = 0.5 * yg + 3.0 * (dense.T @ xg)
+    got = np.vstack([Y.get(p) for p in range(1, P + 1)])
+    scale = 0.5 * np.abs(yg) + 3.0 * (np.abs(dense).T @ np.abs(xg))
+    assert (np.abs(got - ref) <= 1e-12 * scale + 1e-300).all()
+    # beta == 0 overwrites
+    Y2 = O.OMV.from_arrays(m, split(np.full((n, k), np.nan)))
+    A.apply(Y2, X, O.TRANS, 1.0, 0.0)
+    got2 = np.vstack([Y2.get(p) for p in range(1, P + 1)])
+    assert (np.abs(got2 - dense.T @ xg) <= 1e-12 * (np.abs(dense).T @ np.abs(xg)) + 1e-300).all()
