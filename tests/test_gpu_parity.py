@@ -422,3 +422,15 @@ def test_transposed_apply_with_importer_serial():
     OA.apply(OY, OX, O.TRANS, 3.0, 0.5)
     ref = 0.5 * y0 + 3.0 * (dense.T @ x)
     assert np.allclose(Y.data, ref, rtol=1e-13, atol=1e-13) and np.allclose(OY.get(1), ref, rtol=1e-13, atol=1e-13)
+
+
+@pytest.mark.parametrize("k", [8, 11])
+def test_spmm_shared_memory_tile_path(monkeypatch, k):
+    """opt-in SpMM kernel that stages the block's X tile in shared memory (unique-column lists, JP_SPMM_TILE=1)"""
+    monkeypatch.setenv("JP_SPMM_TILE", "1")
+    c, m, A = serial_matrix("27pt", 20)
+    n = m.numMyElements()
+    x = synthetic.vector_block(1, n, k, seed=1)
+    y0 = synthetic.vector_block(1, n, k, seed=2)
+    check_apply(A, x, y0, 3.0, 0.5, exact=False)
+    check_apply(A, x, y0, 1.0, 0.0, exact=False)
