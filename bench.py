@@ -356,7 +356,7 @@ def main():
             "hbm_gbs": bytes_apply / (ms_per_step * 1e-3) / 1e9, "host_enqueue_ms_per_step": host_enqueue_ms, "host_enqueue_burst_ms_per_step": host_burst_ms,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
                          "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0, "bytes_per_launch": bytes_rank,
-                         "kernel": "spmv_kernel (one launch per apply at N=1; interior+boundary launches at N>1)"},
+                         "kernel": "spmv_kernel (one launch per apply at N=1; at N>1 the same row-block code inside spmv_fused_halo_kernel, one launch per apply)"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": dict(clocks or {}, window=clocks_window) if clocks else None,
         }
         print(json.dumps(line), flush=True)

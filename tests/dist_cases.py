@@ -181,3 +181,58 @@ def case_laplacian_1d_golden(rank, world):
     assert A.importer.remoteLIDs().tolist() == exp[1] and A.importer.exportLIDs().tolist() == exp[2]
     assert A.importer.exportPIDs().tolist() == exp[3] and A.importer.numSameIDs() == 2
     assert A.rowOffsets.tolist() == exp[4] and A.localIndices1D.tolist() == exp[5]
+
+
+def case_irregular_matrix(rank, world):
+    """more rows than one rank can fill (an empty rank), unused local columns (permutes) and remotes at once:
+    maps, column map, Import lists and CSR bit-exact against the oracle"""
+    import jpetra_b200 as jp
+    import oracle as O
+    from helpers import assert_plan_equal
+    comm = jp.TorchDistComm()
+    pid, P = comm.myPid(), comm.numProc()
+    N = P + 1 if P > 2 else 5  # uneven split; with P=4: rows per rank 2,1,1,1
+    rng = np.random.default_rng(11)
+    cols_of = {g: sorted(set(rng.integers(1, N + 1, size=3).tolist()) - {2}) or [1] for g in range(1, N + 1)}  # GID 2 is never a column
+    vals_of = {g: rng.standard_normal(len(cols_of[g])) for g in range(1, N + 1)}
+    m = jp.BlockMap(N, comm)
+    oc = O.OComm(P)
+    om = O.OMap.uniform(oc, N)
+    mine = m.myGlobalElements()
+    A = jp.CSRMatrix(m, [len(cols_of[int(g)]) for g in mine], jp.STATIC_PROFILE)
+    for g in mine:
+        A.insertGlobalValues(int(g), cols_of[int(g)], vals_of[int(g)])
+    A._fillCompleteHost(m, m)
+    OA = O.OMatrix(om, [[len(cols_of[int(g)]) for g in om.my_gids(p)] for p in range(1, P + 1)])
+    for p in range(1, P + 1):
+        for g in om.my_gids(p):
+            OA.insert(p, int(g), cols_of[int(g)], vals_of[int(g)])
+    OA.fill_complete(om, om)
+    rp, ci, va = OA.csr(pid)
+    assert np.array_equal(A.rowOffsets, rp) and np.array_equal(A.localIndices1D, ci) and np.array_equal(A.values, va)
+    assert np.array_equal(A.colMap.myGlobalElements(), OA.col_map.my_gids(pid))
+    assert (A.importer is None) == (OA.importer is None)
+    if A.importer is not None:
+        assert_plan_equal(A.importer, OA.importer, pid)
+
+
+def case_export_plan(rank, world):
+    """a non-trivial Export (source = overlapping GID lists, target = uniform map): lists bit-exact against the oracle"""
+    import jpetra_b200 as jp
+    import oracle as O
+    from helpers import assert_plan_equal
+    comm = jp.TorchDistComm()
+    pid, P = comm.myPid(), comm.numProc()
+    n = 3
+    N = n * P
+    tgt = jp.BlockMap(N, comm)
+    # every rank holds its own rows plus the first row of the next rank (an overlapping, non-linear source map)
+    def src_gids(p):
+        own = list(range((p - 1) * n + 1, p * n + 1))
+        return own + [(p % P) * n + 1]
+    src = jp.BlockMap(-1, src_gids(pid), comm)
+    oc = O.OComm(P)
+    otgt = O.OMap.uniform(oc, N)
+    osrc = O.OMap.from_gids(oc, -1, [src_gids(p) for p in range(1, P + 1)])
+    assert src.numGlobalElements() == osrc.info(pid)["numGlobalElements"] == N
+    assert_plan_equal(jp.Export(src, tgt), O.OPlan.make_export(osrc, otgt), pid)

@@ -152,6 +152,36 @@ def main():
         # (A's values are not all positive: use a generous norm-wise bound instead)
         scale = np.abs(ref).max() + 1.0
         assert np.abs(Yj.data - ref).max() <= 200 * TOL * scale, (kind, pid, np.abs(Yj.data - ref).max())
+    # ---- a column map with unused local columns (permutes) AND remotes: the generic import + single-launch path ----
+    Ng = 40 * P + 3
+    rng = np.random.default_rng(11)
+    cols_of = {g: sorted(set(rng.integers(1, Ng + 1, size=4).tolist()) - {2, 7}) or [1] for g in range(1, Ng + 1)}  # GIDs 2, 7 are never columns
+    vals_of = {g: rng.standard_normal(len(cols_of[g])) for g in range(1, Ng + 1)}
+    mg = jp.BlockMap(Ng, comm)
+    Ag = jp.CSRMatrix(mg, [len(cols_of[int(g)]) for g in mg.myGlobalElements()], jp.STATIC_PROFILE)
+    for g in mg.myGlobalElements():
+        Ag.insertGlobalValues(int(g), cols_of[int(g)], vals_of[int(g)])
+    Ag.fillComplete(mg, mg)
+    ocg = O.OComm(P)
+    omg = O.OMap.uniform(ocg, Ng)
+    OAg = O.OMatrix(omg, [[len(cols_of[int(g)]) for g in omg.my_gids(p)] for p in everyone])
+    for p in everyone:
+        for g in omg.my_gids(p):
+            OAg.insert(p, int(g), cols_of[int(g)], vals_of[int(g)])
+    OAg.fill_complete(omg, omg)
+    for k in (1, 3):
+        xs = [synthetic.vector_block(omg.info(p)["minMyGID"], omg.info(p)["numMyElements"], k, seed=1) for p in everyone]
+        ys = [synthetic.vector_block(omg.info(p)["minMyGID"], omg.info(p)["numMyElements"], k, seed=2) for p in everyone]
+        OX, OY = O.OMV.from_arrays(omg, xs), O.OMV.from_arrays(omg, ys)
+        OAg.apply(OY, OX, O.NO_TRANS, 3.0, 0.5)
+        Xj, Yj = jp.DenseMultiVector(mg, xs[rank]), jp.DenseMultiVector(mg, ys[rank])
+        Ag.apply_(Yj, Xj, jp.NO_TRANS, 3.0, 0.5)
+        assert np.abs(Yj.data - OY.get(pid)).max() <= 100 * TOL * (np.abs(OY.get(pid)).max() + 1.0), (pid, k)
+        OY2 = O.OMV.from_arrays(omg, ys)
+        OAg.apply(OY2, OX, O.TRANS, 3.0, 0.5)
+        Yt = jp.DenseMultiVector(mg, ys[rank])
+        Ag.apply_(Yt, Xj, jp.TRANS, 3.0, 0.5)
+        assert np.abs(Yt.data - OY2.get(pid)).max() <= 100 * TOL * (np.abs(OY2.get(pid)).max() + 1.0), (pid, k, "trans")
     # commReduce on a replicated map (test/DenseMultiVectorTests.jl:96-99)
     rep = jp.BlockMap(6, 6, comm)
     v = jp.DenseMultiVector(rep, (10.0 ** pid) * np.ones((6, 3)))

@@ -28,3 +28,13 @@ def test_fill_complete_matches_oracle(world, kind, N):
 
 def test_laplacian_1d_appendix_b():
     dist_cases.run("case_laplacian_1d_golden", 4)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_irregular_matrix_with_permutes_and_remotes(world):
+    dist_cases.run("case_irregular_matrix", world)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_nontrivial_export_plan(world):
+    dist_cases.run("case_export_plan", world)
