@@ -579,6 +579,146 @@ spmm_tile_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Pipelined SpMM: persistent CTAs (one per SM), two shared-memory stages, warp specialisation.
+//   producer warps (8): wait(empty[s]) -> TMA bulk copies of the block's vals / lidx / row pointers / unique columns
+//                       -> gather the block's X tile [KT vectors] x [unique columns] into shared memory -> arrive(full[s])
+//   consumer warps (8): wait(full[s]) -> T lanes per row out of shared memory, KT accumulators in registers -> y
+//                       -> arrive(empty[s])
+// so the TMA latency and the X-tile gather of item i+1 overlap the arithmetic of item i.  An item is one
+// (row block, vector tile) pair; the tiles of a block run back to back on the same CTA.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kPipeConsumers = 256, kPipeProducers = 256, kPipeThreads = kPipeConsumers + kPipeProducers;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_addr(bar)) : "memory");
+}
+
+__host__ __device__ inline size_t pipe_stage_bytes(int cap, int upad, int KT) { return (tile_smem_bytes(cap, upad, KT) + 127) & ~(size_t)127; }
+
+template <int KT, bool HALO>
+__global__ void __launch_bounds__(kPipeThreads, 1)
+spmm_pipe_kernel(const BlockDesc* __restrict__ blocks, int32_t n_blocks, const int32_t* __restrict__ rowptr,
+                 const double* __restrict__ vals, const uint16_t* __restrict__ lidx, const int32_t* __restrict__ ucols,
+                 const double* __restrict__ x, int64_t ldx, const double* __restrict__ halo, int32_t halo_k, int32_t nloc,
+                 double* __restrict__ y, int64_t ldy, int32_t k, int32_t cap, int32_t upad, double alpha, double beta) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t tma_bar[2], full_bar[2], empty_bar[2];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const bool producer = tid >= kPipeConsumers;
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tma_bar[s], 1);
+      mbar_init(&full_bar[s], kPipeProducers / 32);
+      mbar_init(&empty_bar[s], kPipeConsumers / 32);
+    }
+  }
+  __syncthreads();
+  const size_t stage_bytes = pipe_stage_bytes(cap, upad, KT);
+  const int ntiles = (k + KT - 1) / KT;
+  int item = 0;  // the same sequence of items in both roles
+  for (int bi = blockIdx.x; bi < n_blocks; bi += gridDim.x) {
+    const BlockRange b = decode_block(blocks, bi);
+    const int4 aux = __ldg(reinterpret_cast<const int4*>(blocks + bi) + 1);
+    const int ucol0 = aux.x, U = aux.y;
+    const int al0 = b.p0 & ~7;
+    for (int vt = 0; vt < ntiles; ++vt, ++item) {
+      const int s = item & 1;
+      const unsigned ph = (item >> 1) & 1;
+      const int v0 = vt * KT;
+      const int kt = k - v0 < KT ? k - v0 : KT;
+      unsigned char* base = smem_raw + (size_t)s * stage_bytes;
+      double* s_val = reinterpret_cast<double*>(base);
+      double* xs = s_val + cap + 8;
+      int32_t* s_rp = reinterpret_cast<int32_t*>(xs + (size_t)KT * upad);
+      int32_t* s_ucol = s_rp + kMaxRowsPerBlock + 8;
+      uint16_t* s_lidx = reinterpret_cast<uint16_t*>(s_ucol + upad);
+      if (producer) {
+        const int ptid = tid - kPipeConsumers;
+        mbar_wait(&empty_bar[s], ph ^ 1);  // the consumers have finished with this stage (passes at once the first time)
+        if (ptid == 0) {
+          const int ngrp = (b.p1 - b.a0 + 3) >> 2;
+          const int nl8 = (b.p1 - al0 + 7) & ~7;
+          const int ra0 = b.row0 & ~3;
+          const int nrp = (b.row0 + b.nrows + 1 - ra0 + 3) & ~3;
+          const int nu4 = (U + 3) & ~3;
+          const uint64_t pol = policy_evict_first();
+          mbar_expect_tx(&tma_bar[s], (unsigned)(ngrp * 32 + nl8 * 2 + nrp * 4 + nu4 * 4));
+          if (ngrp > 0) bulk_g2s(s_val, vals + b.a0, (unsigned)ngrp * 32, &tma_bar[s], pol);
+          if (nl8 > 0) bulk_g2s(s_lidx, lidx + al0, (unsigned)nl8 * 2, &tma_bar[s], pol);
+          bulk_g2s(s_rp, rowptr + ra0, (unsigned)nrp * 4, &tma_bar[s], pol);
+          if (nu4 > 0) bulk_g2s(s_ucol, ucols + ucol0, (unsigned)nu4 * 4, &tma_bar[s], pol);
+        }
+        mbar_wait(&tma_bar[s], ph);
+        // X tile: xs[j][u] = X[ucol[u], v0 + j]; two columns per thread per pass -> 2*KT loads in flight
+        for (int u0 = ptid; u0 < U; u0 += 2 * kPipeProducers) {
+          const int u1 = u0 + kPipeProducers;
+          const bool has1 = u1 < U;
+          const int c0 = s_ucol[u0], c1 = has1 ? s_ucol[u1] : c0;
+          double a0[KT], a1[KT];
+          if (HALO && (c0 >= nloc || c1 >= nloc)) {
+#pragma unroll
+            for (int j = 0; j < KT; ++j) {
+              a0[j] = j < kt ? (c0 >= nloc ? halo[(size_t)(c0 - nloc) * halo_k + v0 + j] : __ldg(x + c0 + (size_t)(v0 + j) * ldx)) : 0.0;
+              a1[j] = j < kt ? (c1 >= nloc ? halo[(size_t)(c1 - nloc) * halo_k + v0 + j] : __ldg(x + c1 + (size_t)(v0 + j) * ldx)) : 0.0;
+            }
+          } else {
+            const double* x0 = x + c0 + (size_t)v0 * ldx;
+            const double* x1 = x + c1 + (size_t)v0 * ldx;
+#pragma unroll
+            for (int j = 0; j < KT; ++j) {
+              a0[j] = j < kt ? __ldg(x0 + (size_t)j * ldx) : 0.0;
+              a1[j] = j < kt ? __ldg(x1 + (size_t)j * ldx) : 0.0;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < KT; ++j) {
+            xs[(size_t)j * upad + u0] = a0[j];
+            if (has1) xs[(size_t)j * upad + u1] = a1[j];
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[s]);
+      } else {
+        mbar_wait(&full_bar[s], ph);
+        mbar_wait(&tma_bar[s], ph);  // completed long ago; orders this thread after the bulk copies themselves
+        const int32_t* rp = s_rp + b.rpo;
+        int T = 1;
+        while (T < 4 && b.nrows * (T << 1) <= kPipeConsumers) T <<= 1;
+        const int lane_t = tid & (T - 1), group = tid / T, ngroups = kPipeConsumers / T;
+        for (int rbase = 0; rbase < b.nrows; rbase += ngroups) {  // warp-uniform trip count (shuffles below)
+          const int r = rbase + group;
+          const bool valid = r < b.nrows;
+          const int rs = valid ? rp[r] : 0, re = valid ? rp[r + 1] : 0;
+          double acc[KT];
+#pragma unroll
+          for (int j = 0; j < KT; ++j) acc[j] = 0.0;
+          for (int i = rs + lane_t; i < re; i += T) {
+            const int li = s_lidx[i - al0];
+            const double v = s_val[i - b.a0];
+#pragma unroll
+            for (int j = 0; j < KT; ++j) acc[j] = fma(v, xs[(size_t)j * upad + li], acc[j]);
+          }
+          for (int o = T >> 1; o > 0; o >>= 1) {
+#pragma unroll
+            for (int j = 0; j < KT; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+          }
+          if (valid && lane_t == 0) {
+#pragma unroll
+            for (int j = 0; j < KT; ++j)
+              if (j < kt) {
+                double* yp = y + b.row0 + r + (size_t)(v0 + j) * ldy;
+                *yp = combine(beta == 0.0 ? 0.0 : *yp, acc[j], alpha, beta);
+              }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+      }
+    }
+  }
+}
+
 // TRANS / CONJ_TRANS (src/CSRMatrix.jl:1147-1160): Y[ind, v] += (alpha * X[row, v]) * val, after Y *= beta.
 // Scatter with fp64 atomics (RED.ADD.F64): the summation order differs from the reference's row sweep, within
 // the 1e-12 contract.  Warp per row, lanes over the row's entries.
@@ -694,11 +834,15 @@ void build_tiles(Csr& A) {
   std::vector<uint16_t> lidx((size_t)A.nnz + 64, 0);
   std::vector<BlockDesc>& all = A.h_blocks_all;
   const int nthreads = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  bool has_longrow = false;
   auto worker = [&](int tix) {
     for (size_t bi = tix; bi < nb; bi += nthreads) {
       BlockDesc& b = all[bi];
       b.ucount = 0;
-      if ((b.nrows_kind >> 16) == KIND_LONGROW) continue;
+      if ((b.nrows_kind >> 16) == KIND_LONGROW) {
+        has_longrow = true;  // (benign race: only ever set to true)
+        continue;
+      }
       int32_t* u = ubuf.data() + b.p0;
       const int32_t n = b.p1 - b.p0;
       std::copy(ci.begin() + b.p0, ci.begin() + b.p1, u);
@@ -727,7 +871,8 @@ void build_tiles(Csr& A) {
   }
   const int upad = (umax + 3) & ~3;
   // worth it only when columns are shared between the rows of a block, and the tile has to fit beside the stage
-  if (sum_nnz == 0 || (double)sum_u > 0.7 * (double)sum_nnz || tile_smem_bytes(A.nnz_cap, upad, KT) > 200 * 1024 || off > INT32_MAX - 64) {
+  if (has_longrow || sum_nnz == 0 || (double)sum_u > 0.7 * (double)sum_nnz || 2 * pipe_stage_bytes(A.nnz_cap, upad, KT) > 220 * 1024 ||
+      off > INT32_MAX - 64) {
     A.tile_state = -1;
     return;
   }
@@ -760,6 +905,16 @@ void launch_spmm_tile(const Csr& A, const BlockDesc* b, int32_t n_blocks, const 
                       double* y, int64_t ldy, int32_t k, double alpha, double beta, cudaStream_t stream) {
   constexpr int KT = 8;
   const int upad = (A.tile_umax + 3) & ~3;
+  static const int pipe = env_int("JP_SPMM_PIPE", 1);
+  if (pipe) {
+    const size_t smem = 2 * pipe_stage_bytes(A.nnz_cap, upad, KT);
+    set_smem_attr(spmm_pipe_kernel<KT, HALO>, smem);
+    const int grid = std::min<int>(n_blocks, ctx().sm_count);
+    spmm_pipe_kernel<KT, HALO><<<grid, kPipeThreads, smem, stream>>>(b, n_blocks, A.rowptr.as<int32_t>(), A.vals.as<double>(),
+                                                                      A.lidx.as<uint16_t>(), A.ucols.as<int32_t>(), x, ldx, halo, halo_k,
+                                                                      HALO ? A.n_local_cols : A.n_cols, y, ldy, k, A.nnz_cap, upad, alpha, beta);
+    return;
+  }
   const size_t smem = tile_smem_bytes(A.nnz_cap, upad, KT);
   set_smem_attr(spmm_tile_kernel<KT, HALO>, smem);
   spmm_tile_kernel<KT, HALO><<<n_blocks, kTileThreads, smem, stream>>>(b, A.rowptr.as<int32_t>(), A.colind.as<int32_t>(), A.vals.as<double>(),
