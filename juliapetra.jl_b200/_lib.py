@@ -104,6 +104,12 @@ def load():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
+        # not built yet (e.g. a fresh checkout: the .so is git-ignored): compile it; this needs nvcc, not a GPU
+        import shutil
+        import subprocess
+        if shutil.which("nvcc") and shutil.which("make"):
+            subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-j8"], check=False, capture_output=True)
+    if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(or `make -C juliapetra.jl_b200/csrc`). This backend has no CPU fallback.")

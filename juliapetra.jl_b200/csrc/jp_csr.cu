@@ -616,105 +616,135 @@ spmm_pipe_kernel(const BlockDesc* __restrict__ blocks, int32_t n_blocks, const i
   __syncthreads();
   const size_t stage_bytes = pipe_stage_bytes(cap, upad, KT);
   const int ntiles = (k + KT - 1) / KT;
-  int item = 0;  // the same sequence of items in both roles
-  for (int bi = blockIdx.x; bi < n_blocks; bi += gridDim.x) {
-    const BlockRange b = decode_block(blocks, bi);
-    const int4 aux = __ldg(reinterpret_cast<const int4*>(blocks + bi) + 1);
-    const int ucol0 = aux.x, U = aux.y;
-    const int al0 = b.p0 & ~7;
-    for (int vt = 0; vt < ntiles; ++vt, ++item) {
-      const int s = item & 1;
-      const unsigned ph = (item >> 1) & 1;
-      const int v0 = vt * KT;
-      const int kt = k - v0 < KT ? k - v0 : KT;
-      unsigned char* base = smem_raw + (size_t)s * stage_bytes;
-      double* s_val = reinterpret_cast<double*>(base);
+  const int my_blocks = blockIdx.x < n_blocks ? (n_blocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int total_items = my_blocks * ntiles;  // item = (row block, vector tile); the tiles of a block run back to back
+
+  // stage carve-up
+  auto s_val_of = [&](int s) { return reinterpret_cast<double*>(smem_raw + (size_t)s * stage_bytes); };
+
+  if (producer) {
+    const int ptid = tid - kPipeConsumers;
+    // the TMA of item it+1 is issued before the X tile of item it is gathered, so its latency is hidden
+    auto issue_tma = [&](int it) {
+      const int bi = blockIdx.x + (it / ntiles) * gridDim.x;
+      const BlockRange b = decode_block(blocks, bi);
+      const int4 aux = __ldg(reinterpret_cast<const int4*>(blocks + bi) + 1);
+      const int s = it & 1;
+      const unsigned ph = (it >> 1) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);  // the consumers are done with this stage (passes at once the first time)
+      double* s_val = s_val_of(s);
       double* xs = s_val + cap + 8;
       int32_t* s_rp = reinterpret_cast<int32_t*>(xs + (size_t)KT * upad);
       int32_t* s_ucol = s_rp + kMaxRowsPerBlock + 8;
       uint16_t* s_lidx = reinterpret_cast<uint16_t*>(s_ucol + upad);
-      if (producer) {
-        const int ptid = tid - kPipeConsumers;
-        mbar_wait(&empty_bar[s], ph ^ 1);  // the consumers have finished with this stage (passes at once the first time)
-        if (ptid == 0) {
-          const int ngrp = (b.p1 - b.a0 + 3) >> 2;
-          const int nl8 = (b.p1 - al0 + 7) & ~7;
-          const int ra0 = b.row0 & ~3;
-          const int nrp = (b.row0 + b.nrows + 1 - ra0 + 3) & ~3;
-          const int nu4 = (U + 3) & ~3;
-          const uint64_t pol = policy_evict_first();
-          mbar_expect_tx(&tma_bar[s], (unsigned)(ngrp * 32 + nl8 * 2 + nrp * 4 + nu4 * 4));
-          if (ngrp > 0) bulk_g2s(s_val, vals + b.a0, (unsigned)ngrp * 32, &tma_bar[s], pol);
-          if (nl8 > 0) bulk_g2s(s_lidx, lidx + al0, (unsigned)nl8 * 2, &tma_bar[s], pol);
-          bulk_g2s(s_rp, rowptr + ra0, (unsigned)nrp * 4, &tma_bar[s], pol);
-          if (nu4 > 0) bulk_g2s(s_ucol, ucols + ucol0, (unsigned)nu4 * 4, &tma_bar[s], pol);
-        }
-        mbar_wait(&tma_bar[s], ph);
-        // X tile: xs[j][u] = X[ucol[u], v0 + j]; two columns per thread per pass -> 2*KT loads in flight
-        for (int u0 = ptid; u0 < U; u0 += 2 * kPipeProducers) {
-          const int u1 = u0 + kPipeProducers;
-          const bool has1 = u1 < U;
-          const int c0 = s_ucol[u0], c1 = has1 ? s_ucol[u1] : c0;
-          double a0[KT], a1[KT];
-          if (HALO && (c0 >= nloc || c1 >= nloc)) {
+      const int al0 = b.p0 & ~7;
+      const int ngrp = (b.p1 - b.a0 + 3) >> 2;
+      const int nl8 = (b.p1 - al0 + 7) & ~7;
+      const int ra0 = b.row0 & ~3;
+      const int nrp = (b.row0 + b.nrows + 1 - ra0 + 3) & ~3;
+      const int nu4 = (aux.y + 3) & ~3;
+      const uint64_t pol = policy_evict_first();
+      mbar_expect_tx(&tma_bar[s], (unsigned)(ngrp * 32 + nl8 * 2 + nrp * 4 + nu4 * 4));
+      if (ngrp > 0) bulk_g2s(s_val, vals + b.a0, (unsigned)ngrp * 32, &tma_bar[s], pol);
+      if (nl8 > 0) bulk_g2s(s_lidx, lidx + al0, (unsigned)nl8 * 2, &tma_bar[s], pol);
+      bulk_g2s(s_rp, rowptr + ra0, (unsigned)nrp * 4, &tma_bar[s], pol);
+      if (nu4 > 0) bulk_g2s(s_ucol, ucols + aux.x, (unsigned)nu4 * 4, &tma_bar[s], pol);
+    };
+    if (ptid == 0 && total_items > 0) issue_tma(0);
+    for (int it = 0; it < total_items; ++it) {
+      if (ptid == 0 && it + 1 < total_items) issue_tma(it + 1);
+      const int bi = blockIdx.x + (it / ntiles) * gridDim.x;
+      const int4 aux = __ldg(reinterpret_cast<const int4*>(blocks + bi) + 1);
+      const int U = aux.y;
+      const int s = it & 1;
+      const unsigned ph = (it >> 1) & 1;
+      const int v0 = (it % ntiles) * KT;
+      const int kt = k - v0 < KT ? k - v0 : KT;
+      double* xs = s_val_of(s) + cap + 8;
+      const int32_t* s_ucol = reinterpret_cast<const int32_t*>(xs + (size_t)KT * upad) + kMaxRowsPerBlock + 8;
+      mbar_wait(&empty_bar[s], ph ^ 1);  // before overwriting xs of this stage
+      mbar_wait(&tma_bar[s], ph);        // the unique-column list has landed
+      // X tile: xs[j][u] = X[ucol[u], v0 + j]; four columns per thread per pass -> 4*KT loads in flight
+      for (int ub = ptid; ub < U; ub += 4 * kPipeProducers) {
+        int c[4];
+        double a[4][KT];
 #pragma unroll
-            for (int j = 0; j < KT; ++j) {
-              a0[j] = j < kt ? (c0 >= nloc ? halo[(size_t)(c0 - nloc) * halo_k + v0 + j] : __ldg(x + c0 + (size_t)(v0 + j) * ldx)) : 0.0;
-              a1[j] = j < kt ? (c1 >= nloc ? halo[(size_t)(c1 - nloc) * halo_k + v0 + j] : __ldg(x + c1 + (size_t)(v0 + j) * ldx)) : 0.0;
-            }
+        for (int q = 0; q < 4; ++q) {
+          const int u = ub + q * kPipeProducers;
+          c[q] = u < U ? s_ucol[u] : -1;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (c[q] < 0) continue;
+          if (HALO && c[q] >= nloc) {
+            const double* h = halo + (size_t)(c[q] - nloc) * halo_k + v0;
+#pragma unroll
+            for (int j = 0; j < KT; ++j) a[q][j] = j < kt ? h[j] : 0.0;
           } else {
-            const double* x0 = x + c0 + (size_t)v0 * ldx;
-            const double* x1 = x + c1 + (size_t)v0 * ldx;
+            const double* xc = x + c[q] + (size_t)v0 * ldx;
 #pragma unroll
-            for (int j = 0; j < KT; ++j) {
-              a0[j] = j < kt ? __ldg(x0 + (size_t)j * ldx) : 0.0;
-              a1[j] = j < kt ? __ldg(x1 + (size_t)j * ldx) : 0.0;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < KT; ++j) {
-            xs[(size_t)j * upad + u0] = a0[j];
-            if (has1) xs[(size_t)j * upad + u1] = a1[j];
+            for (int j = 0; j < KT; ++j) a[q][j] = j < kt ? __ldg(xc + (size_t)j * ldx) : 0.0;
           }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_bar[s]);
-      } else {
-        mbar_wait(&full_bar[s], ph);
-        mbar_wait(&tma_bar[s], ph);  // completed long ago; orders this thread after the bulk copies themselves
-        const int32_t* rp = s_rp + b.rpo;
-        int T = 1;
-        while (T < 4 && b.nrows * (T << 1) <= kPipeConsumers) T <<= 1;
-        const int lane_t = tid & (T - 1), group = tid / T, ngroups = kPipeConsumers / T;
-        for (int rbase = 0; rbase < b.nrows; rbase += ngroups) {  // warp-uniform trip count (shuffles below)
-          const int r = rbase + group;
-          const bool valid = r < b.nrows;
-          const int rs = valid ? rp[r] : 0, re = valid ? rp[r + 1] : 0;
-          double acc[KT];
 #pragma unroll
-          for (int j = 0; j < KT; ++j) acc[j] = 0.0;
-          for (int i = rs + lane_t; i < re; i += T) {
-            const int li = s_lidx[i - al0];
-            const double v = s_val[i - b.a0];
+        for (int q = 0; q < 4; ++q) {
+          if (c[q] < 0) continue;
+          const int u = ub + q * kPipeProducers;
 #pragma unroll
-            for (int j = 0; j < KT; ++j) acc[j] = fma(v, xs[(size_t)j * upad + li], acc[j]);
-          }
-          for (int o = T >> 1; o > 0; o >>= 1) {
-#pragma unroll
-            for (int j = 0; j < KT; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-          }
-          if (valid && lane_t == 0) {
-#pragma unroll
-            for (int j = 0; j < KT; ++j)
-              if (j < kt) {
-                double* yp = y + b.row0 + r + (size_t)(v0 + j) * ldy;
-                *yp = combine(beta == 0.0 ? 0.0 : *yp, acc[j], alpha, beta);
-              }
-          }
+          for (int j = 0; j < KT; ++j) xs[(size_t)j * upad + u] = a[q][j];
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);
+    }
+  } else {
+    for (int it = 0; it < total_items; ++it) {
+      const int bi = blockIdx.x + (it / ntiles) * gridDim.x;
+      const BlockRange b = decode_block(blocks, bi);
+      const int s = it & 1;
+      const unsigned ph = (it >> 1) & 1;
+      const int v0 = (it % ntiles) * KT;
+      const int kt = k - v0 < KT ? k - v0 : KT;
+      const int al0 = b.p0 & ~7;
+      const double* s_val = s_val_of(s);
+      const double* xs = s_val + cap + 8;
+      const int32_t* s_rp = reinterpret_cast<const int32_t*>(xs + (size_t)KT * upad);
+      const uint16_t* s_lidx = reinterpret_cast<const uint16_t*>(s_rp + kMaxRowsPerBlock + 8 + upad);
+      mbar_wait(&full_bar[s], ph);
+      mbar_wait(&tma_bar[s], ph);  // completed long ago; orders this thread after the bulk copies themselves
+      const int32_t* rp = s_rp + b.rpo;
+      int T = 1;
+      while (T < 4 && b.nrows * (T << 1) <= kPipeConsumers) T <<= 1;
+      const int lane_t = tid & (T - 1), group = tid / T, ngroups = kPipeConsumers / T;
+      for (int rbase = 0; rbase < b.nrows; rbase += ngroups) {  // warp-uniform trip count (shuffles below)
+        const int r = rbase + group;
+        const bool valid = r < b.nrows;
+        const int rs = valid ? rp[r] : 0, re = valid ? rp[r + 1] : 0;
+        double acc[KT];
+#pragma unroll
+        for (int j = 0; j < KT; ++j) acc[j] = 0.0;
+#pragma unroll 2
+        for (int i = rs + lane_t; i < re; i += T) {
+          const int li = s_lidx[i - al0];
+          const double v = s_val[i - b.a0];
+#pragma unroll
+          for (int j = 0; j < KT; ++j) acc[j] = fma(v, xs[(size_t)j * upad + li], acc[j]);
+        }
+        for (int o = T >> 1; o > 0; o >>= 1) {
+#pragma unroll
+          for (int j = 0; j < KT; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+        }
+        if (valid && lane_t == 0) {
+#pragma unroll
+          for (int j = 0; j < KT; ++j)
+            if (j < kt) {
+              double* yp = y + b.row0 + r + (size_t)(v0 + j) * ldy;
+              *yp = combine(beta == 0.0 ? 0.0 : *yp, acc[j], alpha, beta);
+            }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
   }
 }
