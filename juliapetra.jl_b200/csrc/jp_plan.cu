@@ -11,12 +11,15 @@
 //                         receives land directly in the halo buffer the boundary kernel reads)
 //   apply!                src/RowMatrix.jl:261-357
 //
-// Fused apply (NO_TRANS, plan whose remote LIDs are the contiguous tail of the column map, which is what
-// __makeColMap produces, src/CSRGraphInternalMethods.jl:946-981):
-//   comm stream   : wait(X ready) -> pack -> ncclGroup{recv halo, send boundary rows} -> boundary row blocks
-//                   (X + halo buffer) -> record(done)
-//   compute stream: interior row blocks (local columns only, read straight from X: the reference's full local
-//                   copy K8 is gone), concurrently -> wait(done)
+// apply! NO_TRANS with a plan whose remote LIDs are the contiguous tail of the column map (what __makeColMap
+// produces, src/CSRGraphInternalMethods.jl:946-981) never copies the local part of X (the reference's
+// copyAndPermute K8 is gone) and has three halo transports, chosen at run time:
+//   1. k == 1, peers IPC-mappable: ONE kernel (spmv_fused_halo_kernel, jp_csr.cu) = pack + NVLink peer stores +
+//      interior rows + flag wait + boundary rows + ack
+//   2. peer memory, two streams: comm   : wait(X ready) -> pack_p2p -> halo_wait -> boundary rows -> halo_ack -> record
+//                                compute: interior rows, concurrently -> wait(done)
+//   3. NCCL, two streams:        comm   : wait(X ready) -> pack -> ncclGroup{recv, send} -> boundary rows -> record
+// TRANS with a plan runs the exchange backwards with ADD (apply_trans_distributed).
 #include <cstdlib>
 
 #include "jp_common.h"

@@ -434,3 +434,49 @@ def test_spmm_shared_memory_tile_path(monkeypatch, k):
     y0 = synthetic.vector_block(1, n, k, seed=2)
     check_apply(A, x, y0, 3.0, 0.5, exact=False)
     check_apply(A, x, y0, 1.0, 0.0, exact=False)
+
+
+def test_full_size_7pt_256_properties_and_oracle():
+    """BASELINE configs[1] at full size on one GPU: size-independent properties, then the whole vector against the
+    oracle (bit-exact: every block of a stencil is thread-per-row in the reference's summation order)."""
+    N = 256
+    c, m, A = serial_matrix("7pt", N)
+    n = m.numMyElements()
+    assert n == N ** 3 and len(A.values) == 7 * N ** 3 - 6 * N ** 2
+    ones = jp.DenseMultiVector(m, np.ones((n, 1)))
+    Y = jp.DenseMultiVector(m, 1)
+    A.apply_(Y, ones)
+    rs = Y.data[:, 0].reshape((N, N, N))  # [k, j, i]
+    # row sums of the Dirichlet-truncated Laplacian = number of missing neighbours
+    idx = np.arange(N)
+    edge = ((idx == 0) | (idx == N - 1)).astype(np.float64)
+    expect = edge[:, None, None] + edge[None, :, None] + edge[None, None, :]
+    assert np.array_equal(rs, expect)
+    x = synthetic.vector_block(1, n, 1, seed=1)
+    z = synthetic.vector_block(1, n, 1, seed=2)
+    X, Z = jp.DenseMultiVector(m, x), jp.DenseMultiVector(m, z)
+    AX, AZ = jp.DenseMultiVector(m, 1), jp.DenseMultiVector(m, 1)
+    A.apply_(AX, X)
+    A.apply_(AZ, Z)
+    # symmetry: z.(A x) == x.(A z); linearity: A(2x - 3z) == 2 Ax - 3 Az
+    s1, s2 = Z.dot(AX)[0, 0], X.dot(AZ)[0, 0]
+    scale = 12.0 * np.abs(x).T @ np.abs(z)
+    assert abs(s1 - s2) <= 1e-12 * float(scale[0, 0]) + 1e-6 * 0 + 1e-9
+    W = jp.DenseMultiVector(m, 2.0 * x - 3.0 * z)
+    AW = jp.DenseMultiVector(m, 1)
+    A.apply_(AW, W)
+    comb = 2.0 * AX.data - 3.0 * AZ.data
+    assert np.abs(AW.data - comb).max() <= 1e-12 * 12 * 5
+    # the full vector against the oracle's localApply, alpha=3 beta=0.5
+    y0 = z.copy(order="F")
+    Yb = jp.DenseMultiVector(m, y0)
+    A.apply_(Yb, X, jp.NO_TRANS, 3.0, 0.5)
+    ref = O.local_apply_raw(y0, A.rowOffsets, A.localIndices1D, A.values, x, O.NO_TRANS, 3.0, 0.5)
+    assert np.array_equal(Yb.data, ref)
+    # norm / dot at n = 16.7M: the oracle's own sequential rounding error is ~sqrt(n)*eps, so anchor on per-vector
+    # partial agreement at 1e-12 of sum|x||y| and on the exact (math.fsum) value
+    import math
+    d = X.dot(Z)[0, 0]
+    exact = math.fsum((x[:, 0] * z[:, 0]).tolist())
+    assert abs(d - exact) <= 1e-12 * float((np.abs(x).T @ np.abs(z))[0, 0])
+    assert abs(d - O.dot_raw(x, z)[0]) <= 1e-11 * float((np.abs(x).T @ np.abs(z))[0, 0])
