@@ -91,7 +91,15 @@ __global__ void __launch_bounds__(kThreads) fill_kernel(double* __restrict__ y, 
 // y *= alpha  (rmul!, src/MultiVector.jl:63)
 __global__ void __launch_bounds__(kThreads) scale_kernel(double* __restrict__ y, int64_t n, double alpha) {
   const int64_t stride = (int64_t)gridDim.x * kThreads;
-  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) y[i] = __dmul_rn(y[i], alpha);
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {  // four independent loads in flight per thread
+    const double a0 = y[i], a1 = y[i + stride], a2 = y[i + 2 * stride], a3 = y[i + 3 * stride];
+    y[i] = __dmul_rn(a0, alpha);
+    y[i + stride] = __dmul_rn(a1, alpha);
+    y[i + 2 * stride] = __dmul_rn(a2, alpha);
+    y[i + 3 * stride] = __dmul_rn(a3, alpha);
+  }
+  for (; i < n; i += stride) y[i] = __dmul_rn(y[i], alpha);
 }
 
 // column v scaled by alpha[v]  (src/MultiVector.jl:72-77)
@@ -99,7 +107,15 @@ __global__ void __launch_bounds__(kThreads) scale_vec_kernel(double* __restrict_
   const double a = alpha[blockIdx.y];
   double* col = y + (size_t)blockIdx.y * n;
   const int64_t stride = (int64_t)gridDim.x * kThreads;
-  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) col[i] = __dmul_rn(col[i], a);
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    const double a0 = col[i], a1 = col[i + stride], a2 = col[i + 2 * stride], a3 = col[i + 3 * stride];
+    col[i] = __dmul_rn(a0, a);
+    col[i + stride] = __dmul_rn(a1, a);
+    col[i + 2 * stride] = __dmul_rn(a2, a);
+    col[i + 3 * stride] = __dmul_rn(a3, a);
+  }
+  for (; i < n; i += stride) col[i] = __dmul_rn(col[i], a);
 }
 
 // y = (a*x) + (b*y), unfused  (broadcast copyto!, src/MultiVector.jl:497-502)
