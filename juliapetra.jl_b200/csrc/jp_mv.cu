@@ -35,6 +35,15 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(const double* __restri
   double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
   const int64_t stride = (int64_t)gridDim.x * kThreads;
   int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (MODE == 1) {
+    // a single input stream: eight loads in flight per thread to cover the HBM latency
+    for (; i + 7 * stride < n; i += 8 * stride) {
+      const double x0 = xv[i], x1 = xv[i + stride], x2 = xv[i + 2 * stride], x3 = xv[i + 3 * stride];
+      const double x4 = xv[i + 4 * stride], x5 = xv[i + 5 * stride], x6 = xv[i + 6 * stride], x7 = xv[i + 7 * stride];
+      a0 += x0 * x0; a1 += x1 * x1; a2 += x2 * x2; a3 += x3 * x3;
+      a0 += x4 * x4; a1 += x5 * x5; a2 += x6 * x6; a3 += x7 * x7;
+    }
+  }
   for (; i + 3 * stride < n; i += 4 * stride) {
     double x0 = xv[i], x1 = xv[i + stride], x2 = xv[i + 2 * stride], x3 = xv[i + 3 * stride];
     if (MODE == 0) {
