@@ -480,3 +480,25 @@ def test_full_size_7pt_256_properties_and_oracle():
     exact = math.fsum((x[:, 0] * z[:, 0]).tolist())
     assert abs(d - exact) <= 1e-12 * float((np.abs(x).T @ np.abs(z))[0, 0])
     assert abs(d - O.dot_raw(x, z)[0]) <= 1e-11 * float((np.abs(x).T @ np.abs(z))[0, 0])
+
+
+@pytest.mark.parametrize("key,kind,size", [("7pt_64_serial", "7pt", 64), ("5pt_300_serial", "5pt", 300), ("27pt_20_serial", "27pt", 20)])
+def test_against_committed_golden_digests(key, kind, size):
+    """the CUDA path against tests/golden/fixtures.json (no oracle call): SHA-256 of the Float64 result of
+    apply!(Y, A, X, NO_TRANS, 3, 0.5) and of A*X must equal the committed digests; dot / norm within 1e-12"""
+    import hashlib
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fixtures.json")))[key]
+    dig = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    c, m, A = serial_matrix(kind, size)
+    n = m.numMyElements()
+    x = synthetic.vector_block(1, n, 1, seed=1)
+    y0 = synthetic.vector_block(1, n, 1, seed=2)
+    X, Y = jp.DenseMultiVector(m, x), jp.DenseMultiVector(m, y0)
+    A.apply_(Y, X, jp.NO_TRANS, 3.0, 0.5)
+    assert dig(Y.data) == g["apply_3_05_sha256"]
+    AX = A * X
+    assert dig(AX.data) == g["ax_sha256"]
+    assert abs(X.dot(AX)[0, 0] - g["dot_x_ax"]) <= 1e-12 * float(np.abs(x).T @ np.abs(AX.data))
+    assert abs(AX.norm(2)[0, 0] - g["norm2_ax"]) <= 1e-12 * g["norm2_ax"]

@@ -190,3 +190,48 @@ def test_no_cpu_fallback():
         pytest.skip("GPU present")
     with pytest.raises(jp.BackendError):
         jp.DenseMultiVector(jp.BlockMap(4, jp.SerialComm()), 1)
+
+
+# ---- committed golden fixtures (tests/golden/fixtures.json, generated from the oracle by make_fixtures.py) ----------
+def _fixtures():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fixtures.json")))
+
+
+def _digest(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_oracle_reproduces_committed_fixtures():
+    fx = _fixtures()
+    P, N = 4, 6
+    _, m, A = oracle_problem("7pt", N, P)
+    for pid in range(1, P + 1):
+        g = fx["7pt_6_P4"][str(pid)]
+        rp, ci, va = A.csr(pid)
+        assert (_digest(rp), _digest(ci), _digest(va)) == (g["rowptr_sha256"], g["colind_sha256"], g["vals_sha256"])
+        assert _digest(A.col_map.my_gids(pid)) == g["colMap_sha256"]
+        assert _digest(A.importer.field(pid, "remoteLIDs")) == g["remoteLIDs_sha256"]
+        assert _digest(A.importer.field(pid, "exportLIDs")) == g["exportLIDs_sha256"]
+        assert A.importer.distributor.field(pid, "procs_to").tolist() == g["procs_to"]
+
+
+@pytest.mark.parametrize("key,kind,size", [("7pt_64_serial", "7pt", 64), ("5pt_300_serial", "5pt", 300), ("27pt_20_serial", "27pt", 20)])
+def test_host_mirror_csr_feeds_the_committed_apply_digest(key, kind, size):
+    """the host mirror's CSR, pushed through the oracle's localApply, reproduces the committed digests (CPU check of
+    the inputs the GPU test consumes)"""
+    from jpetra_b200 import synthetic
+    g = _fixtures()[key]
+    c = jp.SerialComm()
+    m = jp.BlockMap(global_rows(kind, size), c)
+    A = synthetic.build_matrix(jp, m, kind, size, fill=False)
+    A._fillCompleteHost(m, m)
+    n = m.numMyElements()
+    assert (n, len(A.values)) == (g["n"], g["nnz"])
+    x = synthetic.vector_block(1, n, 1, seed=1)
+    y0 = synthetic.vector_block(1, n, 1, seed=2)
+    assert (_digest(x), _digest(y0)) == (g["x_sha256"], g["y0_sha256"])
+    y = O.local_apply_raw(y0.copy(order="F"), A.rowOffsets, A.localIndices1D, A.values, x, O.NO_TRANS, 3.0, 0.5)
+    assert _digest(y) == g["apply_3_05_sha256"]
