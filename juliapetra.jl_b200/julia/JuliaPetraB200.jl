@@ -103,6 +103,75 @@ function alltoallv(c::NCCLComm, send::Vector{T}, sendcounts::Vector{Int64}, recv
     recv
 end
 
+# ---- Distributor: NCCLDistributor replaces MPIDistributor (src/MPIDistributor.jl) behind src/Distributor.jl:10-41 ----
+# Same plan record and the same field values (they are bit-exact parity targets); what changes is how the plan is
+# learnt (one gatherAll of a P-vector of message lengths instead of Reduce+Scatter, ANY_SOURCE receives and
+# ready-sends, :205-251) and how host records move (one all-to-all-v instead of 2 handshakes + 4 barriers, :487-590).
+mutable struct NCCLDistributor{GID <: Integer, PID <: Integer, LID <: Integer} <: Distributor{GID, PID, LID}
+    comm::NCCLComm{GID, PID, LID}
+    lengths_to::Vector{Int64}; procs_to::Vector{PID}; indices_to::Vector{Int64}; starts_to::Vector{Int64}
+    lengths_from::Vector{Int64}; procs_from::Vector{PID}; starts_from::Vector{Int64}
+    numSends::Int64; numRecvs::Int64; selfMsg::Int64; totalRecvLength::Int64
+    posted::Union{Vector, Nothing}
+    planReverse::Union{NCCLDistributor{GID, PID, LID}, Nothing}
+end
+NCCLDistributor(comm::NCCLComm{GID, PID, LID}) where {GID, PID, LID} =
+    NCCLDistributor{GID, PID, LID}(comm, [], [], [], [], [], [], [], 0, 0, 0, 0, nothing, nothing)
+createDistributor(comm::NCCLComm) = NCCLDistributor(comm)
+
+function JuliaPetra.createFromSends(dist::NCCLDistributor{GID, PID, LID}, exportPIDs::AbstractArray{PID}) where {GID, PID, LID}
+    pid, nProcs = myPid(dist.comm), numProc(dist.comm)
+    counts = zeros(Int64, nProcs)                      # createSendStructure, src/MPIDistributor.jl:69-193
+    for p in exportPIDs; p >= 1 && (counts[p] += 1); end
+    grouped = all(exportPIDs[i] >= exportPIDs[i-1] for i in 2:length(exportPIDs))
+    dist.selfMsg = counts[pid] != 0
+    dist.procs_to = PID[p for p in 1:nProcs if counts[p] > 0]
+    dist.lengths_to = counts[dist.procs_to]
+    ndead = count(<(1), exportPIDs)
+    if grouped
+        dist.indices_to = Int64[]
+        dist.starts_to = (ndead + 1) .+ vcat(0, cumsum(dist.lengths_to)[1:end-1])
+    else
+        active = findall(>=(1), exportPIDs)
+        dist.indices_to = active[sortperm(exportPIDs[active])]
+        dist.starts_to = 1 .+ vcat(0, cumsum(dist.lengths_to)[1:end-1])
+    end
+    dist.numSends = length(dist.procs_to) - dist.selfMsg
+    sendLen = zeros(Int64, nProcs); sendLen[dist.procs_to] = dist.lengths_to   # computeRecvs, :196-273
+    M = reshape(gatherAll(dist.comm, sendLen), nProcs, nProcs)                # M[dst, src]
+    col = M[pid, :]
+    dist.procs_from = PID[q for q in 1:nProcs if col[q] > 0]
+    dist.lengths_from = col[dist.procs_from]
+    dist.starts_from = 1 .+ vcat(0, cumsum(dist.lengths_from)[1:end-1])
+    dist.totalRecvLength = sum(dist.lengths_from)
+    dist.numRecvs = length(dist.procs_from) - dist.selfMsg
+    dist.planReverse = nothing
+    dist.totalRecvLength
+end
+
+function JuliaPetra.createFromRecvs(dist::NCCLDistributor{GID, PID, LID}, remoteGIDs::AbstractArray{GID}, remotePIDs::AbstractArray{PID}) where {GID, PID, LID}
+    length(remoteGIDs) == length(remotePIDs) || throw(InvalidArgumentError("remote lists must be the same length"))
+    tmp = NCCLDistributor(dist.comm)                   # computeSends, :275-299
+    JuliaPetra.createFromSends(tmp, copy(remotePIDs))
+    exportObjs = JuliaPetra.resolve(tmp, [(Int64(g), Int64(myPid(dist.comm))) for g in remoteGIDs])
+    exportGIDs = GID[o[1] for o in exportObjs]; exportPIDs = PID[o[2] for o in exportObjs]
+    JuliaPetra.createFromSends(dist, exportPIDs)
+    exportGIDs, exportPIDs
+end
+
+function JuliaPetra.resolvePosts(dist::NCCLDistributor, exportObjs::AbstractVector{T}) where T   # :451-564
+    nProcs = numProc(dist.comm)
+    send = isempty(dist.indices_to) ? exportObjs[1:sum(dist.lengths_to)] : exportObjs[dist.indices_to]
+    sc = zeros(Int64, nProcs); sc[dist.procs_to] = dist.lengths_to
+    rc = zeros(Int64, nProcs); rc[dist.procs_from] = dist.lengths_from
+    dist.posted = alltoallv(dist.comm, Vector{T}(send), sc, rc)       # arrives in procs_from order (:582-589)
+    nothing
+end
+function JuliaPetra.resolveWaits(dist::NCCLDistributor)                                          # :568-590
+    dist.posted === nothing && throw(InvalidStateError("Cannot resolve waits when no posts have been made"))
+    r = dist.posted; dist.posted = nothing; r
+end
+
 # ---- DenseMultiVector storage on the device (src/DenseMultiVector.jl:6-60) -------------------------------------------
 # The reference documents createViews / createViewsNonConst / releaseViews as the hooks "to fetch data from ... GPU
 # into host memory" (src/DistObject.jl:260-284).  A device multivector keeps a handle and a lazily synchronised
