@@ -68,11 +68,16 @@ struct Context {
   size_t host_scratch_bytes = 0;
   void* flush_buf = nullptr;
   size_t flush_bytes = 0;
+  // host-mapped word the peer-to-peer halo kernels increment when a flag wait times out
+  unsigned long long* p2p_timeout_host = nullptr;
+  unsigned long long* p2p_timeout_dev = nullptr;
 };
 Context& ctx();
 void require_init();
 void* scratch(size_t bytes);
 void* host_scratch(size_t bytes);
+unsigned long long* p2p_timeout_flag_device();  // allocates the mapped word on first use
+void check_p2p_health();                        // throws JP_CUDA_ERROR when a peer-to-peer halo wait has timed out
 
 inline void count_launch(int n = 1) { ctx().launches.fetch_add(n, std::memory_order_relaxed); }
 

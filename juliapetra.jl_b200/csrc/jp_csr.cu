@@ -339,11 +339,8 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_fused_halo_kernel(const Fus
   const uint64_t epoch = a.h.epoch;
   if (bid < a.n_pack) {
     // ---- pack + send ----
-    if (tid < a.h.n_sends && epoch > 1) {  // back-pressure: the receiver consumed the previous halo
-      long long spins = 0;
-      while (ld_acquire_sys(a.h.sends[tid].ack_flag) + 1 < epoch && ++spins < kSpinLimit) {
-      }
-    }
+    if (tid < a.h.n_sends && epoch > 1)  // back-pressure: the receiver consumed the previous halo
+      wait_flag_ge(a.h.sends[tid].ack_flag, epoch - 1, a.h.timeout_flag);
     __syncthreads();
     const int64_t stride = (int64_t)a.n_pack * kSpmvThreads;
     for (int64_t i = (int64_t)bid * kSpmvThreads + tid; i < a.h.n_export; i += stride) {
@@ -366,11 +363,7 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_fused_halo_kernel(const Fus
     spmv_block<false, 1>(b, sv, &s_bar, s_red, a.rowptr, a.colind, a.vals, a.x, nullptr, a.nloc, a.y, a.alpha, a.beta);
   } else {
     // ---- boundary rows: wait for the neighbours' halos first ----
-    if (tid < a.h.n_sources) {
-      long long spins = 0;
-      while (ld_acquire_sys(a.h.sources[tid].ready_flag) < epoch && ++spins < kSpinLimit) {
-      }
-    }
+    if (tid < a.h.n_sources) wait_flag_ge(a.h.sources[tid].ready_flag, epoch, a.h.timeout_flag);
     __syncthreads();
     const StageView sv = stage_view(smem_raw, a.cap);
     const BlockRange b = decode_block(a.boundary, bid - a.n_pack - a.n_interior);

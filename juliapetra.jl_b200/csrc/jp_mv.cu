@@ -189,6 +189,7 @@ void finish_reduction(Comm& c, double* dev_out, int32_t k, double* host_out) {
   double* pinned = (double*)host_scratch((size_t)k * 8);
   JP_CUDA(cudaMemcpyAsync(pinned, dev_out, (size_t)k * 8, cudaMemcpyDeviceToHost, x.compute));
   JP_CUDA(cudaStreamSynchronize(x.compute));
+  check_p2p_health();
   std::memcpy(host_out, pinned, (size_t)k * 8);
 }
 
@@ -264,6 +265,7 @@ int32_t jp_mv_download(jp_handle mv, double* host) {
     JP_CUDA(cudaStreamSynchronize(ctx().comm));
     JP_CUDA(cudaMemcpyAsync(host, m->d(), bytes, cudaMemcpyDeviceToHost, ctx().compute));
     JP_CUDA(cudaStreamSynchronize(ctx().compute));
+    check_p2p_health();
   });
 }
 

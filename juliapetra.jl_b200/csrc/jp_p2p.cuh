@@ -16,7 +16,7 @@ struct P2PSource {
 };
 
 constexpr int kArenaFlagBytes = 4096;        // ready flags at [0, 2048), ack flags at [2048, 4096): 256 ranks max
-constexpr long long kSpinLimit = 1ll << 23;  // a few seconds; a peer that never shows up must not hang the GPU
+constexpr unsigned long long kSpinTimeoutNs = 20ull * 1000 * 1000 * 1000;  // a peer that never shows up must not hang the GPU
 
 __device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
   uint64_t v;
@@ -25,6 +25,24 @@ __device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
 }
 __device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+// spin until *flag >= want; after kSpinTimeoutNs give up and raise the host-visible timeout flag (mapped pinned
+// memory), which the host turns into an error at the next synchronising call -- never a silent wrong answer
+__device__ __forceinline__ void wait_flag_ge(const uint64_t* flag, uint64_t want, unsigned long long* timeout_flag) {
+  if (ld_acquire_sys(flag) >= want) return;
+  const unsigned long long t0 = global_timer_ns();
+  while (ld_acquire_sys(flag) < want) {
+    if (global_timer_ns() - t0 > kSpinTimeoutNs) {
+      atomicAdd_system(timeout_flag, 1ull);
+      return;
+    }
+  }
 }
 
 // everything the fused apply kernel needs besides the SpMV arguments
@@ -37,6 +55,7 @@ struct FusedHalo {
   int32_t n_sources;
   uint64_t epoch;           // this apply's epoch (host counter of the plan: applies are collective and in order)
   unsigned int* tickets;    // [0] pack blocks done, [1] boundary blocks done (each re-armed by its last block)
+  unsigned long long* timeout_flag;  // host-mapped; incremented when a flag wait gives up
 };
 
 }  // namespace jp

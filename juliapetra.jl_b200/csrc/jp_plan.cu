@@ -131,14 +131,11 @@ void exchange(Plan& p, int32_t k, bool reverse, cudaStream_t st) {
 // fused pack + send: dst[(i - start)*k + j] = src[lid[i] + j*ld] for every export entry i, into the receivers' buffers.
 __global__ void __launch_bounds__(kThreads) pack_p2p_kernel(const double* __restrict__ src, int64_t ld, const int32_t* __restrict__ lids,
                                                               int32_t n, int32_t k, const P2PSend* __restrict__ table, int32_t n_blocks,
-                                                              uint64_t epoch, unsigned int* __restrict__ ticket) {
+                                                              uint64_t epoch, unsigned int* __restrict__ ticket,
+                                                              unsigned long long* timeout_flag) {
   __shared__ bool is_last;
   // back-pressure: the receiver must have consumed the previous halo before its buffer is overwritten
-  if (threadIdx.x < n_blocks && epoch > 1) {
-    long long spins = 0;
-    while (ld_acquire_sys(table[threadIdx.x].ack_flag) + 1 < epoch && ++spins < kSpinLimit) {
-    }
-  }
+  if (threadIdx.x < n_blocks && epoch > 1) wait_flag_ge(table[threadIdx.x].ack_flag, epoch - 1, timeout_flag);
   __syncthreads();
   const int64_t total = (int64_t)n * k;
   const int64_t stride = (int64_t)gridDim.x * kThreads;
@@ -160,12 +157,9 @@ __global__ void __launch_bounds__(kThreads) pack_p2p_kernel(const double* __rest
 }
 
 // one warp: wait until every source has published this epoch's halo
-__global__ void halo_wait_kernel(const P2PSource* __restrict__ sources, int32_t n_sources, uint64_t epoch) {
-  if ((int)threadIdx.x < n_sources) {
-    long long spins = 0;
-    while (ld_acquire_sys(sources[threadIdx.x].ready_flag) < epoch && ++spins < kSpinLimit) {
-    }
-  }
+__global__ void halo_wait_kernel(const P2PSource* __restrict__ sources, int32_t n_sources, uint64_t epoch,
+                                 unsigned long long* timeout_flag) {
+  if ((int)threadIdx.x < n_sources) wait_flag_ge(sources[threadIdx.x].ready_flag, epoch, timeout_flag);
 }
 
 // one warp: tell every source that this epoch's halo has been consumed
@@ -456,10 +450,10 @@ const double* plan_post_p2p(Plan& p, const MultiVector& src) {
   // always launched: it also advances the epoch
   pack_p2p_kernel<<<grid_for((int64_t)p.n_export * k), kThreads, 0, x.comm>>>(src.d(), src.n, p.export_lids.as<int32_t>(), p.n_export, k,
                                                                              p.send_table.as<P2PSend>(), p.n_send_blocks, p.epoch,
-                                                                             p.p2p_tickets.as<unsigned int>());
+                                                                             p.p2p_tickets.as<unsigned int>(), p2p_timeout_flag_device());
   JP_LAUNCH_CHECK();
   if (p.n_sources > 0) {
-    halo_wait_kernel<<<1, 32, 0, x.comm>>>(p.wait_table.as<P2PSource>(), p.n_sources, p.epoch);
+    halo_wait_kernel<<<1, 32, 0, x.comm>>>(p.wait_table.as<P2PSource>(), p.n_sources, p.epoch, p2p_timeout_flag_device());
     JP_LAUNCH_CHECK();
   }
   return reinterpret_cast<const double*>((const char*)p.arena.p + kArenaFlagBytes);
@@ -551,6 +545,7 @@ void apply_no_trans(Csr* a, Plan* p, MultiVector* y, MultiVector* x, double alph
       h.n_sources = p->n_sources;
       h.epoch = ++p->epoch;
       h.tickets = p->p2p_tickets.as<unsigned int>();
+      h.timeout_flag = p2p_timeout_flag_device();
       const double* halo = reinterpret_cast<const double*>(static_cast<const char*>(p->arena.p) + kArenaFlagBytes);
       launch_spmv_fused(*a, h, x->d(), halo, y->d(), alpha, beta, c.compute);
       return;
@@ -816,6 +811,7 @@ int32_t jp_apply_host(jp_handle comm, jp_handle A, jp_handle plan, const double*
       apply_impl(a, p, y, x, mode, alpha, beta);
       if (yb) JP_CUDA(cudaMemcpyAsync(y_host, y->d(), yb, cudaMemcpyDeviceToHost, c.compute));
       JP_CUDA(cudaStreamSynchronize(c.compute));
+      check_p2p_health();
       return;
     }
     // Pipelined single-GPU path: PCIe is full duplex, so X goes up in row chunks on one stream, each chunk of row

@@ -46,6 +46,24 @@ void* host_scratch(size_t bytes) {
   return c.host_scratch;
 }
 
+unsigned long long* p2p_timeout_flag_device() {
+  Context& c = ctx();
+  if (!c.p2p_timeout_host) {
+    JP_CUDA(cudaHostAlloc((void**)&c.p2p_timeout_host, 64, cudaHostAllocMapped));
+    *c.p2p_timeout_host = 0;
+    JP_CUDA(cudaHostGetDevicePointer((void**)&c.p2p_timeout_dev, c.p2p_timeout_host, 0));
+  }
+  return c.p2p_timeout_dev;
+}
+
+void check_p2p_health() {
+  Context& c = ctx();
+  if (c.p2p_timeout_host && *reinterpret_cast<volatile unsigned long long*>(c.p2p_timeout_host) != 0) {
+    *c.p2p_timeout_host = 0;
+    fail(JP_CUDA_ERROR, "peer-to-peer halo exchange timed out waiting for a neighbour rank (20 s): results of the last apply! are invalid");
+  }
+}
+
 // ---- registry -------------------------------------------------------------------------------------
 static std::mutex g_reg_mu;
 static std::unordered_map<jp_handle, std::unique_ptr<Object>> g_objects;
@@ -168,6 +186,8 @@ int32_t jp_finalize(void) {
     if (c.scratch) cudaFree(c.scratch);
     if (c.host_scratch) cudaFreeHost(c.host_scratch);
     if (c.flush_buf) cudaFree(c.flush_buf);
+    if (c.p2p_timeout_host) cudaFreeHost(c.p2p_timeout_host);
+    c.p2p_timeout_host = c.p2p_timeout_dev = nullptr;
     c.scratch = c.host_scratch = c.flush_buf = nullptr;
     c.scratch_bytes = c.host_scratch_bytes = c.flush_bytes = 0;
     cudaEventDestroy(c.ev_x_ready);
@@ -199,6 +219,7 @@ int32_t jp_synchronize(void) {
     JP_CUDA(cudaStreamSynchronize(ctx().comm));
     JP_CUDA(cudaStreamSynchronize(ctx().compute));
     JP_CUDA(cudaStreamSynchronize(ctx().copy));
+    check_p2p_health();
   });
 }
 
@@ -265,6 +286,8 @@ int32_t jp_flush_l2(int64_t bytes) {
     size_t want = bytes > 0 ? (size_t)bytes : (size_t)256 << 20;
     if (want > c.flush_bytes) {
       if (c.flush_buf) cudaFree(c.flush_buf);
+    if (c.p2p_timeout_host) cudaFreeHost(c.p2p_timeout_host);
+    c.p2p_timeout_host = c.p2p_timeout_dev = nullptr;
       JP_CUDA(cudaMalloc(&c.flush_buf, want));
       c.flush_bytes = want;
     }
