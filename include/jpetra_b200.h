@@ -138,7 +138,9 @@ int32_t jp_transfer_wait(jp_handle plan);
  * (n_cols rows) for NO_TRANS, a row-map one for TRANS. */
 int32_t jp_local_apply(jp_handle Y, jp_handle A, jp_handle X, int32_t mode, double alpha, double beta);
 /* apply!(Y, A, X, mode, alpha, beta), src/RowMatrix.jl:261-357, with the Import halo (plan, or 0 when the
- * importer is `nothing`) overlapped with the interior rows.  X is a domain-map MultiVector. */
+ * importer is `nothing`) inside or overlapped with the interior rows.  NO_TRANS: X on the domain map, Y on the row
+ * map.  TRANS / CONJ_TRANS: X on the row map, Y on the domain map; with a plan the exchange runs backwards and ADDs
+ * (the semantics of src/RowMatrix.jl:324-352, i.e. Tpetra's applyTranspose).  Collective over the plan's comm. */
 int32_t jp_apply(jp_handle comm, jp_handle Y, jp_handle A, jp_handle X, jp_handle plan, int32_t mode, double alpha,
                  double beta);
 /* the same call with HOST buffers (what a Julia caller holding Array{Float64,2} makes): uploads X, applies,
