@@ -500,5 +500,5 @@ def test_against_committed_golden_digests(key, kind, size):
     assert dig(Y.data) == g["apply_3_05_sha256"]
     AX = A * X
     assert dig(AX.data) == g["ax_sha256"]
-    assert abs(X.dot(AX)[0, 0] - g["dot_x_ax"]) <= 1e-12 * float(np.abs(x).T @ np.abs(AX.data))
+    assert abs(X.dot(AX)[0, 0] - g["dot_x_ax"]) <= 1e-12 * float((np.abs(x).T @ np.abs(AX.data))[0, 0])
     assert abs(AX.norm(2)[0, 0] - g["norm2_ax"]) <= 1e-12 * g["norm2_ax"]
