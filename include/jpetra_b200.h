@@ -97,6 +97,19 @@ int32_t jp_csr_info(jp_handle A, int64_t* info);
 /* read the device copy back (0-based) -- parity tests */
 int32_t jp_csr_download(jp_handle A, int32_t* rowptr, int32_t* colind, double* vals);
 
+/* fillComplete on the device for a CONTIGUOUS domain map (src/CSRMatrix.jl:706-747): __makeColMap
+ * (src/CSRGraphInternalMethods.jl:852-982; remote GIDs ordered by owner PID, then GID), makeIndicesLocal (:636-712),
+ * sortAndMergeIndicesAndValues (src/CSRMatrix.jl:549-606; duplicates summed in insertion order) and
+ * fillLocalGraphAndMatrix (:403-484).  entry_ptr[n_rows+1] are 0-based offsets of every row's entries in insertion
+ * order, col_gids / vals the entries; [min_all_gid, max_all_gid] is the domain map's global id range and the calling
+ * rank owns dom_num_my ids from dom_min_gid.  info[4] = columns of the column map, used local columns, numSameIDs of
+ * Import(domainMap, colMap), nnz after the merge.  The result is an ordinary CSR handle (n_local_cols = numSameIDs). */
+int32_t jp_csr_fill_complete(int32_t n_rows, const int64_t* entry_ptr, const int64_t* col_gids, const double* vals,
+                             int64_t min_all_gid, int64_t max_all_gid, int64_t dom_min_gid, int32_t dom_num_my,
+                             jp_handle* out, int64_t* info);
+/* GIDs of the column map in LID order (n_cols of them) of a matrix made by jp_csr_fill_complete */
+int32_t jp_csr_col_map(jp_handle A, int64_t* gids);
+
 /* ---- DenseMultiVector storage (src/DenseMultiVector.jl:6-60) and the MultiVector
  *      kernels (src/MultiVector.jl:52-161) -------------------------------------------- */
 int32_t jp_mv_create(int32_t n_local, int32_t k, jp_handle* out);           /* zero-filled */

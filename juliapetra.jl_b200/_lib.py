@@ -55,6 +55,8 @@ PROTOTYPES = {
     "jp_csr_destroy": [c_i64],
     "jp_csr_info": [c_i64, c_vp],
     "jp_csr_download": [c_i64, c_vp, c_vp, c_vp],
+    "jp_csr_fill_complete": [c_i32, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i32, P(c_i64), c_vp],
+    "jp_csr_col_map": [c_i64, c_vp],
     "jp_mv_create": [c_i32, c_i32, P(c_i64)],
     "jp_mv_destroy": [c_i64],
     "jp_mv_shape": [c_i64, P(c_i32), P(c_i32)],

@@ -38,6 +38,7 @@ class BlockMap:
         self.minAllGID_ = self.maxAllGID_ = self.minMyGID_ = self.maxMyGID_ = 0
         self.minLID_ = self.maxLID_ = 0
         self.linearMap_ = False
+        self.contiguousByPid_ = False  # GIDs ascend with the owner PID (uniform / user-linear constructors)
         self.distributedGlobal_ = False
         self.oneToOneIsDetermined = False
         self.oneToOne = False
@@ -52,6 +53,7 @@ class BlockMap:
         self._blank(N, comm)
         P = comm.numProc()
         self.linearMap_ = True
+        self.contiguousByPid_ = True
         myPIDVal = comm.myPid() - 1
         numMy = N // P
         remainder = N % P
@@ -76,6 +78,7 @@ class BlockMap:
         self._blank(N, comm)
         self.numMyElements_ = numMy
         self.linearMap_ = True
+        self.contiguousByPid_ = True
         self.distributedGlobal_ = self._isDistributedGlobal(N, numMy)
         if not self.distributedGlobal_ or comm.numProc() == 1:
             self.numGlobalElements_ = numMy

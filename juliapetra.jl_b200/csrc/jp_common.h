@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
@@ -87,6 +88,15 @@ inline void count_launch(int n = 1) { ctx().launches.fetch_add(n, std::memory_or
     JP_CUDA(cudaGetLastError());     \
   } while (0)
 
+// Kernels that live in *_kernels.cuh headers are written so that tests/cuda_emul can execute the same source on the
+// CPU; these two macros are the only launch-side syntax that differs between the two builds.
+#define JP_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#define JP_KLAUNCH(kernel, grid, block, smem, stream, ...)         \
+  do {                                                             \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);    \
+    JP_LAUNCH_CHECK();                                             \
+  } while (0)
+
 // ---- handle registry ------------------------------------------------------------------------
 enum class Kind : int { Comm = 1, Csr, MultiVector, Plan, Event };
 
@@ -142,6 +152,10 @@ struct DeviceBuffer {
     p = nullptr;
     bytes = 0;
   }
+  void swap(DeviceBuffer& o) {
+    std::swap(p, o.p);
+    std::swap(bytes, o.bytes);
+  }
   template <class T>
   T* as() const { return static_cast<T*>(p); }
 };
@@ -193,6 +207,8 @@ struct Csr : Object {
   // cache of the column-map multivector (A.importMV, src/CSRMatrix.jl:10,772-781); only used when the column
   // map is not [domain prefix | remote tail] and the fused apply path does not apply
   std::unique_ptr<MultiVector> import_mv;
+  // GIDs of the column map in LID order, kept when the matrix was fill-completed on the device (jp_csr_fill_complete)
+  DeviceBuffer colmap_gids;
   // host-buffer path (jp_apply_host): the all-blocks list cut into chunks; chunk c covers blocks
   // [chunk_block[c], chunk_block[c+1]) = rows [chunk_row[c], chunk_row[c+1]) and reads columns <= chunk_maxcol[c]
   // (prefix maximum), so its kernel can start as soon as that much of X has been uploaded
@@ -256,6 +272,7 @@ void launch_spmv(const Csr& A, const DeviceBuffer& blocks, int32_t n_blocks, boo
                  cudaStream_t stream);
 void launch_spmv_trans(const Csr& A, const double* x, int64_t ldx, double* y, int64_t ldy, int32_t ny, int32_t k, double alpha,
                        double beta, cudaStream_t stream);
+void csr_finalize_structure(Csr& A, const std::vector<int32_t>& rp, const std::vector<int32_t>& rowmax);
 void launch_scale_fill(double* y, int64_t n, double beta, cudaStream_t stream);  // y = beta==0 ? 0 : beta*y
 void plan_ensure_buffers(Plan& p, int32_t k);
 void plan_post(Plan& p, const MultiVector& src, MultiVector* tgt, bool halo_only, int32_t combine_mode, bool reverse);

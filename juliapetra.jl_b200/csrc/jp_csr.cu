@@ -1032,6 +1032,49 @@ void launch_spmv_trans(const Csr& A, const double* x, int64_t ldx, double* y, in
   JP_LAUNCH_CHECK();
 }
 
+
+// Row blocks, SpMM lanes per row and the host-path chunk table from the row pointers and every row's largest column
+// (rowmax[r] = -1 for an empty row).  Shared by jp_csr_create (host arrays) and jp_csr_fill_complete (device arrays).
+void csr_finalize_structure(Csr& A, const std::vector<int32_t>& rp, const std::vector<int32_t>& rowmax) {
+  const int32_t n_rows = A.n_rows;
+  std::vector<uint8_t> cls((size_t)n_rows, 0);
+  int32_t maxlen = 0;
+  for (int32_t r = 0; r < n_rows; ++r) {
+    cls[r] = rowmax[r] >= A.n_local_cols;
+    maxlen = std::max(maxlen, rp[r + 1] - rp[r]);
+  }
+  A.max_row_len = maxlen;
+  const double mean = n_rows ? (double)A.nnz / n_rows : 0.0;
+  // SpMM lanes per row from the mean row length (power of two)
+  int T = 1;
+  while (T < 32 && mean > 12.0 * T) T <<= 1;
+  T = env_int("JP_SPMM_T", T);
+  JP_REQUIRE(T >= 1 && T <= 32 && (T & (T - 1)) == 0, "JP_SPMM_T must be a power of two in [1,32]");
+  A.threads_per_row = T;
+  int cap = env_int("JP_SPMV_CAP", 2048);
+  JP_REQUIRE(cap >= 256 && cap <= 16384 && cap % 4 == 0, "JP_SPMV_CAP must be a multiple of 4 in [256,16384]");
+  A.nnz_cap = cap;
+  int max_rows = env_int("JP_SPMV_ROWS", kSpmvThreads);
+  JP_REQUIRE(max_rows >= 1 && max_rows <= kMaxRowsPerBlock, "JP_SPMV_ROWS must be in [1,512]");
+  std::vector<BlockDesc>&bi = A.h_blocks_interior, &bb = A.h_blocks_boundary, &ba = A.h_blocks_all;
+  build_blocks(rp, cls, cap, max_rows, env_int("JP_SPMV_DIRECT", 1) != 0, bi, bb, ba);
+  upload_blocks(bi, A.blocks_interior, A.n_blocks_interior);
+  upload_blocks(bb, A.blocks_boundary, A.n_blocks_boundary);
+  upload_blocks(ba, A.blocks_all, A.n_blocks_all);
+  // chunks of the all-blocks list for the pipelined host-buffer path
+  const int nchunks = std::max(1, std::min<int>(env_int("JP_HOST_CHUNKS", 16), (int)ba.size()));
+  int32_t run = -1;
+  for (int c = 0; c <= nchunks; ++c) {
+    const int32_t bidx = (int32_t)((int64_t)ba.size() * c / nchunks);
+    A.chunk_block.push_back(bidx);
+    A.chunk_row.push_back(bidx < (int32_t)ba.size() ? ba[bidx].row0 : n_rows);
+  }
+  for (int c = 0; c < nchunks; ++c) {
+    for (int32_t r = A.chunk_row[c]; r < A.chunk_row[c + 1]; ++r) run = std::max(run, rowmax[r]);
+    A.chunk_maxcol.push_back(run);
+  }
+}
+
 }  // namespace jp
 
 using namespace jp;
@@ -1062,9 +1105,7 @@ int32_t jp_csr_create(int32_t n_rows, int32_t n_cols, int32_t n_local_cols, int6
       if (r > 0) JP_REQUIRE(rp[r] >= rp[r - 1], "jp_csr_create: rowptr must be non-decreasing");
     }
     JP_REQUIRE(rp[n_rows] == nnz, "jp_csr_create: rowptr[last] does not match nnz");
-    std::vector<uint8_t> cls((size_t)n_rows, 0);
     std::vector<int32_t> rowmax((size_t)n_rows, -1);
-    int32_t maxlen = 0;
     for (int32_t r = 0; r < n_rows; ++r) {
       int32_t mx = -1;
       for (int32_t i = rp[r]; i < rp[r + 1]; ++i) {
@@ -1072,41 +1113,9 @@ int32_t jp_csr_create(int32_t n_rows, int32_t n_cols, int32_t n_local_cols, int6
         JP_REQUIRE(c >= 0 && c < n_cols, "jp_csr_create: column index outside the column map");
         mx = c > mx ? c : mx;
       }
-      cls[r] = mx >= n_local_cols;
       rowmax[r] = mx;
-      maxlen = std::max(maxlen, rp[r + 1] - rp[r]);
     }
-    A->max_row_len = maxlen;
-    const double mean = n_rows ? (double)nnz / n_rows : 0.0;
-    // SpMM lanes per row from the mean row length (power of two)
-    int T = 1;
-    while (T < 32 && mean > 12.0 * T) T <<= 1;
-    T = env_int("JP_SPMM_T", T);
-    JP_REQUIRE(T >= 1 && T <= 32 && (T & (T - 1)) == 0, "JP_SPMM_T must be a power of two in [1,32]");
-    A->threads_per_row = T;
-    int cap = env_int("JP_SPMV_CAP", 2048);
-    JP_REQUIRE(cap >= 256 && cap <= 16384 && cap % 4 == 0, "JP_SPMV_CAP must be a multiple of 4 in [256,16384]");
-    A->nnz_cap = cap;
-    int max_rows = env_int("JP_SPMV_ROWS", kSpmvThreads);
-    JP_REQUIRE(max_rows >= 1 && max_rows <= kMaxRowsPerBlock, "JP_SPMV_ROWS must be in [1,512]");
-    std::vector<BlockDesc>&bi = A->h_blocks_interior, &bb = A->h_blocks_boundary, &ba = A->h_blocks_all;
-    build_blocks(rp, cls, cap, max_rows, env_int("JP_SPMV_DIRECT", 1) != 0, bi, bb, ba);
-    upload_blocks(bi, A->blocks_interior, A->n_blocks_interior);
-    upload_blocks(bb, A->blocks_boundary, A->n_blocks_boundary);
-    upload_blocks(ba, A->blocks_all, A->n_blocks_all);
-    {  // chunks of the all-blocks list for the pipelined host-buffer path
-      const int nchunks = std::max(1, std::min<int>(env_int("JP_HOST_CHUNKS", 16), (int)ba.size()));
-      int32_t run = -1;
-      for (int c = 0; c <= nchunks; ++c) {
-        const int32_t bidx = (int32_t)((int64_t)ba.size() * c / nchunks);
-        A->chunk_block.push_back(bidx);
-        A->chunk_row.push_back(bidx < (int32_t)ba.size() ? ba[bidx].row0 : n_rows);
-      }
-      for (int c = 0; c < nchunks; ++c) {
-        for (int32_t r = A->chunk_row[c]; r < A->chunk_row[c + 1]; ++r) run = std::max(run, rowmax[r]);
-        A->chunk_maxcol.push_back(run);
-      }
-    }
+    csr_finalize_structure(*A, rp, rowmax);
     // device arrays; 64 elements of zeroed slack so the 16-byte staging may over-read past nnz
     A->rowptr.alloc(((size_t)n_rows + 1 + 16) * 4);  // slack: row pointers are staged in aligned groups of 4
     JP_CUDA(cudaMemset(A->rowptr.p, 0, ((size_t)n_rows + 1 + 16) * 4));

@@ -11,12 +11,13 @@ from __future__ import annotations
 
 import ctypes as C
 import enum
+import os
 
 import numpy as np
 
 from . import _lib
 from .blockmap import BlockMap
-from .errors import InvalidArgumentError, InvalidStateError
+from .errors import BackendError, InvalidArgumentError, InvalidStateError
 from .importexport import Export, Import
 from .multivector import DenseMultiVector
 from .utils import computeOffsets
@@ -64,8 +65,10 @@ class CSRMatrix:
         self.importer = self.exporter = None
         self._fillComplete = False
         self.h = None  # device CSR
-        # packed local CSR after fillComplete (1-based, like LocalCSRGraph/LocalCSRMatrix)
-        self.rowOffsets = self.localIndices1D = self.values = None
+        # packed local CSR after fillComplete (1-based, like LocalCSRGraph/LocalCSRMatrix); after a device
+        # fillComplete the host copy is downloaded on first use
+        self._csr_host = None
+        self._nnz = 0
 
     def __del__(self):
         try:
@@ -137,18 +140,104 @@ class CSRMatrix:
         return self.rowMap.numMyElements()
 
     def getLocalNumEntries(self):
-        return int(self._numRowEntries.sum()) if not self._fillComplete else len(self.values)
+        return int(self._numRowEntries.sum()) if not self._fillComplete else self._nnz
+
+    def _host_csr(self):
+        if self._csr_host is None and self._fillComplete and self.h:
+            n = self.getLocalNumRows()
+            rp = np.empty(n + 1, dtype=np.int32)
+            ci = np.empty(self._nnz, dtype=np.int32)
+            va = np.empty(self._nnz, dtype=np.float64)
+            _lib.check(_lib.lib().jp_csr_download(self.h, _lib.ptr(rp), _lib.ptr(ci), _lib.ptr(va)))
+            self._csr_host = (rp + 1, ci + 1, va)
+        return self._csr_host
+
+    @property
+    def rowOffsets(self):
+        c = self._host_csr()
+        return None if c is None else c[0]
+
+    @property
+    def localIndices1D(self):
+        c = self._host_csr()
+        return None if c is None else c[1]
+
+    @property
+    def values(self):
+        c = self._host_csr()
+        return None if c is None else c[2]
 
     def getLocalRowCopy(self, localRow: int):
         s, e = self.rowOffsets[localRow - 1] - 1, self.rowOffsets[localRow] - 1
         return self.localIndices1D[s:e].copy(), self.values[s:e].copy()
 
     # ---- fillComplete ----
-    def fillComplete(self, domainMap: BlockMap | None = None, rangeMap: BlockMap | None = None, **plist):
-        """fillComplete(matrix[, domainMap, rangeMap]) -- src/CSRMatrix.jl:706-747; then the device upload."""
+    def fillComplete(self, domainMap: BlockMap | None = None, rangeMap: BlockMap | None = None, device: bool | None = None, **plist):
+        """fillComplete(matrix[, domainMap, rangeMap]) -- src/CSRMatrix.jl:706-747.
+        device=False: column map / remap / sort+merge / pack in numpy on the host, then the upload (jp_csr_create).
+        device=True (or JP_FILL=device): the entries are uploaded and the same steps run as CUDA kernels
+        (jp_csr_fill_complete); needs a contiguous domain map, otherwise the host path is taken.  Both give
+        bit-identical column maps, local indices and values."""
+        if device is None:
+            device = os.environ.get("JP_FILL", "host") == "device"
+        dom = domainMap if domainMap is not None else self.rowMap
+        if device and self.colMap is None and getattr(dom, "contiguousByPid_", False) and self._fillCompleteDevice(domainMap, rangeMap):
+            return self
         self._fillCompleteHost(domainMap, rangeMap)
         self._upload()
         return self
+
+    def _fillCompleteDevice(self, domainMap=None, rangeMap=None) -> bool:
+        """Device fillComplete; False when the serial colMap == domMap special case of the reference
+        (src/CSRGraphInternalMethods.jl:918-925) applies to a non-square matrix, which the host path handles."""
+        if self._fillComplete:
+            raise InvalidStateError("Matrix cannot be fill complete when fillComplete(...) is called")
+        dom = domainMap if domainMap is not None else self.rowMap
+        comm = self.comm
+        ptr0, gcols, vals = self._packed_global()
+        ptr0, gcols, vals = _lib.as_i64(ptr0), _lib.as_i64(gcols), _lib.as_f64(vals)
+        n_rows, n_dom = self.getLocalNumRows(), dom.numMyElements()
+        h, info = C.c_int64(), np.zeros(4, dtype=np.int64)
+        error = False
+        try:
+            _lib.check(_lib.lib().jp_csr_fill_complete(n_rows, _lib.ptr(ptr0), _lib.ptr(gcols), _lib.ptr(vals), dom.minAllGID(), dom.maxAllGID(),
+                                                       dom.minMyGID() if n_dom else dom.minAllGID(), n_dom, C.byref(h), _lib.ptr(info)))
+        except InvalidArgumentError:
+            error = True  # a column GID nobody owns: remotePIDs == 0 in the reference (:936-939)
+        n_cols, n_local_used, n_same, nnz = (int(v) for v in info)
+        serial = comm.numProc() == 1
+        if not error and serial and n_cols > n_local_used:
+            error = True  # remote GIDs on one process, :918-921
+        if bool(comm.maxAllScalar(int(error))):
+            if h.value:
+                _lib.lib().jp_csr_destroy(h.value)
+            raise RuntimeError("makeColMap reports an error on at least one process")
+        if serial and n_local_used == n_rows and n_local_used != n_dom:
+            _lib.lib().jp_csr_destroy(h.value)
+            return False
+        self.domainMap = dom
+        self.rangeMap = rangeMap if rangeMap is not None else self.rowMap
+        if serial and n_local_used == n_rows:
+            self.colMap = dom  # :922-924
+        else:
+            gids = np.empty(n_cols, dtype=np.int64)
+            _lib.check(_lib.lib().jp_csr_col_map(h.value, _lib.ptr(gids)))
+            self.colMap = BlockMap(dom.numGlobalElements(), gids, comm)  # :981
+        if not self.domainMap.sameAs(self.colMap):
+            self.importer = Import(self.domainMap, self.colMap)
+        if not self.rangeMap.sameAs(self.rowMap):
+            self.exporter = Export(self.rowMap, self.rangeMap)
+        expect_same = self.importer.numSameIDs() if self.importer is not None else n_cols
+        if expect_same != n_same:
+            _lib.lib().jp_csr_destroy(h.value)
+            raise BackendError(f"device fillComplete: numSameIDs {n_same} disagrees with the Import ({expect_same})")
+        self.h = h.value
+        self._nnz = nnz
+        self._globalIndices1D = self._values = None
+        self._fillComplete = True
+        if self.importer is not None:
+            self.importer.device_plan()
+        return True
 
     def _packed_global(self):
         """entries actually inserted, row by row in insertion order: (ptr0, gcols, vals)"""
@@ -260,9 +349,8 @@ class CSRMatrix:
         # fillLocalGraphAndMatrix, src/CSRMatrix.jl:403-484: packed 1-based CSR with LID (int32) indices
         if len(lcols) and (len(lcols) >= 2**31 - 64 or self.colMap.numMyElements() >= 2**31 - 1):
             raise InvalidArgumentError("local matrix does not fit Int32 LIDs")
-        self.rowOffsets = (ptr0 + 1).astype(np.int32)
-        self.localIndices1D = lcols.astype(np.int32)
-        self.values = np.ascontiguousarray(vals, dtype=np.float64)
+        self._csr_host = ((ptr0 + 1).astype(np.int32), lcols.astype(np.int32), np.ascontiguousarray(vals, dtype=np.float64))
+        self._nnz = len(self._csr_host[2])
         self._globalIndices1D = self._values = None
         self._fillComplete = True
 

@@ -1,0 +1,56 @@
+"""ctypes loader of tests/cuda_emul/_build/libjp_emul.so: the product's *_kernels.cuh and *_pipeline.h compiled for the
+CPU execution model of tests/cuda_emul/cuda_emul.h.  TEST INFRASTRUCTURE ONLY (imported by tests/test_emul_*.py)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cuda_emul")
+_lib = None
+
+
+class EmulError(Exception):
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        subprocess.run(["make", "-C", _DIR], check=True, capture_output=True)
+        L = C.CDLL(os.path.join(_DIR, "_build", "libjp_emul.so"))
+        L.emul_last_error.restype = C.c_char_p
+        L.emul_launch_count.restype = C.c_uint64
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise EmulError(rc, lib().emul_last_error().decode())
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def fill_complete(entry_ptr, gids, vals, gmin, gmax, dom_min, dom_n):
+    """device fillComplete (csrc/jp_fill_pipeline.h) on the CPU model -> dict with 0-based rowptr/colind, vals,
+    colmap GIDs, rowmax and the counts"""
+    ptr = np.ascontiguousarray(entry_ptr, dtype=np.int64)
+    g = np.ascontiguousarray(gids, dtype=np.int64)
+    v = np.ascontiguousarray(vals, dtype=np.float64)
+    n_rows = len(ptr) - 1
+    info = np.zeros(4, dtype=np.int64)
+    h = C.c_void_p()
+    _check(lib().emul_fill_complete(C.c_int32(n_rows), _p(ptr), _p(g), _p(v), C.c_int64(gmin), C.c_int64(gmax), C.c_int64(dom_min),
+                                    C.c_int32(dom_n), _p(info), C.byref(h)))
+    n_cols, n_local_used, n_same, nnz = (int(x) for x in info)
+    out = dict(n_cols=n_cols, n_local_used=n_local_used, n_same=n_same, nnz=nnz,
+               rowptr=np.empty(n_rows + 1, dtype=np.int32), colind=np.empty(nnz, dtype=np.int32),
+               vals=np.empty(nnz, dtype=np.float64), colmap=np.empty(n_cols, dtype=np.int64), rowmax=np.empty(n_rows, dtype=np.int32))
+    lib().emul_fill_get(h, _p(out["rowptr"]), _p(out["colind"]), _p(out["vals"]), _p(out["colmap"]), _p(out["rowmax"]))
+    lib().emul_fill_free(h)
+    return out
