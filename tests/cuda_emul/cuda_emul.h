@@ -27,7 +27,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 #define __shared__ static
 // dynamic shared memory: CUDA `extern __shared__ __align__(128) unsigned char name[];`
 #define JP_DYN_SMEM(name) unsigned char* name = ::emul::state().dyn_smem

@@ -3,6 +3,7 @@
 // tests/test_emul_*.py, never by the product.
 #include "emul_runtime.h"
 
+#include "../../juliapetra.jl_b200/csrc/jp_csr_blocks.h"
 #include "../../juliapetra.jl_b200/csrc/jp_fill_pipeline.h"
 
 namespace {
@@ -55,5 +56,120 @@ void emul_fill_get(void* handle, int32_t* rowptr, int32_t* colind, double* vals,
 }
 
 void emul_fill_free(void* handle) { delete static_cast<jp::FillOutput*>(handle); }
+
+
+// ---- localApply (csrc/jp_csr_kernels.cuh) ----
+// One rank's y = beta*y + alpha*A*x through the product's kernels.  rowptr/colind are 0-based; x holds the first
+// x_rows rows of the column space (ld = x_rows) and halo the remaining columns LID-major, vector-minor (halo == null:
+// x is the whole column-map multivector and the HALO=false kernels run).  variant: 0 gather kernels (spmv_kernel for
+// k == 1, spmm_kernel otherwise), 1 spmm_tile_kernel, 2 spmm_pipe_kernel.  stats[4] = blocks, DIRECT, TWOPHASE+WARPROW,
+// LONGROW.  Returns 0, or -1 when the tile tables are not usable for this matrix.
+int emul_local_apply(int32_t n_rows, int32_t n_cols, int32_t n_local_cols, const int32_t* rowptr, const int32_t* colind,
+                     const double* vals, const double* x, int32_t x_rows, const double* halo, double* y, int32_t k, double alpha,
+                     double beta, int32_t variant, int32_t cap, int32_t max_rows, int32_t T, int32_t tma, int32_t allow_direct,
+                     int64_t* stats) {
+  using namespace jp;
+  using namespace jp::csrk;
+  const int64_t nnz = rowptr[n_rows];
+  std::vector<int32_t> rp(rowptr, rowptr + n_rows + 1);
+  std::vector<uint8_t> cls((size_t)n_rows, 0);
+  for (int32_t r = 0; r < n_rows; ++r) {
+    int32_t mx = -1;
+    for (int32_t i = rp[r]; i < rp[r + 1]; ++i) mx = std::max(mx, colind[i]);
+    cls[r] = mx >= n_local_cols;
+  }
+  std::vector<BlockDesc> bi, bb, ba;
+  build_blocks(rp, cls, cap, max_rows, allow_direct != 0, bi, bb, ba);
+  if (stats) {
+    stats[0] = (int64_t)ba.size();
+    stats[1] = stats[2] = stats[3] = 0;
+    for (const BlockDesc& b : ba) {
+      const int kind = b.nrows_kind >> 16;
+      ++stats[kind == KIND_DIRECT ? 1 : kind == KIND_LONGROW ? 3 : 2];
+    }
+  }
+  // device arrays with the slack jp_csr_create gives them
+  DeviceBuffer d_rp, d_ci, d_va, d_blocks, d_x, d_halo, d_y, d_ucols, d_lidx;
+  d_rp.alloc(((size_t)n_rows + 1 + 16) * 4);
+  std::memset(d_rp.p, 0, d_rp.bytes);
+  std::memcpy(d_rp.p, rp.data(), rp.size() * 4);
+  d_ci.alloc(((size_t)nnz + 64) * 4);
+  d_va.alloc(((size_t)nnz + 64) * 8);
+  std::memset(d_ci.p, 0, d_ci.bytes);
+  std::memset(d_va.p, 0, d_va.bytes);
+  std::memcpy(d_ci.p, colind, (size_t)nnz * 4);
+  std::memcpy(d_va.p, vals, (size_t)nnz * 8);
+  const bool use_halo = halo != nullptr;
+  const int32_t n_remote = n_cols - x_rows;
+  d_x.alloc((size_t)x_rows * k * 8 + 64);
+  std::memcpy(d_x.p, x, (size_t)x_rows * k * 8);
+  d_halo.alloc((size_t)std::max(n_remote, 0) * k * 8 + 64);
+  if (use_halo) std::memcpy(d_halo.p, halo, (size_t)n_remote * k * 8);
+  d_y.alloc((size_t)n_rows * k * 8 + 64);
+  std::memcpy(d_y.p, y, (size_t)n_rows * k * 8);
+  const int32_t nloc = use_halo ? n_local_cols : n_cols;
+  const size_t smem = stage_smem_bytes(cap);
+  const unsigned nb = (unsigned)ba.size();
+  constexpr int KT = 8;
+  int rc = 0;
+  if (nb == 0 || k == 0) {
+  } else if (variant == 0) {
+    d_blocks.alloc(ba.size() * sizeof(BlockDesc) + 16);
+    std::memcpy(d_blocks.p, ba.data(), ba.size() * sizeof(BlockDesc));
+    const BlockDesc* b = d_blocks.as<BlockDesc>();
+    auto launch = [&](auto kernel_spmv, auto kernel_spmm) {
+      if (k == 1)
+        JP_KLAUNCH(kernel_spmv, nb, kSpmvThreads, smem, nullptr, b, d_rp.as<int32_t>(), d_ci.as<int32_t>(), d_va.as<double>(),
+                   d_x.as<double>(), d_halo.as<double>(), nloc, d_y.as<double>(), cap, alpha, beta);
+      else
+        JP_KLAUNCH(kernel_spmm, nb, kSpmvThreads, smem, nullptr, b, d_rp.as<int32_t>(), d_ci.as<int32_t>(), d_va.as<double>(),
+                   d_x.as<double>(), (int64_t)x_rows, d_halo.as<double>(), k, nloc, d_y.as<double>(), (int64_t)n_rows, k, cap, T, alpha,
+                   beta);
+    };
+    if (use_halo && tma) launch(spmv_kernel<true, 1>, spmm_kernel<KT, true, 1>);
+    else if (use_halo) launch(spmv_kernel<true, 0>, spmm_kernel<KT, true, 0>);
+    else if (tma) launch(spmv_kernel<false, 1>, spmm_kernel<KT, false, 1>);
+    else launch(spmv_kernel<false, 0>, spmm_kernel<KT, false, 0>);
+  } else {
+    std::vector<int32_t> ci(colind, colind + nnz);
+    TileTables t;
+    if (!build_tile_tables(ci, ba, cap, KT, t)) {
+      rc = -1;
+    } else {
+      d_blocks.alloc(ba.size() * sizeof(BlockDesc) + 16);
+      std::memcpy(d_blocks.p, ba.data(), ba.size() * sizeof(BlockDesc));
+      const BlockDesc* b = d_blocks.as<BlockDesc>();
+      d_ucols.alloc(t.ucols.size() * 4);
+      d_lidx.alloc(t.lidx.size() * 2);
+      std::memcpy(d_ucols.p, t.ucols.data(), t.ucols.size() * 4);
+      std::memcpy(d_lidx.p, t.lidx.data(), t.lidx.size() * 2);
+      const int upad = (t.umax + 3) & ~3;
+      if (variant == 1) {
+        const size_t sm = tile_smem_bytes(cap, upad, KT);
+        if (use_halo)
+          JP_KLAUNCH((spmm_tile_kernel<KT, true>), nb, kTileThreads, sm, nullptr, b, d_rp.as<int32_t>(), d_ci.as<int32_t>(), d_va.as<double>(),
+                     d_lidx.as<uint16_t>(), d_ucols.as<int32_t>(), d_x.as<double>(), (int64_t)x_rows, d_halo.as<double>(), k, nloc,
+                     d_y.as<double>(), (int64_t)n_rows, k, cap, upad, alpha, beta);
+        else
+          JP_KLAUNCH((spmm_tile_kernel<KT, false>), nb, kTileThreads, sm, nullptr, b, d_rp.as<int32_t>(), d_ci.as<int32_t>(), d_va.as<double>(),
+                     d_lidx.as<uint16_t>(), d_ucols.as<int32_t>(), d_x.as<double>(), (int64_t)x_rows, d_halo.as<double>(), k, nloc,
+                     d_y.as<double>(), (int64_t)n_rows, k, cap, upad, alpha, beta);
+      } else {
+        const size_t sm = 2 * pipe_stage_bytes(cap, upad, KT);
+        const unsigned grid = std::min<unsigned>(nb, (unsigned)ctx().sm_count);
+        if (use_halo)
+          JP_KLAUNCH((spmm_pipe_kernel<KT, true>), grid, kPipeThreads, sm, nullptr, b, (int32_t)nb, d_rp.as<int32_t>(), d_va.as<double>(),
+                     d_lidx.as<uint16_t>(), d_ucols.as<int32_t>(), d_x.as<double>(), (int64_t)x_rows, d_halo.as<double>(), k, nloc,
+                     d_y.as<double>(), (int64_t)n_rows, k, cap, upad, alpha, beta);
+        else
+          JP_KLAUNCH((spmm_pipe_kernel<KT, false>), grid, kPipeThreads, sm, nullptr, b, (int32_t)nb, d_rp.as<int32_t>(), d_va.as<double>(),
+                     d_lidx.as<uint16_t>(), d_ucols.as<int32_t>(), d_x.as<double>(), (int64_t)x_rows, d_halo.as<double>(), k, nloc,
+                     d_y.as<double>(), (int64_t)n_rows, k, cap, upad, alpha, beta);
+      }
+    }
+  }
+  std::memcpy(y, d_y.p, (size_t)n_rows * k * 8);
+  return rc;
+}
 
 }  // extern "C"

@@ -54,3 +54,32 @@ def fill_complete(entry_ptr, gids, vals, gmin, gmax, dom_min, dom_n):
     lib().emul_fill_get(h, _p(out["rowptr"]), _p(out["colind"]), _p(out["vals"]), _p(out["colmap"]), _p(out["rowmax"]))
     lib().emul_fill_free(h)
     return out
+
+
+def local_apply(rowptr0, colind0, vals, x, y, alpha=1.0, beta=0.0, n_local_cols=None, halo_split=False, variant=0, cap=2048,
+                max_rows=256, T=1, tma=1, allow_direct=1):
+    """y = beta*y + alpha*A*x through csrc/jp_csr_kernels.cuh on the CPU model.  x: (n_cols, k) column-map multivector.
+    halo_split: rows >= n_local_cols of x are handed over as the LID-major halo buffer (the HALO=true kernels).
+    Returns (y_new, stats) or (None, stats) when the tile tables are unusable for this matrix."""
+    rp = np.ascontiguousarray(rowptr0, dtype=np.int32)
+    ci = np.ascontiguousarray(colind0, dtype=np.int32)
+    va = np.ascontiguousarray(vals, dtype=np.float64)
+    x = np.asfortranarray(x, dtype=np.float64)
+    if x.ndim == 1:
+        x = x.reshape(-1, 1, order="F")
+    n_cols, k = x.shape
+    n_rows = len(rp) - 1
+    yy = np.asfortranarray(np.array(y, dtype=np.float64).reshape(n_rows, k), dtype=np.float64).copy(order="F")
+    nloc = n_cols if n_local_cols is None else int(n_local_cols)
+    if halo_split:
+        xl = np.asfortranarray(x[:nloc, :]).copy(order="F")
+        halo = np.ascontiguousarray(x[nloc:, :])  # (n_remote, k) row-major = LID-major, vector-minor
+        x_rows, hp = nloc, _p(halo)
+    else:
+        xl, x_rows, hp = x, n_cols, None
+    stats = np.zeros(4, dtype=np.int64)
+    rc = lib().emul_local_apply(C.c_int32(n_rows), C.c_int32(n_cols), C.c_int32(nloc), _p(rp), _p(ci), _p(va), _p(xl), C.c_int32(x_rows), hp,
+                                _p(yy), C.c_int32(k), C.c_double(alpha), C.c_double(beta), C.c_int32(variant), C.c_int32(cap),
+                                C.c_int32(max_rows), C.c_int32(T), C.c_int32(tma), C.c_int32(allow_direct), _p(stats))
+    st = dict(zip(("blocks", "direct", "twophase_warprow", "longrow"), (int(s) for s in stats)))
+    return (None if rc != 0 else yy), st

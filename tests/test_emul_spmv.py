@@ -1,0 +1,91 @@
+"""The localApply kernels (csrc/jp_csr_kernels.cuh: spmv_kernel, spmm_kernel, spmm_tile_kernel, spmm_pipe_kernel, every
+block kind, TMA and cp.async staging, with and without the halo buffer) executed on the CPU model of tests/cuda_emul and
+compared with the CPU oracle's localApply (src/CSRMatrix.jl:1123-1162).  DIRECT blocks are bit-exact; the rest meets the
+1e-12 contract of the north star.  GPU runs of the same kernels: tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import emul
+from helpers import O, oracle_problem, synthetic
+
+
+def _problem(kind, N, **kw):
+    c, m, A = oracle_problem(kind, N, 1, **kw)
+    rp, ci, va = A.csr(1)
+    return rp - 1, ci - 1, va
+
+
+def _oracle(rp0, ci0, va, x, y0, alpha, beta):
+    return O.local_apply_raw(y0.copy(order="F"), rp0 + 1, ci0 + 1, va, x, O.NO_TRANS, alpha, beta)
+
+
+def _bound(rp0, ci0, va, x, y0, alpha, beta):
+    return 1e-12 * (abs(alpha) * _oracle(rp0, ci0, np.abs(va), np.abs(x), np.zeros_like(y0), 1.0, 0.0) + abs(beta) * np.abs(y0)) + 1e-300
+
+
+def _vectors(n_cols, n_rows, k):
+    return synthetic.vector_block(1, n_cols, k, seed=1), synthetic.vector_block(1, n_rows, k, seed=2)
+
+
+@pytest.mark.parametrize("tma", [1, 0])
+@pytest.mark.parametrize("kind,N", [("5pt", 20), ("7pt", 9), ("27pt", 6)])
+def test_spmv_direct_blocks_are_bit_exact(kind, N, tma):
+    rp, ci, va = _problem(kind, N)
+    n = len(rp) - 1
+    x, y0 = _vectors(n, n, 1)
+    for alpha, beta in ((1.0, 0.0), (3.0, 0.5)):
+        got, st = emul.local_apply(rp, ci, va, x, y0, alpha, beta, tma=tma)
+        assert st["direct"] == st["blocks"] > 0
+        assert np.array_equal(got, _oracle(rp, ci, va, x, y0, alpha, beta))
+
+
+@pytest.mark.parametrize("cap,allow_direct", [(2048, 1), (256, 1), (2048, 0)])
+def test_spmv_irregular_rows_all_block_kinds(cap, allow_direct):
+    rp, ci, va = _problem("powerlaw", 4000, mean=16.0, max_len=1500)
+    n = len(rp) - 1
+    x, y0 = _vectors(n, n, 1)
+    got, st = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, cap=cap, allow_direct=allow_direct)
+    assert st["twophase_warprow"] > 0 and (cap != 256 or st["longrow"] > 0)
+    ref = _oracle(rp, ci, va, x, y0, 3.0, 0.5)
+    assert (np.abs(got - ref) <= _bound(rp, ci, va, x, y0, 3.0, 0.5)).all()
+
+
+def test_spmv_with_halo_buffer():
+    rp, ci, va = _problem("7pt", 8)
+    n = len(rp) - 1
+    x, y0 = _vectors(n, n, 1)
+    nloc = n - 2 * 64  # the last two z-planes play the remote columns
+    got, st = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, n_local_cols=nloc, halo_split=True)
+    assert np.array_equal(got, _oracle(rp, ci, va, x, y0, 3.0, 0.5))
+    rp, ci, va = _problem("powerlaw", 1500)
+    n = len(rp) - 1
+    x, y0 = _vectors(n, n, 1)
+    got, st = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, n_local_cols=1000, halo_split=True)
+    ref = _oracle(rp, ci, va, x, y0, 3.0, 0.5)
+    assert (np.abs(got - ref) <= _bound(rp, ci, va, x, y0, 3.0, 0.5)).all()
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("k", [2, 8, 11])
+def test_spmm_kernels(variant, k):
+    rp, ci, va = _problem("27pt", 6)
+    n = len(rp) - 1
+    x, y0 = _vectors(n, n, k)
+    for halo in (False, True):
+        got, st = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, variant=variant, T=2, n_local_cols=n - 40 if halo else None,
+                                   halo_split=halo)
+        assert got is not None
+        ref = _oracle(rp, ci, va, x, y0, 3.0, 0.5)
+        assert (np.abs(got - ref) <= _bound(rp, ci, va, x, y0, 3.0, 0.5)).all()
+
+
+def test_spmm_irregular_rows():
+    rp, ci, va = _problem("powerlaw", 2500, mean=16.0, max_len=900)
+    n = len(rp) - 1
+    x, y0 = _vectors(n, n, 5)
+    for cap in (2048, 256):
+        got, st = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, cap=cap, T=4)
+        ref = _oracle(rp, ci, va, x, y0, 3.0, 0.5)
+        assert (np.abs(got - ref) <= _bound(rp, ci, va, x, y0, 3.0, 0.5)).all()
+    got, st = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, variant=1)
+    assert got is None  # random columns: the tile tables are rejected and the gather kernel is used
