@@ -122,6 +122,9 @@ int32_t jp_mv_fill(jp_handle mv, double value);                             /* f
 int32_t jp_mv_scale(jp_handle mv, double alpha);                            /* scale!, src/MultiVector.jl:62-65 */
 int32_t jp_mv_scale_vec(jp_handle mv, const double* alpha_k);               /* scale! per vector, :72-77 */
 int32_t jp_mv_axpby(jp_handle y, double a, jp_handle x, double b);          /* y = a*x + b*y; broadcast copyto!, :497-502 */
+/* y = a*x + b*y and norm(y, 2) of the result in one pass (the residual update of a CG iteration + its norm):
+ * broadcast copyto! (:497-502) fused with norm (:122-133); out_k as jp_mv_norm2 */
+int32_t jp_mv_axpby_norm2(jp_handle comm, jp_handle y, double a, jp_handle x, double b, double* out_k);
 int32_t jp_mv_dot(jp_handle comm, jp_handle x, jp_handle y, double* out_k);    /* dot, :84-108 (allreduce included) */
 int32_t jp_mv_norm2(jp_handle comm, jp_handle x, double* out_k);               /* norm(.,2), :122-133 */
 int32_t jp_mv_normp(jp_handle comm, jp_handle x, double p, double* out_k);     /* norm(.,p), :135-144 */
@@ -156,6 +159,10 @@ int32_t jp_local_apply(jp_handle Y, jp_handle A, jp_handle X, int32_t mode, doub
  * (the semantics of src/RowMatrix.jl:324-352, i.e. Tpetra's applyTranspose).  Collective over the plan's comm. */
 int32_t jp_apply(jp_handle comm, jp_handle Y, jp_handle A, jp_handle X, jp_handle plan, int32_t mode, double alpha,
                  double beta);
+/* apply! followed by dot(W, Y) (src/MultiVector.jl:84-108) without a host round trip in between; for k = 1, NO_TRANS
+ * and no importer the dot product is accumulated by the SpMV kernel itself (p'Ap of a CG iteration: W = X). */
+int32_t jp_apply_dot(jp_handle comm, jp_handle Y, jp_handle A, jp_handle X, jp_handle plan, int32_t mode, double alpha,
+                     double beta, jp_handle W, double* out_k);
 /* the same call with HOST buffers (what a Julia caller holding Array{Float64,2} makes): uploads X, applies,
  * downloads Y.  y_host is also read when beta != 0. */
 int32_t jp_apply_host(jp_handle comm, jp_handle A, jp_handle plan, const double* x_host, double* y_host, int32_t k,

@@ -67,6 +67,7 @@ PROTOTYPES = {
     "jp_mv_scale": [c_i64, c_f64],
     "jp_mv_scale_vec": [c_i64, c_vp],
     "jp_mv_axpby": [c_i64, c_f64, c_i64, c_f64],
+    "jp_mv_axpby_norm2": [c_i64, c_i64, c_f64, c_i64, c_f64, c_vp],
     "jp_mv_dot": [c_i64, c_i64, c_i64, c_vp],
     "jp_mv_norm2": [c_i64, c_i64, c_vp],
     "jp_mv_normp": [c_i64, c_i64, c_f64, c_vp],
@@ -79,6 +80,7 @@ PROTOTYPES = {
     "jp_transfer_wait": [c_i64],
     "jp_local_apply": [c_i64, c_i64, c_i64, c_i32, c_f64, c_f64],
     "jp_apply": [c_i64, c_i64, c_i64, c_i64, c_i64, c_i32, c_f64, c_f64],
+    "jp_apply_dot": [c_i64, c_i64, c_i64, c_i64, c_i64, c_i32, c_f64, c_f64, c_i64, c_vp],
     "jp_apply_host": [c_i64, c_i64, c_i64, c_vp, c_vp, c_i32, c_i32, c_f64, c_f64],
 }
 

@@ -200,6 +200,8 @@ struct Csr : Object {
   std::unique_ptr<MultiVector> import_mv;
   // GIDs of the column map in LID order, kept when the matrix was fill-completed on the device (jp_csr_fill_complete)
   DeviceBuffer colmap_gids;
+  // jp_apply_dot workspace: [block partials | result | ticket], zeroed once (the kernel re-arms the ticket)
+  DeviceBuffer dot_ws;
   // host-buffer path (jp_apply_host): the all-blocks list cut into chunks; chunk c covers blocks
   // [chunk_block[c], chunk_block[c+1]) = rows [chunk_row[c], chunk_row[c+1]) and reads columns <= chunk_maxcol[c]
   // (prefix maximum), so its kernel can start as soon as that much of X has been uploaded
@@ -278,5 +280,9 @@ void apply_trans_distributed(Csr* a, Plan* p, MultiVector* y, MultiVector* x, do
 void comm_allreduce_device(Comm& c, double* buf, int64_t n, cudaStream_t stream);
 void release_host_path_cache();
 void release_reduce_workspace();
+double* mv_dot_local(const MultiVector& x, const MultiVector& y);  // k local dot products -> device workspace (compute stream)
+void mv_finish_reduction(Comm& c, double* dev_out, int32_t k, double* host_out);  // allreduce + D2H + synchronise
+// y = beta*y + alpha*A*x over all row blocks (x = the whole column-map vector) and sum_r w[r]*y[r] -> returned device slot
+double* launch_spmv_dot(Csr& A, const double* x, double* y, double alpha, double beta, const double* w, cudaStream_t stream);
 
 }  // namespace jp

@@ -244,6 +244,36 @@ void launch_spmv_fused(const Csr& A, const FusedHalo& h, const double* x, const 
   JP_LAUNCH_CHECK();
 }
 
+double* launch_spmv_dot(Csr& A, const double* x, double* y, double alpha, double beta, const double* w, cudaStream_t stream) {
+  const int32_t nb = A.n_blocks_all;
+  const size_t ws_bytes = ((size_t)nb + 4) * 8;
+  if (A.dot_ws.bytes < ws_bytes) {
+    A.dot_ws.alloc(ws_bytes);
+    JP_CUDA(cudaMemsetAsync(A.dot_ws.p, 0, ws_bytes, stream));
+  }
+  double* partials = A.dot_ws.as<double>();
+  double* out = partials + nb;
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(partials + nb + 1);
+  if (nb == 0) {
+    JP_CUDA(cudaMemsetAsync(out, 0, 8, stream));
+    return out;
+  }
+  const size_t smem = stage_smem_bytes(A.nnz_cap);
+  static const int tma = env_int("JP_SPMV_TMA", 1);
+  const BlockDesc* b = A.blocks_all.as<BlockDesc>();
+  if (tma) {
+    set_smem_attr(spmv_dot_kernel<false, 1>, smem);
+    spmv_dot_kernel<false, 1><<<nb, kSpmvThreads, smem, stream>>>(b, A.rowptr.as<int32_t>(), A.colind.as<int32_t>(), A.vals.as<double>(), x,
+                                                                   nullptr, A.n_cols, y, A.nnz_cap, alpha, beta, w, partials, ticket, out);
+  } else {
+    set_smem_attr(spmv_dot_kernel<false, 0>, smem);
+    spmv_dot_kernel<false, 0><<<nb, kSpmvThreads, smem, stream>>>(b, A.rowptr.as<int32_t>(), A.colind.as<int32_t>(), A.vals.as<double>(), x,
+                                                                   nullptr, A.n_cols, y, A.nnz_cap, alpha, beta, w, partials, ticket, out);
+  }
+  JP_LAUNCH_CHECK();
+  return out;
+}
+
 void launch_spmv(const Csr& A, const DeviceBuffer& blocks, int32_t n_blocks, bool use_halo, const double* x, int64_t ldx,
                  const double* halo, int32_t halo_k, double* y, int64_t ldy, int32_t k, double alpha, double beta,
                  cudaStream_t stream) {

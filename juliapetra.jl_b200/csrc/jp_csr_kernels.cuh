@@ -137,16 +137,20 @@ __device__ void long_row(const int32_t* __restrict__ colind, const double* __res
   }
 }
 
-// one row block of y = beta*y + alpha*A*x (k = 1); called by every thread of the CTA
-template <bool HALO, int TMA>
-__device__ __forceinline__ void spmv_block(const BlockRange& b, const StageView& sv, uint64_t* s_bar_p, double* s_red,
-                                           const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
-                                           const double* __restrict__ vals, const double* __restrict__ x,
-                                           const double* __restrict__ halo, int32_t nloc, double* __restrict__ y, double alpha, double beta) {
+// one row block of y = beta*y + alpha*A*x (k = 1); called by every thread of the CTA.  Returns this thread's share of
+// sum_r w[r] * y_new[r] over the block's rows when DOT (0 otherwise).
+template <bool HALO, int TMA, bool DOT = false>
+__device__ __forceinline__ double spmv_block(const BlockRange& b, const StageView& sv, uint64_t* s_bar_p, double* s_red,
+                                             const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                                             const double* __restrict__ vals, const double* __restrict__ x,
+                                             const double* __restrict__ halo, int32_t nloc, double* __restrict__ y, double alpha, double beta,
+                                             const double* __restrict__ w = nullptr) {
   const int tid = threadIdx.x;
+  double dacc = 0.0;
   if (b.kind == KIND_LONGROW) {
     long_row<HALO>(colind, vals, x, 0, halo, 1, nloc, y, 0, 1, b.row0, b.p0, b.p1, alpha, beta, s_red);
-    return;
+    if (DOT && tid == 0) dacc = __ldg(w + b.row0) * y[b.row0];  // thread 0 wrote y[row0] itself
+    return dacc;
   }
   stage_block<TMA>(sv, s_bar_p, rowptr, colind, vals, b);
   const int32_t* rp = sv.s_rp + b.rpo;  // rp[r] is a global nonzero index; shared index = rp[r] - a0
@@ -163,8 +167,9 @@ __device__ __forceinline__ void spmv_block(const BlockRange& b, const StageView&
       }
       double* yp = y + b.row0 + r;
       *yp = combine(beta == 0.0 ? 0.0 : *yp, sum, alpha, beta);
+      if (DOT) dacc += __ldg(w + b.row0 + r) * *yp;
     }
-    return;
+    return dacc;
   }
   // phase A: products, thread-per-nonzero (every gather of the block is independent of row structure);
   // 8 nonzeros per thread per pass so 8 gathers are in flight before the first product is needed
@@ -193,6 +198,7 @@ __device__ __forceinline__ void spmv_block(const BlockRange& b, const StageView&
       const int s = rp[r] - b.a0, e = rp[r + 1] - b.a0;
       double* yp = y + b.row0 + r;
       *yp = combine(beta == 0.0 ? 0.0 : *yp, row_sum_sequential(sv.s_val, s, e), alpha, beta);
+      if (DOT) dacc += __ldg(w + b.row0 + r) * *yp;
     }
   } else {
     // WARPROW: the block holds at least one long row.  Short rows still go thread-per-row (sequential sum, the
@@ -202,6 +208,7 @@ __device__ __forceinline__ void spmv_block(const BlockRange& b, const StageView&
       if (e - s <= kLongRowLen) {
         double* yp = y + b.row0 + r;
         *yp = combine(beta == 0.0 ? 0.0 : *yp, row_sum_sequential(sv.s_val, s, e), alpha, beta);
+        if (DOT) dacc += __ldg(w + b.row0 + r) * *yp;
       }
     }
     const int lane = tid & 31, warp = tid >> 5;
@@ -214,9 +221,76 @@ __device__ __forceinline__ void spmv_block(const BlockRange& b, const StageView&
       if (lane == 0) {
         double* yp = y + b.row0 + r;
         *yp = combine(beta == 0.0 ? 0.0 : *yp, sum, alpha, beta);
+        if (DOT) dacc += __ldg(w + b.row0 + r) * *yp;
       }
     }
   }
+  return dacc;
+}
+
+// Sum of every thread's `v` over the whole GRID, deterministic for a given launch geometry: block partials in block
+// order, added by the last block to finish (ticket counter), which re-arms the ticket for the next launch.
+// s_red: kSpmvThreads / 32 doubles of shared memory.  Called by every thread of every CTA of the launch.
+__device__ __forceinline__ void grid_sum_finish(double v, double* s_red, double* __restrict__ partials, unsigned int* __restrict__ ticket,
+                                                double* __restrict__ out, unsigned bid, unsigned nblocks) {
+  __shared__ bool s_last_block;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double s = warp_sum(v);
+  __syncthreads();  // s_red may still be in use by the row block
+  if (lane == 0) s_red[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    double t = lane < kSpmvThreads / 32 ? s_red[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) {
+      partials[bid] = t;
+      __threadfence();
+      s_last_block = atomicAdd(ticket, 1u) == nblocks - 1;
+    }
+  }
+  __syncthreads();
+  if (s_last_block) {  // block-uniform
+    __threadfence();
+    const volatile double* pv = partials;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    unsigned b = tid;
+    for (; b + 3 * kSpmvThreads < nblocks; b += 4 * kSpmvThreads) {
+      a0 += pv[b];
+      a1 += pv[b + kSpmvThreads];
+      a2 += pv[b + 2 * kSpmvThreads];
+      a3 += pv[b + 3 * kSpmvThreads];
+    }
+    for (; b < nblocks; b += kSpmvThreads) a0 += pv[b];
+    const double t = warp_sum((a0 + a1) + (a2 + a3));
+    __syncthreads();
+    if (lane == 0) s_red[warp] = t;
+    __syncthreads();
+    if (warp == 0) {
+      double u = lane < kSpmvThreads / 32 ? s_red[lane] : 0.0;
+      u = warp_sum(u);
+      if (lane == 0) {
+        out[0] = u;
+        *ticket = 0;
+      }
+    }
+  }
+}
+
+// apply + dot in one pass: y = beta*y + alpha*A*x and out[0] = sum_r w[r] * y[r], so a CG
+// iteration's p'Ap costs no second sweep over p and Ap (16 bytes per row less HBM traffic, one launch less)
+template <bool HALO, int TMA>
+__global__ void __launch_bounds__(kSpmvThreads)
+spmv_dot_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                const double* __restrict__ vals, const double* __restrict__ x, const double* __restrict__ halo, int32_t nloc,
+                double* __restrict__ y, int32_t cap, double alpha, double beta, const double* __restrict__ w,
+                double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ out) {
+  JP_DYN_SMEM(smem_raw);
+  __shared__ double s_red[kSpmvThreads / 32];
+  __shared__ __align__(8) uint64_t s_bar;
+  const StageView sv = stage_view(smem_raw, cap);
+  const BlockRange b = decode_block(blocks, blockIdx.x);
+  const double dacc = spmv_block<HALO, TMA, true>(b, sv, &s_bar, s_red, rowptr, colind, vals, x, halo, nloc, y, alpha, beta, w);
+  grid_sum_finish(dacc, s_red, partials, ticket, out, blockIdx.x, gridDim.x);
 }
 
 template <bool HALO, int TMA>

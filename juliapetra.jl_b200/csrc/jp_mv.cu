@@ -8,6 +8,7 @@
 // Elementwise arithmetic uses explicit non-fused __dmul_rn/__dadd_rn so results are bit-identical to the
 // reference's scalar loops (Julia does not contract a*x+b*y into an FMA).
 #include "jp_common.h"
+#include "jp_mv_kernels.cuh"
 
 namespace jp {
 
@@ -195,6 +196,9 @@ void finish_reduction(Comm& c, double* dev_out, int32_t k, double* host_out) {
 
 }  // namespace
 
+double* mv_dot_local(const MultiVector& x, const MultiVector& y) { return reduce_local<0>(x, &y, 0.0); }
+void mv_finish_reduction(Comm& c, double* dev_out, int32_t k, double* host_out) { finish_reduction(c, dev_out, k, host_out); }
+
 void release_reduce_workspace() {
   g_reduce_buf.release();
   g_reduce_k = 0;
@@ -333,6 +337,27 @@ int32_t jp_mv_axpby(jp_handle y, double a, jp_handle x, double b) {
     if (n == 0) return;
     axpby_kernel<<<grid_for(n, 4), kThreads, 0, ctx().compute>>>(my->d(), mx->d(), n, a, b);
     JP_LAUNCH_CHECK();
+  });
+}
+
+int32_t jp_mv_axpby_norm2(jp_handle comm, jp_handle y, double a, jp_handle x, double b, double* out_k) {
+  return guarded([&] {
+    require_init();
+    Comm* c = get<Comm>(comm, Kind::Comm, "comm");
+    MultiVector* my = get<MultiVector>(y, Kind::MultiVector, "multivector");
+    MultiVector* mx = get<MultiVector>(x, Kind::MultiVector, "multivector");
+    JP_REQUIRE(my->n == mx->n && my->k == mx->k, "jp_mv_axpby_norm2: shapes differ");
+    JP_REQUIRE(my != mx, "jp_mv_axpby_norm2: x and y must be different multivectors");
+    if (my->k == 0) return;
+    JP_REQUIRE(out_k != nullptr, "jp_mv_axpby_norm2: null output");
+    ReduceWorkspace w = reduce_workspace(my->k);
+    int blocks = grid_for(my->n, 8);
+    if (blocks > kMaxReduceBlocks) blocks = kMaxReduceBlocks;
+    dim3 grid(blocks, my->k);
+    mvk::axpby_norm2_kernel<<<grid, mvk::kThreads, 0, ctx().compute>>>(my->d(), mx->d(), my->n, a, b, w.partials, w.tickets, w.out);
+    JP_LAUNCH_CHECK();
+    finish_reduction(*c, w.out, my->k, out_k);
+    for (int v = 0; v < my->k; ++v) out_k[v] = std::sqrt(out_k[v]);  // sqrt after the allreduce, src/MultiVector.jl:132-133
   });
 }
 

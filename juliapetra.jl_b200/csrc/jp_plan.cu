@@ -783,6 +783,34 @@ int32_t jp_apply(jp_handle comm, jp_handle Y, jp_handle A, jp_handle X, jp_handl
   });
 }
 
+int32_t jp_apply_dot(jp_handle comm, jp_handle Y, jp_handle A, jp_handle X, jp_handle plan, int32_t mode, double alpha, double beta,
+                     jp_handle W, double* out_k) {
+  return guarded([&] {
+    require_init();
+    Comm* c = get<Comm>(comm, Kind::Comm, "comm");
+    Csr* a = get<Csr>(A, Kind::Csr, "csr matrix");
+    MultiVector* y = get<MultiVector>(Y, Kind::MultiVector, "multivector");
+    MultiVector* x = get<MultiVector>(X, Kind::MultiVector, "multivector");
+    MultiVector* w = get<MultiVector>(W, Kind::MultiVector, "multivector");
+    Plan* p = plan ? get<Plan>(plan, Kind::Plan, "plan") : nullptr;
+    JP_REQUIRE(w->n == y->n && w->k == y->k, "jp_apply_dot: W must have the shape of Y");
+    JP_REQUIRE(x != y, "apply!: X and Y must be different multivectors");
+    JP_REQUIRE(x->k == y->k, "apply!: X and Y must have the same number of vectors");
+    if (y->k == 0) return;
+    JP_REQUIRE(out_k != nullptr, "jp_apply_dot: null output");
+    // one kernel when the whole apply is one launch over all row blocks: k = 1, NO_TRANS, no importer
+    const bool fused = mode == JP_NO_TRANS && alpha != 0.0 && y->k == 1 && p == nullptr && w != y && x->n == a->n_cols && y->n == a->n_rows;
+    if (fused) {
+      double* dev = launch_spmv_dot(*a, x->d(), y->d(), alpha, beta, w->d(), ctx().compute);
+      mv_finish_reduction(*c, dev, 1, out_k);
+      return;
+    }
+    apply_impl(a, p, y, x, mode, alpha, beta);
+    double* dev = mv_dot_local(*w, *y);  // stream-ordered after the apply: no host round trip in between
+    mv_finish_reduction(*c, dev, y->k, out_k);
+  });
+}
+
 int32_t jp_apply_host(jp_handle comm, jp_handle A, jp_handle plan, const double* x_host, double* y_host, int32_t k, int32_t mode,
                       double alpha, double beta) {
   return guarded([&] {

@@ -389,6 +389,25 @@ class CSRMatrix:
             Y.commReduce()  # src/RowMatrix.jl:353-355 (identity on SerialComm)
         return Y
 
+    def apply_dot_(self, Y: DenseMultiVector, X: DenseMultiVector, W: DenseMultiVector | None = None, mode=NO_TRANS, alpha=1.0, beta=0.0):
+        """apply!(Y, A, X, mode, alpha, beta) followed by dot(W, Y) (W defaults to X: the p'Ap of a CG iteration), as ONE
+        C-ABI call (jp_apply_dot): no host round trip between the two, and for k = 1 without an importer the SpMV kernel
+        accumulates the dot product itself.  Returns the 1 x numVectors array `dot` returns (src/MultiVector.jl:84-108)."""
+        if self.isFillActive():
+            raise InvalidStateError("Cannot call apply(...) until fillComplete(...)")
+        if self.exporter is not None:
+            raise InvalidStateError("apply!: rangeMap != rowMap is non-functional in the reference (out of scope)")
+        W = X if W is None else W
+        comm = self.comm
+        if not Y.getMap().distributedGlobal() and comm.numProc() > 1:
+            # replicated Y needs the commReduce between apply! and dot (src/RowMatrix.jl:353-355): not fusable
+            self.apply_(Y, X, mode, alpha, beta)
+            return W.dot(Y)
+        out = np.empty((1, Y.numVectors()), dtype=np.float64)
+        plan = self.importer.device_plan() if self.importer is not None else 0
+        _lib.check(_lib.lib().jp_apply_dot(comm.handle, Y.h, self.h, X.h, plan, int(mode), float(alpha), float(beta), W.h, _lib.ptr(out)))
+        return out
+
     def apply(self, X: DenseMultiVector, mode=NO_TRANS, alpha=1.0):  # src/Operator.jl:80-88
         Y = DenseMultiVector(self.domainMap if isTransposed(mode) else self.rangeMap, X.numVectors())
         return self.apply_(Y, X, mode, alpha, 0.0)

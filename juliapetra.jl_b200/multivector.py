@@ -129,6 +129,13 @@ class DenseMultiVector:
         _lib.check(_lib.lib().jp_mv_axpby(self.h, float(a), x.h, float(b)))
         return self
 
+    def axpby_norm2_(self, a, x: "DenseMultiVector", b) -> np.ndarray:
+        """self = a*x + b*self and norm(self, 2) of the result in one pass over the data (jp_mv_axpby_norm2): the
+        residual update of a CG iteration fused with its norm.  Returns what `norm(self, 2)` would."""
+        out = np.empty((1, self.numVectors_), dtype=np.float64)
+        _lib.check(_lib.lib().jp_mv_axpby_norm2(self.getComm().handle, self.h, float(a), x.h, float(b), _lib.ptr(out)))
+        return out
+
     # ---- src/MultiVector.jl:84-161 ----
     def dot(self, other: "DenseMultiVector") -> np.ndarray:
         out = np.empty((1, self.numVectors_), dtype=np.float64)

@@ -5,6 +5,7 @@
 
 #include "../../juliapetra.jl_b200/csrc/jp_csr_blocks.h"
 #include "../../juliapetra.jl_b200/csrc/jp_fill_pipeline.h"
+#include "../../juliapetra.jl_b200/csrc/jp_mv_kernels.cuh"
 
 namespace {
 std::string g_error;
@@ -170,6 +171,87 @@ int emul_local_apply(int32_t n_rows, int32_t n_cols, int32_t n_local_cols, const
   }
   std::memcpy(y, d_y.p, (size_t)n_rows * k * 8);
   return rc;
+}
+
+
+// ---- fused CG building blocks ----
+// y = beta*y + alpha*A*x and out = sum_r w[r]*y[r] (spmv_dot_kernel), `repeats` times with the same workspace so the
+// ticket re-arm is exercised; y is reset to y0 before every repeat.  x is the whole column-map vector.
+int emul_spmv_dot(int32_t n_rows, int32_t n_cols, const int32_t* rowptr, const int32_t* colind, const double* vals, const double* x,
+                  const double* w, double* y, double alpha, double beta, int32_t cap, int32_t max_rows, int32_t tma, int32_t repeats,
+                  double* out) {
+  using namespace jp;
+  using namespace jp::csrk;
+  const int64_t nnz = rowptr[n_rows];
+  std::vector<int32_t> rp(rowptr, rowptr + n_rows + 1);
+  std::vector<uint8_t> cls((size_t)n_rows, 0);
+  std::vector<BlockDesc> bi, bb, ba;
+  build_blocks(rp, cls, cap, max_rows, true, bi, bb, ba);
+  const unsigned nb = (unsigned)ba.size();
+  DeviceBuffer d_rp, d_ci, d_va, d_blocks, d_x, d_w, d_y, ws;
+  d_rp.alloc(((size_t)n_rows + 1 + 16) * 4);
+  std::memset(d_rp.p, 0, d_rp.bytes);
+  std::memcpy(d_rp.p, rp.data(), rp.size() * 4);
+  d_ci.alloc(((size_t)nnz + 64) * 4);
+  d_va.alloc(((size_t)nnz + 64) * 8);
+  std::memset(d_ci.p, 0, d_ci.bytes);
+  std::memset(d_va.p, 0, d_va.bytes);
+  std::memcpy(d_ci.p, colind, (size_t)nnz * 4);
+  std::memcpy(d_va.p, vals, (size_t)nnz * 8);
+  d_blocks.alloc(ba.size() * sizeof(BlockDesc) + 16);
+  std::memcpy(d_blocks.p, ba.data(), ba.size() * sizeof(BlockDesc));
+  d_x.alloc((size_t)n_cols * 8 + 64);
+  std::memcpy(d_x.p, x, (size_t)n_cols * 8);
+  d_w.alloc((size_t)n_rows * 8 + 64);
+  std::memcpy(d_w.p, w, (size_t)n_rows * 8);
+  d_y.alloc((size_t)n_rows * 8 + 64);
+  ws.alloc(((size_t)nb + 4) * 8);
+  std::memset(ws.p, 0, ws.bytes);
+  double* partials = ws.as<double>();
+  double* d_out = partials + nb;
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(partials + nb + 1);
+  const size_t smem = stage_smem_bytes(cap);
+  for (int rep = 0; rep < repeats; ++rep) {
+    std::memcpy(d_y.p, y, (size_t)n_rows * 8);
+    *d_out = -12345.0;
+    if (nb == 0) {
+      *d_out = 0.0;
+    } else if (tma) {
+      JP_KLAUNCH((spmv_dot_kernel<false, 1>), nb, kSpmvThreads, smem, nullptr, d_blocks.as<BlockDesc>(), d_rp.as<int32_t>(),
+                 d_ci.as<int32_t>(), d_va.as<double>(), d_x.as<double>(), (const double*)nullptr, n_cols, d_y.as<double>(), cap, alpha, beta,
+                 d_w.as<double>(), partials, ticket, d_out);
+    } else {
+      JP_KLAUNCH((spmv_dot_kernel<false, 0>), nb, kSpmvThreads, smem, nullptr, d_blocks.as<BlockDesc>(), d_rp.as<int32_t>(),
+                 d_ci.as<int32_t>(), d_va.as<double>(), d_x.as<double>(), (const double*)nullptr, n_cols, d_y.as<double>(), cap, alpha, beta,
+                 d_w.as<double>(), partials, ticket, d_out);
+    }
+    out[rep] = *d_out;
+    if (*ticket != 0) return -2;  // the last block must re-arm the ticket
+  }
+  std::memcpy(y, d_y.p, (size_t)n_rows * 8);
+  return 0;
+}
+
+// y = a*x + b*y (n x k, column-major) and out[v] = sum y_new[:, v]^2, `repeats` times on the same workspace
+int emul_axpby_norm2(double* y, const double* x, int64_t n, int32_t k, double a, double b, int32_t blocks, int32_t repeats, double* out) {
+  using namespace jp;
+  DeviceBuffer d_y, d_x, ws;
+  d_y.alloc((size_t)n * k * 8 + 64);
+  d_x.alloc((size_t)n * k * 8 + 64);
+  std::memcpy(d_y.p, y, (size_t)n * k * 8);
+  std::memcpy(d_x.p, x, (size_t)n * k * 8);
+  ws.alloc(((size_t)k * blocks + 2 * (size_t)k) * 8);
+  std::memset(ws.p, 0, ws.bytes);
+  double* partials = ws.as<double>();
+  double* d_out = partials + (size_t)k * blocks;
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(d_out + k);
+  for (int rep = 0; rep < repeats; ++rep) {
+    JP_KLAUNCH(mvk::axpby_norm2_kernel, dim3(blocks, k), mvk::kThreads, 0, nullptr, d_y.as<double>(), d_x.as<double>(), n, a, b, partials,
+               tickets, d_out);
+    for (int v = 0; v < k; ++v) out[(size_t)rep * k + v] = d_out[v];
+  }
+  std::memcpy(y, d_y.p, (size_t)n * k * 8);
+  return 0;
 }
 
 }  // extern "C"

@@ -83,3 +83,33 @@ def local_apply(rowptr0, colind0, vals, x, y, alpha=1.0, beta=0.0, n_local_cols=
                                 C.c_int32(max_rows), C.c_int32(T), C.c_int32(tma), C.c_int32(allow_direct), _p(stats))
     st = dict(zip(("blocks", "direct", "twophase_warprow", "longrow"), (int(s) for s in stats)))
     return (None if rc != 0 else yy), st
+
+
+def spmv_dot(rowptr0, colind0, vals, x, w, y, alpha=1.0, beta=0.0, cap=2048, max_rows=256, tma=1, repeats=2):
+    """spmv_dot_kernel on the CPU model: returns (y_new, [dot per repeat])"""
+    rp = np.ascontiguousarray(rowptr0, dtype=np.int32)
+    ci = np.ascontiguousarray(colind0, dtype=np.int32)
+    va = np.ascontiguousarray(vals, dtype=np.float64)
+    x = np.ascontiguousarray(np.asarray(x, dtype=np.float64).ravel())
+    w = np.ascontiguousarray(np.asarray(w, dtype=np.float64).ravel())
+    yy = np.ascontiguousarray(np.asarray(y, dtype=np.float64).ravel()).copy()
+    out = np.zeros(repeats, dtype=np.float64)
+    rc = lib().emul_spmv_dot(C.c_int32(len(rp) - 1), C.c_int32(len(x)), _p(rp), _p(ci), _p(va), _p(x), _p(w), _p(yy), C.c_double(alpha),
+                             C.c_double(beta), C.c_int32(cap), C.c_int32(max_rows), C.c_int32(tma), C.c_int32(repeats), _p(out))
+    assert rc == 0, f"emul_spmv_dot rc={rc}"
+    return yy, out
+
+
+def axpby_norm2(y, a, x, b, blocks=3, repeats=1):
+    """axpby_norm2_kernel on the CPU model, applied `repeats` times: returns (y_final, sums[repeats, k])"""
+    yy = np.asfortranarray(np.array(y, dtype=np.float64))
+    if yy.ndim == 1:
+        yy = yy.reshape(-1, 1, order="F")
+    xx = np.asfortranarray(np.asarray(x, dtype=np.float64).reshape(yy.shape, order="F"))
+    yy = yy.copy(order="F")
+    n, k = yy.shape
+    out = np.zeros((repeats, k), dtype=np.float64)
+    rc = lib().emul_axpby_norm2(_p(yy), _p(xx), C.c_int64(n), C.c_int32(k), C.c_double(a), C.c_double(b), C.c_int32(blocks),
+                                C.c_int32(repeats), _p(out))
+    assert rc == 0
+    return yy, out
