@@ -55,6 +55,7 @@ PROTOTYPES = {
     "jp_csr_destroy": [c_i64],
     "jp_csr_info": [c_i64, c_vp],
     "jp_csr_download": [c_i64, c_vp, c_vp, c_vp],
+    "jp_csr_spmm_info": [c_i64, c_vp],
     "jp_csr_fill_complete": [c_i32, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i32, P(c_i64), c_vp],
     "jp_csr_col_map": [c_i64, c_vp],
     "jp_mv_create": [c_i32, c_i32, P(c_i64)],

@@ -194,6 +194,62 @@ void build_tiles(Csr& A) {
   A.tile_state = 1;
 }
 
+// Build the tables of the SpMM runs path (lazily, at the first k > 1 apply); one-time host cost like build_tiles.
+void build_runs(Csr& A) {
+  if (A.nnz == 0 || A.n_rows == 0 || env_int("JP_SPMM_RUNS", 0) == 0) {  // opt-in until measured on the GPU (profiles/)
+    A.runs_state = -1;
+    return;
+  }
+  const int cap = env_int("JP_SPMM_RUNS_CAP", 2048);
+  const int kt = env_int("JP_SPMM_RUNS_KT", 4);
+  JP_REQUIRE(cap >= 256 && cap <= 8192 && cap % 4 == 0, "JP_SPMM_RUNS_CAP must be a multiple of 4 in [256,8192]");
+  JP_REQUIRE(kt == 4 || kt == 8, "JP_SPMM_RUNS_KT must be 4 or 8");
+  std::vector<int32_t> ci((size_t)A.nnz), rp((size_t)A.n_rows + 1);
+  JP_CUDA(cudaStreamSynchronize(ctx().compute));
+  JP_CUDA(cudaMemcpy(ci.data(), A.colind.p, (size_t)A.nnz * 4, cudaMemcpyDeviceToHost));
+  JP_CUDA(cudaMemcpy(rp.data(), A.rowptr.p, rp.size() * 4, cudaMemcpyDeviceToHost));
+  std::vector<uint8_t> cls((size_t)A.n_rows, 0);
+  for (int32_t r = 0; r < A.n_rows; ++r) {
+    int32_t mx = -1;
+    for (int32_t i = rp[r]; i < rp[r + 1]; ++i) mx = std::max(mx, ci[i]);
+    cls[r] = mx >= A.n_local_cols;
+  }
+  std::vector<BlockDesc> bi, bb, ba;
+  build_blocks(rp, cls, cap, kRunsMaxRows, true, bi, bb, ba);
+  // the widest tile that still leaves two CTAs per SM
+  const int max_tile_cols = (int)((110 * 1024 - (int64_t)runs_smem_bytes(cap, 0, kt)) / (8 * kt)) & ~1;
+  RunTables t;
+  if (max_tile_cols < 64 || !build_run_tables(ci, ba, max_tile_cols, t)) {
+    A.runs_state = -1;
+    return;
+  }
+  size_t j = 0;  // the interior list is a subsequence of the all-list
+  for (BlockDesc& d : bi) {
+    while (ba[j].row0 != d.row0) ++j;
+    d = ba[j];
+  }
+  A.runs.alloc(t.runs.size() * 4);
+  A.runs_lidx.alloc(t.lidx.size() * 2);
+  JP_CUDA(cudaMemcpy(A.runs.p, t.runs.data(), t.runs.size() * 4, cudaMemcpyHostToDevice));
+  JP_CUDA(cudaMemcpy(A.runs_lidx.p, t.lidx.data(), t.lidx.size() * 2, cudaMemcpyHostToDevice));
+  upload_blocks(ba, A.runs_blocks_all, A.n_runs_blocks_all);
+  upload_blocks(bi, A.runs_blocks_interior, A.n_runs_blocks_interior);
+  A.runs_wmax = t.wmax;
+  A.runs_cap = cap;
+  A.runs_kt = kt;
+  A.runs_state = 1;
+}
+
+template <int KT>
+void launch_spmm_runs_impl(const Csr& A, const BlockDesc* b, int32_t n_blocks, const double* x, int64_t ldx, double* y, int64_t ldy, int32_t k,
+                           double alpha, double beta, cudaStream_t stream) {
+  const int wpad = (A.runs_wmax + 1) & ~1;
+  const size_t smem = runs_smem_bytes(A.runs_cap, wpad, KT);
+  set_smem_attr(spmm_runs_kernel<KT>, smem);
+  spmm_runs_kernel<KT><<<n_blocks, kRunsThreads, smem, stream>>>(b, A.rowptr.as<int32_t>(), A.vals.as<double>(), A.runs_lidx.as<uint16_t>(),
+                                                                  A.runs.as<int2>(), x, ldx, y, ldy, k, A.runs_cap, wpad, alpha, beta);
+}
+
 template <bool HALO>
 void launch_spmm_tile(const Csr& A, const BlockDesc* b, int32_t n_blocks, const double* x, int64_t ldx, const double* halo, int32_t halo_k,
                       double* y, int64_t ldy, int32_t k, double alpha, double beta, cudaStream_t stream) {
@@ -287,6 +343,20 @@ void launch_spmv_blocks(const Csr& A, const void* blocks_int4, int32_t n_blocks,
   if (k > 1 && A.tile_state == 0) {
     // lazily build the SpMM tile tables; the block lists are re-uploaded in place (same buffers, same order)
     build_tiles(const_cast<Csr&>(A));
+  }
+  if (k > 1 && A.runs_state == 0) build_runs(const_cast<Csr&>(A));
+  if (k > 1 && A.runs_state == 1 && !use_halo && (ldx & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+      (blocks_int4 == A.blocks_all.p || blocks_int4 == A.blocks_interior.p)) {
+    // banded matrix, no halo columns in this launch: the run-staged kernel on its own (64-row) block list
+    const bool all = blocks_int4 == A.blocks_all.p;
+    const BlockDesc* rb = (all ? A.runs_blocks_all : A.runs_blocks_interior).as<BlockDesc>();
+    const int32_t rn = all ? A.n_runs_blocks_all : A.n_runs_blocks_interior;
+    if (rn > 0) {
+      if (A.runs_kt == 8) launch_spmm_runs_impl<8>(A, rb, rn, x, ldx, y, ldy, k, alpha, beta, stream);
+      else launch_spmm_runs_impl<4>(A, rb, rn, x, ldx, y, ldy, k, alpha, beta, stream);
+      JP_LAUNCH_CHECK();
+    }
+    return;
   }
   const size_t smem = stage_smem_bytes(A.nnz_cap);
   const BlockDesc* b = static_cast<const BlockDesc*>(blocks_int4);
@@ -454,6 +524,17 @@ int32_t jp_csr_info(jp_handle A, int64_t* info) {
     info[5] = a->n_blocks_boundary;
     info[6] = a->max_row_len;
     info[7] = a->threads_per_row;
+  });
+}
+
+int32_t jp_csr_spmm_info(jp_handle A, int64_t* info) {
+  return guarded([&] {
+    Csr* a = get<Csr>(A, Kind::Csr, "csr matrix");
+    JP_REQUIRE(info != nullptr, "jp_csr_spmm_info: null output");
+    info[0] = a->tile_state;
+    info[1] = a->runs_state;
+    info[2] = a->n_runs_blocks_all;
+    info[3] = a->runs_wmax;
   });
 }
 

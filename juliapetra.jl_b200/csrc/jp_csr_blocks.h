@@ -108,5 +108,94 @@ inline bool build_tile_tables(const std::vector<int32_t>& ci, std::vector<BlockD
   return true;
 }
 
+
+// SpMM "runs" path (spmm_runs_kernel): per block the columns it references, merged into 16-byte ALIGNED RUNS
+// (start even, length even) so that the block's X tile can be copied global -> shared with 16-byte cp.async, and per
+// nonzero the uint16 position of its column in the concatenated runs.  Returns false when the matrix is not banded
+// enough for this to pay (tile wider than 0.7 nnz on average), when a block's tile does not fit, or with LONGROW blocks.
+struct RunTables {
+  std::vector<int32_t> runs;   // (start column, length) pairs, block b's at [2*ucol0, 2*(ucol0 + ucount))
+  std::vector<uint16_t> lidx;  // per nonzero
+  int32_t wmax = 0;            // widest tile (columns)
+};
+
+inline bool build_run_tables(const std::vector<int32_t>& ci, std::vector<BlockDesc>& all, int32_t max_tile_cols, RunTables& out) {
+  const size_t nb = all.size();
+  const size_t nnz = ci.size();
+  out.lidx.assign(nnz + 64, 0);
+  std::vector<std::vector<int32_t>> block_runs(nb);
+  std::vector<int32_t> width(nb, 0);
+  const int nthreads = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  bool reject = false;  // (benign race: only ever set to true)
+  auto worker = [&](int tix) {
+    std::vector<int32_t> u, base;
+    for (size_t bi = tix; bi < nb; bi += nthreads) {
+      const BlockDesc& b = all[bi];
+      if ((b.nrows_kind >> 16) == KIND_LONGROW) {
+        reject = true;
+        continue;
+      }
+      u.assign(ci.begin() + b.p0, ci.begin() + b.p1);
+      std::sort(u.begin(), u.end());
+      u.erase(std::unique(u.begin(), u.end()), u.end());
+      std::vector<int32_t>& runs = block_runs[bi];
+      base.clear();
+      int32_t w = 0, cur_end = -1;
+      for (int32_t c : u) {
+        if (c < cur_end) continue;  // covered by the aligned tail of the current run
+        if (!runs.empty() && (c & ~1) == cur_end) {
+          runs.back() += 2;  // extend
+        } else {
+          runs.push_back(c & ~1);
+          runs.push_back(2);
+          base.push_back(w);
+        }
+        cur_end = (c | 1) + 1;
+        w += 2;
+      }
+      width[bi] = w;
+      if (w > max_tile_cols || w > 65534) {
+        reject = true;
+        continue;
+      }
+      const size_t nr = runs.size() / 2;
+      for (int32_t i = b.p0; i < b.p1; ++i) {
+        const int32_t c = ci[i];
+        size_t lo = 0, hi = nr;  // last run with start <= c
+        while (hi - lo > 1) {
+          const size_t mid = (lo + hi) / 2;
+          if (runs[2 * mid] <= c) lo = mid;
+          else hi = mid;
+        }
+        out.lidx[i] = (uint16_t)(base[lo] + (c - runs[2 * lo]));
+      }
+    }
+  };
+  {
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t) th.emplace_back(worker, t);
+    worker(0);
+    for (auto& t : th) t.join();
+  }
+  if (reject) return false;
+  int64_t sum_w = 0, sum_nnz = 0, off = 0;
+  int32_t wmax = 0;
+  for (size_t bi = 0; bi < nb; ++bi) {
+    BlockDesc& b = all[bi];
+    b.ucol0 = (int32_t)off;
+    b.ucount = (int32_t)(block_runs[bi].size() / 2);
+    b.pad0 = width[bi];
+    off += b.ucount;
+    wmax = std::max(wmax, width[bi]);
+    sum_w += width[bi];
+    sum_nnz += b.p1 - b.p0;
+  }
+  if (sum_nnz == 0 || (double)sum_w > 0.7 * (double)sum_nnz || off > INT32_MAX / 2 - 64) return false;
+  out.runs.assign((size_t)off * 2 + 64, 0);
+  for (size_t bi = 0; bi < nb; ++bi) std::copy(block_runs[bi].begin(), block_runs[bi].end(), out.runs.begin() + 2 * (size_t)all[bi].ucol0);
+  out.wmax = wmax;
+  return true;
+}
+
 }  // namespace csrk
 }  // namespace jp

@@ -667,6 +667,114 @@ spmm_pipe_kernel(const BlockDesc* __restrict__ blocks, int32_t n_blocks, const i
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// SpMM with the block's X tile staged through ALIGNED COLUMN RUNS (banded / stencil-like matrices), many small CTAs.
+// Lessons of the two kernels above (profiles/r1_ncu_spmm_powerlaw_summary.txt): gathering X through L1 costs ~3x the
+// wavefronts of a shared-memory read, and a tile that is gathered through registers AFTER the matrix stage has landed
+// serialises two global-memory latencies per block at 3 CTAs/SM.  Here
+//   * a block is at most kRunsMaxRows rows; the columns it references are merged at build time into 16-byte aligned
+//     runs (a 27-point block of 64 rows = 9 runs of 66 columns), and every nonzero carries the uint16 position of its
+//     column in the concatenated runs;
+//   * ONE thread issues the TMA bulk copies of vals / positions / row pointers, while ALL threads issue 16-byte
+//     cp.async copies of the runs straight from X into the tile (no registers, no dependency on the matrix stage: the
+//     run list is read from global memory), so both latencies overlap;
+//   * then T lanes per row accumulate KT vectors out of shared memory: consecutive lanes are consecutive rows, their
+//     tile positions are consecutive -> conflict-free LDS.64;
+//   * 128 threads and ~40 KB (KT = 4) of shared memory per CTA -> 5 CTAs/SM keep the LDS pipe busy while other CTAs
+//     wait for their copies.
+// X must be 16-byte aligned with an even leading dimension (the launcher checks; otherwise the gather kernel runs).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kRunsThreads = 128;
+constexpr int kRunsMaxRows = 64;
+
+__host__ __device__ inline size_t runs_smem_bytes(int cap, int wpad, int KT) {
+  return (size_t)(cap + 8) * 8 + (size_t)KT * wpad * 8 + (size_t)(kRunsMaxRows + 8) * 4 + (size_t)(cap + 16) * 2;
+}
+
+template <int KT>
+__global__ void __launch_bounds__(kRunsThreads)
+spmm_runs_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ rowptr, const double* __restrict__ vals,
+                 const uint16_t* __restrict__ lidx, const int2* __restrict__ runs, const double* __restrict__ x, int64_t ldx,
+                 double* __restrict__ y, int64_t ldy, int32_t k, int32_t cap, int32_t wpad, double alpha, double beta) {
+  JP_DYN_SMEM(smem_raw);
+  __shared__ __align__(8) uint64_t s_bar;
+  double* s_val = reinterpret_cast<double*>(smem_raw);                  // [cap + 8]
+  double* xs = s_val + cap + 8;                                          // [KT][wpad]
+  int32_t* s_rp = reinterpret_cast<int32_t*>(xs + (size_t)KT * wpad);    // [kRunsMaxRows + 8]
+  uint16_t* s_lidx = reinterpret_cast<uint16_t*>(s_rp + kRunsMaxRows + 8);  // [cap + 16]
+  const BlockRange b = decode_block(blocks, blockIdx.x);
+  const int4 aux = __ldg(reinterpret_cast<const int4*>(blocks + blockIdx.x) + 1);
+  const int run0 = aux.x, nruns = aux.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // matrix stage: vals, tile positions, row pointers (three TMA bulk copies by one thread)
+  const int ngrp = (b.p1 - b.a0 + 3) >> 2;
+  const int al0 = b.p0 & ~7;               // 16-byte aligned first staged position
+  const int nl8 = (b.p1 - al0 + 7) & ~7;   // positions staged (multiple of 8)
+  const int ra0 = b.row0 & ~3;
+  const int nrp = (b.row0 + b.nrows + 1 - ra0 + 3) & ~3;
+  if (tid == 0) mbar_init(&s_bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    const uint64_t pol = policy_evict_first();
+    mbar_expect_tx(&s_bar, (unsigned)(ngrp * 32 + nl8 * 2 + nrp * 4));
+    if (ngrp > 0) bulk_g2s(s_val, vals + b.a0, (unsigned)ngrp * 32, &s_bar, pol);
+    if (nl8 > 0) bulk_g2s(s_lidx, lidx + al0, (unsigned)nl8 * 2, &s_bar, pol);
+    bulk_g2s(s_rp, rowptr + ra0, (unsigned)nrp * 4, &s_bar, pol);
+  }
+  // lanes per row: as many as keep every thread busy, at most 4 (block-uniform, power of two)
+  int T = 1;
+  while (T < 4 && b.nrows * (T << 1) <= kRunsThreads) T <<= 1;
+  const int lane_t = tid & (T - 1), group = tid / T, ngroups = kRunsThreads / T;
+  for (int v0 = 0; v0 < k; v0 += KT) {
+    const int kt = k - v0 < KT ? k - v0 : KT;
+    // X tile: a warp per run, lanes over (vector, 16-byte chunk); xs[j][base + c - start] = X[c, v0 + j]
+    int base = 0;
+    for (int q = 0; q < nruns; ++q) {  // block-uniform; every warp walks the run list to keep `base` without a table
+      const int2 run = __ldg(runs + run0 + q);
+      if ((q & (kRunsThreads / 32 - 1)) == warp) {
+        const int chunks = run.y >> 1;
+        const double* src = x + (size_t)v0 * ldx + run.x;
+        for (int idx = lane; idx < kt * chunks; idx += 32) {
+          const int j = idx / chunks, t = idx - j * chunks;
+          cp_async16(xs + (size_t)j * wpad + base + 2 * t, src + (size_t)j * ldx + 2 * t);
+        }
+      }
+      base += run.y;
+    }
+    cp_async_wait_all();
+    if (v0 == 0) mbar_wait(&s_bar, 0);
+    __syncthreads();
+    const int32_t* rp = s_rp + b.rpo;
+    for (int rbase = 0; rbase < b.nrows; rbase += ngroups) {  // warp-uniform trip count (shuffles below)
+      const int r = rbase + group;
+      const bool valid = r < b.nrows;
+      const int s = valid ? rp[r] : 0, e = valid ? rp[r + 1] : 0;
+      double acc[KT];
+#pragma unroll
+      for (int j = 0; j < KT; ++j) acc[j] = 0.0;
+      for (int i = s + lane_t; i < e; i += T) {
+        const int li = s_lidx[i - al0];
+        const double v = s_val[i - b.a0];
+#pragma unroll
+        for (int j = 0; j < KT; ++j) acc[j] = fma(v, xs[(size_t)j * wpad + li], acc[j]);
+      }
+      for (int o = T >> 1; o > 0; o >>= 1) {
+#pragma unroll
+        for (int j = 0; j < KT; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+      }
+      if (valid && lane_t == 0) {
+#pragma unroll
+        for (int j = 0; j < KT; ++j)
+          if (j < kt) {
+            double* yp = y + b.row0 + r + (size_t)(v0 + j) * ldy;
+            *yp = combine(beta == 0.0 ? 0.0 : *yp, acc[j], alpha, beta);
+          }
+      }
+    }
+    __syncthreads();  // the next vector tile overwrites xs
+  }
+}
+
 // TRANS / CONJ_TRANS (src/CSRMatrix.jl:1147-1160): Y[ind, v] += (alpha * X[row, v]) * val, after Y *= beta.
 // Scatter with fp64 atomics (RED.ADD.F64): the summation order differs from the reference's row sweep, within
 // the 1e-12 contract.  Warp per row, lanes over the row's entries.

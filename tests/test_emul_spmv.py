@@ -65,13 +65,13 @@ def test_spmv_with_halo_buffer():
     assert (np.abs(got - ref) <= _bound(rp, ci, va, x, y0, 3.0, 0.5)).all()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])  # gather, tile, pipelined tile, runs (KT = 4), runs (KT = 8)
 @pytest.mark.parametrize("k", [2, 8, 11])
 def test_spmm_kernels(variant, k):
     rp, ci, va = _problem("27pt", 6)
     n = len(rp) - 1
     x, y0 = _vectors(n, n, k)
-    for halo in (False, True):
+    for halo in ((False,) if variant >= 3 else (False, True)):  # the runs kernel serves launches without halo columns
         got, st = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, variant=variant, T=2, n_local_cols=n - 40 if halo else None,
                                    halo_split=halo)
         assert got is not None
@@ -87,5 +87,17 @@ def test_spmm_irregular_rows():
         got, st = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, cap=cap, T=4)
         ref = _oracle(rp, ci, va, x, y0, 3.0, 0.5)
         assert (np.abs(got - ref) <= _bound(rp, ci, va, x, y0, 3.0, 0.5)).all()
-    got, st = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, variant=1)
-    assert got is None  # random columns: the tile tables are rejected and the gather kernel is used
+    for variant in (1, 3):
+        got, st = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, variant=variant)
+        assert got is None  # random columns: the tile / run tables are rejected and the gather kernel is used
+
+
+@pytest.mark.parametrize("kind,N", [("5pt", 20), ("7pt", 8)])
+def test_spmm_runs_kernel_other_stencils(kind, N):
+    rp, ci, va = _problem(kind, N)
+    n = len(rp) - 1
+    x, y0 = _vectors(n, n, 5)
+    for variant, cap in ((3, 2048), (4, 256)):
+        got, st = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, variant=variant, cap=cap)
+        ref = _oracle(rp, ci, va, x, y0, 3.0, 0.5)
+        assert (np.abs(got - ref) <= _bound(rp, ci, va, x, y0, 3.0, 0.5)).all()

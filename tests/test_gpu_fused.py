@@ -45,7 +45,11 @@ def test_apply_dot_multivector_and_transposed_fall_back_to_two_kernels():
         A.apply_(Y1, X, mode, 2.0, 0.0)
         d1 = X.dot(Y1)
         d2 = A.apply_dot_(Y2, X, None, mode, 2.0, 0.0)
-        assert np.array_equal(Y1.data, Y2.data) and np.array_equal(d1, d2)
+        if mode == jp.NO_TRANS:
+            assert np.array_equal(Y1.data, Y2.data) and np.array_equal(d1, d2)
+        else:  # the transposed kernel scatters with atomics: the summation order differs from run to run
+            ref = np.abs(Y1.data).max()
+            assert np.abs(Y1.data - Y2.data).max() <= 1e-12 * ref and (np.abs(d1 - d2) <= 1e-12 * np.abs(x).T @ np.abs(Y1.data) @ np.ones(3)).all()
 
 
 @pytest.mark.parametrize("n,k", [(1, 1), (1000, 1), (300001, 2)])

@@ -436,6 +436,22 @@ def test_spmm_shared_memory_tile_path(monkeypatch, k):
     check_apply(A, x, y0, 1.0, 0.0, exact=False)
 
 
+@pytest.mark.parametrize("kt", ["4", "8"])
+@pytest.mark.parametrize("kind,N,k", [("27pt", 20, 8), ("27pt", 20, 11), ("7pt", 24, 3), ("5pt", 60, 32)])
+def test_spmm_run_staged_path(monkeypatch, kind, N, k, kt):
+    """opt-in SpMM kernel that stages the block's X tile through aligned column runs with cp.async (JP_SPMM_RUNS=1)"""
+    monkeypatch.setenv("JP_SPMM_RUNS", "1")
+    monkeypatch.setenv("JP_SPMM_RUNS_KT", kt)
+    c, m, A = serial_matrix(kind, N)
+    n = m.numMyElements()
+    x = synthetic.vector_block(1, n, k, seed=1)
+    y0 = synthetic.vector_block(1, n, k, seed=2)
+    check_apply(A, x, y0, 3.0, 0.5, exact=False)
+    check_apply(A, x, y0, 1.0, 0.0, exact=False)
+    info = A.spmm_info()
+    assert info["runs_state"] == 1 and info["runs_blocks"] > 0, info  # the run-staged kernel really ran
+
+
 def test_full_size_7pt_256_properties_and_oracle():
     """BASELINE configs[1] at full size on one GPU: size-independent properties, then the whole vector against the
     oracle (bit-exact: every block of a stencil is thread-per-row in the reference's summation order)."""

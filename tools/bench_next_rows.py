@@ -72,6 +72,33 @@ def main():
         cg["fused" if fused else "separate"] = {"iterations": its, "ms_per_iteration": per_it, "rel_residual": rel,
                                                 "algorithmic_gbs": bytes_it / per_it / 1e6}
     out["cg"] = cg
+
+    # ---- the building blocks one by one (ms per call, device events; dot/norm include their host synchronisation) ----
+    def timed(fn, reps=50):
+        for _ in range(5):
+            fn()
+        lib.jp_synchronize()
+        _lib.check(lib.jp_event_record(e0.value))
+        for _ in range(reps):
+            fn()
+        _lib.check(lib.jp_event_record(e1.value))
+        ms = C.c_double()
+        _lib.check(lib.jp_event_elapsed_ms(e0.value, e1.value, C.byref(ms)))
+        return ms.value / reps
+
+    P = jp.DenseMultiVector(m, xs)
+    Ap = jp.DenseMultiVector(m, 1)
+    R = jp.DenseMultiVector(m, synthetic.vector_block(1, n, 1, seed=9))
+    out["ops_ms"] = {
+        "apply": timed(lambda: Ah.apply_(Ap, P)),
+        "apply_then_dot": timed(lambda: (Ah.apply_(Ap, P), P.dot(Ap))),
+        "apply_dot": timed(lambda: Ah.apply_dot_(Ap, P)),
+        "dot": timed(lambda: P.dot(Ap)),
+        "norm2": timed(lambda: R.norm(2)),
+        "axpby": timed(lambda: R.axpby_(-1e-9, Ap, 1.0)),
+        "axpby_then_norm2": timed(lambda: (R.axpby_(-1e-9, Ap, 1.0), R.norm(2))),
+        "axpby_norm2": timed(lambda: R.axpby_norm2_(-1e-9, Ap, 1.0)),
+    }
     print(json.dumps(out))
 
 

@@ -1,0 +1,90 @@
+#!/usr/bin/env python
+"""A/B of the SpMM kernels on one GPU (BASELINE configs[2] family: 3-D 27-point stencil, k = 8 and 32): the matrix is
+built once on the host and uploaded once per variant (the path is chosen per matrix from the environment at its first
+k > 1 apply).  Device-event time per localApply, algorithmic GB/s (nnz*12 + (n+1)*4 + 16*n*k) and the maximum
+difference from the gather kernel's result.  Prints one JSON object.
+Usage: python tools/bench_spmm.py [--N 128] [--kind 27pt] [--reps 20]"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import jpetra_b200 as jp  # noqa: E402
+from jpetra_b200 import _lib, synthetic  # noqa: E402
+
+VARIANTS = [
+    ("gather", {}),
+    ("runs_kt4", {"JP_SPMM_RUNS": "1", "JP_SPMM_RUNS_KT": "4"}),
+    ("runs_kt8", {"JP_SPMM_RUNS": "1", "JP_SPMM_RUNS_KT": "8"}),
+    ("runs_kt4_cap1024", {"JP_SPMM_RUNS": "1", "JP_SPMM_RUNS_KT": "4", "JP_SPMM_RUNS_CAP": "1024"}),
+]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--N", type=int, default=128)
+    ap.add_argument("--kind", default="27pt")
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--ks", default="8,32")
+    ap.add_argument("--variants", default="")
+    args = ap.parse_args()
+    lib = _lib.init(0)
+    comm = jp.SerialComm()
+    N, kind = args.N, args.kind
+    n = N ** synthetic.STENCILS[kind][0]
+    m = jp.BlockMap(n, comm)
+    A = synthetic.build_matrix(jp, m, kind, N)
+    rp, ci, va = A.rowOffsets, A.localIndices1D, A.values
+    nnz = len(va)
+    peak = 6531.9
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peak = json.load(open(pk)).get("hbm_gbs", peak)
+    e0, e1 = C.c_int64(), C.c_int64()
+    _lib.check(lib.jp_event_create(C.byref(e0)))
+    _lib.check(lib.jp_event_create(C.byref(e1)))
+    out = {"kind": kind, "N": N, "n": n, "nnz": nnz, "peak_gbs": peak, "cases": []}
+    ref = {}
+    keep = [v for v in args.variants.split(",") if v]
+    for label, env in VARIANTS:
+        if keep and label not in keep:
+            continue
+        for key in ("JP_SPMM_RUNS", "JP_SPMM_RUNS_KT", "JP_SPMM_RUNS_CAP", "JP_SPMM_TILE"):
+            os.environ.pop(key, None)
+        os.environ.update(env)
+        h = C.c_int64()
+        _lib.check(lib.jp_csr_create(n, n, n, nnz, _lib.ptr(rp), _lib.ptr(ci), _lib.ptr(va), 1, C.byref(h)))
+        for k in (int(s) for s in args.ks.split(",")):
+            X = jp.DenseMultiVector(m, synthetic.vector_block(1, n, k, seed=1))
+            Y = jp.DenseMultiVector(m, k)
+            for _ in range(3):
+                _lib.check(lib.jp_local_apply(Y.h, h.value, X.h, 1, 1.0, 0.0))
+            lib.jp_synchronize()
+            _lib.check(lib.jp_event_record(e0.value))
+            for _ in range(args.reps):
+                _lib.check(lib.jp_local_apply(Y.h, h.value, X.h, 1, 1.0, 0.0))
+            _lib.check(lib.jp_event_record(e1.value))
+            ms = C.c_double()
+            _lib.check(lib.jp_event_elapsed_ms(e0.value, e1.value, C.byref(ms)))
+            t = ms.value / args.reps
+            y = Y.data
+            if label == "gather":
+                ref[k] = y
+            info = np.zeros(4, dtype=np.int64)
+            _lib.check(lib.jp_csr_spmm_info(h.value, _lib.ptr(info)))
+            gbs = (nnz * 12 + (n + 1) * 4 + 16 * n * k) / t / 1e6
+            out["cases"].append({"variant": label, "k": k, "ms": t, "algorithmic_gbs": gbs, "frac_of_peak": gbs / peak,
+                                 "gflops": 2.0 * nnz * k / t / 1e6, "runs_state": int(info[1]), "widest_tile": int(info[3]),
+                                 "max_abs_diff_vs_gather": float(np.abs(y - ref[k]).max()) if k in ref else None})
+            del X, Y
+        _lib.check(lib.jp_csr_destroy(h.value))
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
