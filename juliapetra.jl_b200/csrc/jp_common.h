@@ -198,7 +198,7 @@ struct Csr : Object {
   // SpMM runs path (spmm_runs_kernel; built lazily at the first k > 1 apply): its own row blocks (<= 64 rows), the
   // aligned column runs of every block and the uint16 tile position of every nonzero
   int runs_state = 0;        // 0 = not built, 1 = active, -1 = not usable / disabled
-  int32_t runs_wmax = 0, runs_cap = 0, runs_kt = 4;
+  int32_t runs_wmax = 0, runs_cap = 0, runs_kt = 4, runs_threads = 128;
   DeviceBuffer runs, runs_lidx, runs_blocks_all, runs_blocks_interior;
   int32_t n_runs_blocks_all = 0, n_runs_blocks_interior = 0;
   // cache of the column-map multivector (A.importMV, src/CSRMatrix.jl:10,772-781); only used when the column

@@ -204,6 +204,8 @@ void build_runs(Csr& A) {
   const int kt = env_int("JP_SPMM_RUNS_KT", 4);
   JP_REQUIRE(cap >= 256 && cap <= 8192 && cap % 4 == 0, "JP_SPMM_RUNS_CAP must be a multiple of 4 in [256,8192]");
   JP_REQUIRE(kt == 4 || kt == 8, "JP_SPMM_RUNS_KT must be 4 or 8");
+  const int threads = env_int("JP_SPMM_RUNS_THREADS", 128);
+  JP_REQUIRE(threads == 128 || threads == 256, "JP_SPMM_RUNS_THREADS must be 128 or 256");
   std::vector<int32_t> ci((size_t)A.nnz), rp((size_t)A.n_rows + 1);
   JP_CUDA(cudaStreamSynchronize(ctx().compute));
   JP_CUDA(cudaMemcpy(ci.data(), A.colind.p, (size_t)A.nnz * 4, cudaMemcpyDeviceToHost));
@@ -237,17 +239,18 @@ void build_runs(Csr& A) {
   A.runs_wmax = t.wmax;
   A.runs_cap = cap;
   A.runs_kt = kt;
+  A.runs_threads = threads;
   A.runs_state = 1;
 }
 
-template <int KT>
+template <int KT, int THREADS>
 void launch_spmm_runs_impl(const Csr& A, const BlockDesc* b, int32_t n_blocks, const double* x, int64_t ldx, double* y, int64_t ldy, int32_t k,
                            double alpha, double beta, cudaStream_t stream) {
   const int wpad = (A.runs_wmax + 1) & ~1;
   const size_t smem = runs_smem_bytes(A.runs_cap, wpad, KT);
-  set_smem_attr(spmm_runs_kernel<KT>, smem);
-  spmm_runs_kernel<KT><<<n_blocks, kRunsThreads, smem, stream>>>(b, A.rowptr.as<int32_t>(), A.vals.as<double>(), A.runs_lidx.as<uint16_t>(),
-                                                                  A.runs.as<int2>(), x, ldx, y, ldy, k, A.runs_cap, wpad, alpha, beta);
+  set_smem_attr(spmm_runs_kernel<KT, THREADS>, smem);
+  spmm_runs_kernel<KT, THREADS><<<n_blocks, THREADS, smem, stream>>>(b, A.rowptr.as<int32_t>(), A.vals.as<double>(), A.runs_lidx.as<uint16_t>(),
+                                                                      A.runs.as<int2>(), x, ldx, y, ldy, k, A.runs_cap, wpad, alpha, beta);
 }
 
 template <bool HALO>
@@ -352,8 +355,10 @@ void launch_spmv_blocks(const Csr& A, const void* blocks_int4, int32_t n_blocks,
     const BlockDesc* rb = (all ? A.runs_blocks_all : A.runs_blocks_interior).as<BlockDesc>();
     const int32_t rn = all ? A.n_runs_blocks_all : A.n_runs_blocks_interior;
     if (rn > 0) {
-      if (A.runs_kt == 8) launch_spmm_runs_impl<8>(A, rb, rn, x, ldx, y, ldy, k, alpha, beta, stream);
-      else launch_spmm_runs_impl<4>(A, rb, rn, x, ldx, y, ldy, k, alpha, beta, stream);
+      if (A.runs_kt == 8 && A.runs_threads == 256) launch_spmm_runs_impl<8, 256>(A, rb, rn, x, ldx, y, ldy, k, alpha, beta, stream);
+      else if (A.runs_kt == 8) launch_spmm_runs_impl<8, 128>(A, rb, rn, x, ldx, y, ldy, k, alpha, beta, stream);
+      else if (A.runs_threads == 256) launch_spmm_runs_impl<4, 256>(A, rb, rn, x, ldx, y, ldy, k, alpha, beta, stream);
+      else launch_spmm_runs_impl<4, 128>(A, rb, rn, x, ldx, y, ldy, k, alpha, beta, stream);
       JP_LAUNCH_CHECK();
     }
     return;

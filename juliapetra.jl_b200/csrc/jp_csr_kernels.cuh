@@ -680,19 +680,18 @@ spmm_pipe_kernel(const BlockDesc* __restrict__ blocks, int32_t n_blocks, const i
 //     run list is read from global memory), so both latencies overlap;
 //   * then T lanes per row accumulate KT vectors out of shared memory: consecutive lanes are consecutive rows, their
 //     tile positions are consecutive -> conflict-free LDS.64;
-//   * 128 threads and ~40 KB (KT = 4) of shared memory per CTA -> 5 CTAs/SM keep the LDS pipe busy while other CTAs
-//     wait for their copies.
+//   * 128 or 256 threads and ~40 KB (KT = 4) of shared memory per CTA -> 5 CTAs/SM keep the LDS pipe busy while other
+//     CTAs wait for their copies.
 // X must be 16-byte aligned with an even leading dimension (the launcher checks; otherwise the gather kernel runs).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kRunsThreads = 128;
 constexpr int kRunsMaxRows = 64;
 
 __host__ __device__ inline size_t runs_smem_bytes(int cap, int wpad, int KT) {
   return (size_t)(cap + 8) * 8 + (size_t)KT * wpad * 8 + (size_t)(kRunsMaxRows + 8) * 4 + (size_t)(cap + 16) * 2;
 }
 
-template <int KT>
-__global__ void __launch_bounds__(kRunsThreads)
+template <int KT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 spmm_runs_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ rowptr, const double* __restrict__ vals,
                  const uint16_t* __restrict__ lidx, const int2* __restrict__ runs, const double* __restrict__ x, int64_t ldx,
                  double* __restrict__ y, int64_t ldy, int32_t k, int32_t cap, int32_t wpad, double alpha, double beta) {
@@ -700,7 +699,7 @@ spmm_runs_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict
   __shared__ __align__(8) uint64_t s_bar;
   double* s_val = reinterpret_cast<double*>(smem_raw);                  // [cap + 8]
   double* xs = s_val + cap + 8;                                          // [KT][wpad]
-  int32_t* s_rp = reinterpret_cast<int32_t*>(xs + (size_t)KT * wpad);    // [kRunsMaxRows + 8]
+  int32_t* s_rp = reinterpret_cast<int32_t*>(xs + KT * wpad);            // [kRunsMaxRows + 8]
   uint16_t* s_lidx = reinterpret_cast<uint16_t*>(s_rp + kRunsMaxRows + 8);  // [cap + 16]
   const BlockRange b = decode_block(blocks, blockIdx.x);
   const int4 aux = __ldg(reinterpret_cast<const int4*>(blocks + blockIdx.x) + 1);
@@ -723,20 +722,25 @@ spmm_runs_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict
   }
   // lanes per row: as many as keep every thread busy, at most 4 (block-uniform, power of two)
   int T = 1;
-  while (T < 4 && b.nrows * (T << 1) <= kRunsThreads) T <<= 1;
-  const int lane_t = tid & (T - 1), group = tid / T, ngroups = kRunsThreads / T;
+  while (T < 4 && b.nrows * (T << 1) <= THREADS) T <<= 1;
+  const int lane_t = tid & (T - 1), group = tid / T, ngroups = THREADS / T;
+  // the shared-memory views are indexed relative to the staged ranges
+  const double* val0 = s_val - b.a0;
+  const uint16_t* lidx0 = s_lidx - al0;
   for (int v0 = 0; v0 < k; v0 += KT) {
     const int kt = k - v0 < KT ? k - v0 : KT;
-    // X tile: a warp per run, lanes over (vector, 16-byte chunk); xs[j][base + c - start] = X[c, v0 + j]
+    // X tile: a warp per run, lanes over the run's 16-byte chunks, one pass per vector:
+    // xs[j][base + c - start] = X[c, v0 + j]
     int base = 0;
     for (int q = 0; q < nruns; ++q) {  // block-uniform; every warp walks the run list to keep `base` without a table
       const int2 run = __ldg(runs + run0 + q);
-      if ((q & (kRunsThreads / 32 - 1)) == warp) {
-        const int chunks = run.y >> 1;
+      if ((q & (THREADS / 32 - 1)) == warp) {
         const double* src = x + (size_t)v0 * ldx + run.x;
-        for (int idx = lane; idx < kt * chunks; idx += 32) {
-          const int j = idx / chunks, t = idx - j * chunks;
-          cp_async16(xs + (size_t)j * wpad + base + 2 * t, src + (size_t)j * ldx + 2 * t);
+        double* dst = xs + base;
+        for (int j = 0; j < kt; ++j) {
+          for (int t = 2 * lane; t < run.y; t += 64) cp_async16(dst + t, src + t);
+          src += ldx;
+          dst += wpad;
         }
       }
       base += run.y;
@@ -752,11 +756,12 @@ spmm_runs_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict
       double acc[KT];
 #pragma unroll
       for (int j = 0; j < KT; ++j) acc[j] = 0.0;
+#pragma unroll 2
       for (int i = s + lane_t; i < e; i += T) {
-        const int li = s_lidx[i - al0];
-        const double v = s_val[i - b.a0];
+        const int li = lidx0[i];
+        const double v = val0[i];
 #pragma unroll
-        for (int j = 0; j < KT; ++j) acc[j] = fma(v, xs[(size_t)j * wpad + li], acc[j]);
+        for (int j = 0; j < KT; ++j) acc[j] = fma(v, xs[j * wpad + li], acc[j]);
       }
       for (int o = T >> 1; o > 0; o >>= 1) {
 #pragma unroll

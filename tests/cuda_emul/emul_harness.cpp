@@ -153,11 +153,11 @@ int emul_local_apply(int32_t n_rows, int32_t n_cols, int32_t n_local_cols, const
       const int wpad = (t.wmax + 1) & ~1;
       const size_t sm = runs_smem_bytes(cap, wpad, kt);
       if (kt == 4)
-        JP_KLAUNCH(spmm_runs_kernel<4>, (unsigned)ra.size(), kRunsThreads, sm, nullptr, d_blocks.as<BlockDesc>(), d_rp.as<int32_t>(),
+        JP_KLAUNCH((spmm_runs_kernel<4, 128>), (unsigned)ra.size(), 128, sm, nullptr, d_blocks.as<BlockDesc>(), d_rp.as<int32_t>(),
                    d_va.as<double>(), d_lidx.as<uint16_t>(), d_ucols.as<int2>(), d_x.as<double>(), (int64_t)x_rows, d_y.as<double>(),
                    (int64_t)n_rows, k, cap, wpad, alpha, beta);
       else
-        JP_KLAUNCH(spmm_runs_kernel<8>, (unsigned)ra.size(), kRunsThreads, sm, nullptr, d_blocks.as<BlockDesc>(), d_rp.as<int32_t>(),
+        JP_KLAUNCH((spmm_runs_kernel<8, 256>), (unsigned)ra.size(), 256, sm, nullptr, d_blocks.as<BlockDesc>(), d_rp.as<int32_t>(),
                    d_va.as<double>(), d_lidx.as<uint16_t>(), d_ucols.as<int2>(), d_x.as<double>(), (int64_t)x_rows, d_y.as<double>(),
                    (int64_t)n_rows, k, cap, wpad, alpha, beta);
     }
