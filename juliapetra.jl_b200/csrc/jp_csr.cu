@@ -205,7 +205,9 @@ void build_runs(Csr& A) {
   JP_REQUIRE(cap >= 256 && cap <= 8192 && cap % 4 == 0, "JP_SPMM_RUNS_CAP must be a multiple of 4 in [256,8192]");
   JP_REQUIRE(kt == 4 || kt == 8, "JP_SPMM_RUNS_KT must be 4 or 8");
   const int threads = env_int("JP_SPMM_RUNS_THREADS", 128);
-  JP_REQUIRE(threads == 128 || threads == 256, "JP_SPMM_RUNS_THREADS must be 128 or 256");
+  JP_REQUIRE(threads == 64 || threads == 128 || threads == 256, "JP_SPMM_RUNS_THREADS must be 64, 128 or 256");
+  const int max_rows = env_int("JP_SPMM_RUNS_ROWS", 64);
+  JP_REQUIRE(max_rows >= 16 && max_rows <= kRunsMaxRows, "JP_SPMM_RUNS_ROWS must be in [16,128]");
   std::vector<int32_t> ci((size_t)A.nnz), rp((size_t)A.n_rows + 1);
   JP_CUDA(cudaStreamSynchronize(ctx().compute));
   JP_CUDA(cudaMemcpy(ci.data(), A.colind.p, (size_t)A.nnz * 4, cudaMemcpyDeviceToHost));
@@ -217,7 +219,7 @@ void build_runs(Csr& A) {
     cls[r] = mx >= A.n_local_cols;
   }
   std::vector<BlockDesc> bi, bb, ba;
-  build_blocks(rp, cls, cap, kRunsMaxRows, true, bi, bb, ba);
+  build_blocks(rp, cls, cap, max_rows, true, bi, bb, ba);
   // the widest tile that still leaves two CTAs per SM
   const int max_tile_cols = (int)((110 * 1024 - (int64_t)runs_smem_bytes(cap, 0, kt)) / (8 * kt)) & ~1;
   RunTables t;
@@ -358,6 +360,7 @@ void launch_spmv_blocks(const Csr& A, const void* blocks_int4, int32_t n_blocks,
       if (A.runs_kt == 8 && A.runs_threads == 256) launch_spmm_runs_impl<8, 256>(A, rb, rn, x, ldx, y, ldy, k, alpha, beta, stream);
       else if (A.runs_kt == 8) launch_spmm_runs_impl<8, 128>(A, rb, rn, x, ldx, y, ldy, k, alpha, beta, stream);
       else if (A.runs_threads == 256) launch_spmm_runs_impl<4, 256>(A, rb, rn, x, ldx, y, ldy, k, alpha, beta, stream);
+      else if (A.runs_threads == 64) launch_spmm_runs_impl<4, 64>(A, rb, rn, x, ldx, y, ldy, k, alpha, beta, stream);
       else launch_spmm_runs_impl<4, 128>(A, rb, rn, x, ldx, y, ldy, k, alpha, beta, stream);
       JP_LAUNCH_CHECK();
     }

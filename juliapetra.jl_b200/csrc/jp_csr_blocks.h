@@ -124,7 +124,7 @@ inline bool build_run_tables(const std::vector<int32_t>& ci, std::vector<BlockDe
   const size_t nnz = ci.size();
   out.lidx.assign(nnz + 64, 0);
   std::vector<std::vector<int32_t>> block_runs(nb);
-  std::vector<int32_t> width(nb, 0);
+  std::vector<int32_t> width(nb, 0), ncopied(nb, 0);
   const int nthreads = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
   bool reject = false;  // (benign race: only ever set to true)
   auto worker = [&](int tix) {
@@ -139,8 +139,7 @@ inline bool build_run_tables(const std::vector<int32_t>& ci, std::vector<BlockDe
       std::sort(u.begin(), u.end());
       u.erase(std::unique(u.begin(), u.end()), u.end());
       std::vector<int32_t>& runs = block_runs[bi];
-      base.clear();
-      int32_t w = 0, cur_end = -1;
+      int32_t cur_end = -1;
       for (int32_t c : u) {
         if (c < cur_end) continue;  // covered by the aligned tail of the current run
         if (!runs.empty() && (c & ~1) == cur_end) {
@@ -148,17 +147,23 @@ inline bool build_run_tables(const std::vector<int32_t>& ci, std::vector<BlockDe
         } else {
           runs.push_back(c & ~1);
           runs.push_back(2);
-          base.push_back(w);
         }
         cur_end = (c | 1) + 1;
-        w += 2;
+      }
+      const size_t nr = runs.size() / 2;
+      base.assign(nr, 0);
+      int32_t w = 0, copied = 0;
+      for (size_t q = 0; q < nr; ++q) {  // tile position of every run (padded strides: run_stride)
+        base[q] = w;
+        w += run_stride(runs[2 * q + 1]);
+        copied += runs[2 * q + 1];
       }
       width[bi] = w;
+      ncopied[bi] = copied;
       if (w > max_tile_cols || w > 65534) {
         reject = true;
         continue;
       }
-      const size_t nr = runs.size() / 2;
       for (int32_t i = b.p0; i < b.p1; ++i) {
         const int32_t c = ci[i];
         size_t lo = 0, hi = nr;  // last run with start <= c
@@ -184,10 +189,11 @@ inline bool build_run_tables(const std::vector<int32_t>& ci, std::vector<BlockDe
     BlockDesc& b = all[bi];
     b.ucol0 = (int32_t)off;
     b.ucount = (int32_t)(block_runs[bi].size() / 2);
-    b.pad0 = width[bi];
+    b.pad0 = width[bi];    // tile columns incl. the padding between runs
+    b.pad1 = ncopied[bi];  // columns actually copied (sum of the run lengths)
     off += b.ucount;
     wmax = std::max(wmax, width[bi]);
-    sum_w += width[bi];
+    sum_w += ncopied[bi];
     sum_nnz += b.p1 - b.p0;
   }
   if (sum_nnz == 0 || (double)sum_w > 0.7 * (double)sum_nnz || off > INT32_MAX / 2 - 64) return false;

@@ -684,7 +684,13 @@ spmm_pipe_kernel(const BlockDesc* __restrict__ blocks, int32_t n_blocks, const i
 //     CTAs wait for their copies.
 // X must be 16-byte aligned with an even leading dimension (the launcher checks; otherwise the gather kernel runs).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kRunsMaxRows = 64;
+constexpr int kRunsMaxRows = 128;  // upper bound of the rows-per-block setting (JP_SPMM_RUNS_ROWS, default 64)
+
+// Tile columns a run of `len` columns occupies: padded so that consecutive runs start 10 (mod 16) doubles apart.  With
+// two lanes per row, the iteration in which a lane pair straddles two runs reads [base_q + r + 2] and [base_q+1 + r]
+// for 8 consecutive rows r per half-warp; 10 apart puts the two 8-bank windows side by side instead of on top of each
+// other (profiles/r1_ncu_spmm_runs_summary.txt: 38 % of the shared-memory wavefronts were conflict replays without it).
+__host__ __device__ inline int run_stride(int len) { return len + ((10 - len) & 15); }
 
 __host__ __device__ inline size_t runs_smem_bytes(int cap, int wpad, int KT) {
   return (size_t)(cap + 8) * 8 + (size_t)KT * wpad * 8 + (size_t)(kRunsMaxRows + 8) * 4 + (size_t)(cap + 16) * 2;
@@ -713,9 +719,10 @@ spmm_runs_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict
   const int nrp = (b.row0 + b.nrows + 1 - ra0 + 3) & ~3;
   if (tid == 0) mbar_init(&s_bar, 1);
   __syncthreads();
-  if (tid == 0) {
+  const int kt0 = k < KT ? k : KT;
+  if (tid == 0) {  // the first phase of the barrier covers this stage AND the first X tile
     const uint64_t pol = policy_evict_first();
-    mbar_expect_tx(&s_bar, (unsigned)(ngrp * 32 + nl8 * 2 + nrp * 4));
+    mbar_expect_tx(&s_bar, (unsigned)(ngrp * 32 + nl8 * 2 + nrp * 4 + aux.w * 8 * kt0));
     if (ngrp > 0) bulk_g2s(s_val, vals + b.a0, (unsigned)ngrp * 32, &s_bar, pol);
     if (nl8 > 0) bulk_g2s(s_lidx, lidx + al0, (unsigned)nl8 * 2, &s_bar, pol);
     bulk_g2s(s_rp, rowptr + ra0, (unsigned)nrp * 4, &s_bar, pol);
@@ -727,27 +734,42 @@ spmm_runs_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict
   // the shared-memory views are indexed relative to the staged ranges
   const double* val0 = s_val - b.a0;
   const uint16_t* lidx0 = s_lidx - al0;
+  unsigned phase = 0;
   for (int v0 = 0; v0 < k; v0 += KT) {
     const int kt = k - v0 < KT ? k - v0 : KT;
-    // X tile: a warp per run, lanes over the run's 16-byte chunks, one pass per vector:
-    // xs[j][base + c - start] = X[c, v0 + j]
-    int base = 0;
-    for (int q = 0; q < nruns; ++q) {  // block-uniform; every warp walks the run list to keep `base` without a table
-      const int2 run = __ldg(runs + run0 + q);
-      if ((q & (THREADS / 32 - 1)) == warp) {
-        const double* src = x + (size_t)v0 * ldx + run.x;
-        double* dst = xs + base;
-        for (int j = 0; j < kt; ++j) {
-          for (int t = 2 * lane; t < run.y; t += 64) cp_async16(dst + t, src + t);
-          src += ldx;
-          dst += wpad;
+    // X tile by TMA as well (no LSU issue slots, no registers): warp 0, one lane per run, one bulk copy per (run, vector):
+    // xs[j][base + c - start] = X[c, v0 + j]; aux.w = columns copied per vector.
+    if (warp == 0) {
+      if (v0 > 0 && lane == 0) mbar_expect_tx(&s_bar, (unsigned)(aux.w * 8 * kt));
+      __syncwarp();  // the barrier is armed before any lane's copy can complete on it
+      const uint64_t pol_x = policy_evict_last();
+      int carry = 0;
+      for (int q0 = 0; q0 < nruns; q0 += 32) {  // warp-uniform
+        const int q = q0 + lane;
+        int2 run = make_int2(0, 0);
+        if (q < nruns) run = __ldg(runs + run0 + q);
+        const int stride = q < nruns ? run_stride(run.y) : 0;
+        int incl = stride;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const int base = carry + incl - stride;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+        if (run.y > 0) {
+          const double* src = x + (size_t)v0 * ldx + run.x;
+          double* dst = xs + base;
+          for (int j = 0; j < kt; ++j) {
+            bulk_g2s(dst, src, (unsigned)run.y * 8, &s_bar, pol_x);
+            src += ldx;
+            dst += wpad;
+          }
         }
       }
-      base += run.y;
     }
-    cp_async_wait_all();
-    if (v0 == 0) mbar_wait(&s_bar, 0);
-    __syncthreads();
+    mbar_wait(&s_bar, phase);
+    phase ^= 1;
     const int32_t* rp = s_rp + b.rpo;
     for (int rbase = 0; rbase < b.nrows; rbase += ngroups) {  // warp-uniform trip count (shuffles below)
       const int r = rbase + group;

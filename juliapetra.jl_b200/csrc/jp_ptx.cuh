@@ -44,6 +44,11 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
   return pol;
 }
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
+  return pol;
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar, uint64_t pol) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::"r"(
                    smem_addr(dst)),
@@ -103,6 +108,7 @@ inline void mbar_wait(uint64_t* bar, unsigned parity) {  // returns once the pha
   while (m->phase == (parity & 1)) ::emul::yield();
 }
 inline uint64_t policy_evict_first() { return 0; }
+inline uint64_t policy_evict_last() { return 0; }
 inline void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar, uint64_t) {
   if ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src) | bytes) & 15) {
     std::fprintf(stderr, "cuda_emul: cp.async.bulk needs 16-byte aligned addresses and size (dst %p src %p bytes %u)\n", dst, src, bytes);

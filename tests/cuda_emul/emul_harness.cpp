@@ -131,12 +131,13 @@ int emul_local_apply(int32_t n_rows, int32_t n_cols, int32_t n_local_cols, const
     else if (use_halo) launch(spmv_kernel<true, 0>, spmm_kernel<KT, true, 0>);
     else if (tma) launch(spmv_kernel<false, 1>, spmm_kernel<KT, false, 1>);
     else launch(spmv_kernel<false, 0>, spmm_kernel<KT, false, 0>);
-  } else if (variant == 3 || variant == 4) {
-    // spmm_runs_kernel on its own block list (<= kRunsMaxRows rows), KT = 4 (variant 3) or 8 (variant 4)
+  } else if (variant == 3 || variant == 4 || variant == 5) {
+    // spmm_runs_kernel on its own block list: variant 3: KT = 4, 64 rows, 128 threads (two lanes per row); variant 4:
+    // KT = 8, 128 rows, 256 threads; variant 5: KT = 4, 64 rows, 64 threads (one lane per row)
     if (use_halo || (x_rows & 1)) return -3;
     std::vector<BlockDesc> ri, rb, ra;
-    build_blocks(rp, cls, cap, kRunsMaxRows, allow_direct != 0, ri, rb, ra);
-    const int kt = variant == 3 ? 4 : 8;
+    build_blocks(rp, cls, cap, variant == 4 ? kRunsMaxRows : 64, allow_direct != 0, ri, rb, ra);
+    const int kt = variant == 4 ? 8 : 4;
     const int max_tile_cols = (int)((110 * 1024 - (int64_t)runs_smem_bytes(cap, 0, kt)) / (8 * kt)) & ~1;
     std::vector<int32_t> ci(colind, colind + nnz);
     RunTables t;
@@ -152,7 +153,11 @@ int emul_local_apply(int32_t n_rows, int32_t n_cols, int32_t n_local_cols, const
       std::memcpy(d_lidx.p, t.lidx.data(), t.lidx.size() * 2);
       const int wpad = (t.wmax + 1) & ~1;
       const size_t sm = runs_smem_bytes(cap, wpad, kt);
-      if (kt == 4)
+      if (variant == 5)
+        JP_KLAUNCH((spmm_runs_kernel<4, 64>), (unsigned)ra.size(), 64, sm, nullptr, d_blocks.as<BlockDesc>(), d_rp.as<int32_t>(),
+                   d_va.as<double>(), d_lidx.as<uint16_t>(), d_ucols.as<int2>(), d_x.as<double>(), (int64_t)x_rows, d_y.as<double>(),
+                   (int64_t)n_rows, k, cap, wpad, alpha, beta);
+      else if (kt == 4)
         JP_KLAUNCH((spmm_runs_kernel<4, 128>), (unsigned)ra.size(), 128, sm, nullptr, d_blocks.as<BlockDesc>(), d_rp.as<int32_t>(),
                    d_va.as<double>(), d_lidx.as<uint16_t>(), d_ucols.as<int2>(), d_x.as<double>(), (int64_t)x_rows, d_y.as<double>(),
                    (int64_t)n_rows, k, cap, wpad, alpha, beta);

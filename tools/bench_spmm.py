@@ -22,6 +22,11 @@ VARIANTS = [
     ("runs_kt4", {"JP_SPMM_RUNS": "1", "JP_SPMM_RUNS_KT": "4"}),
     ("runs_kt8", {"JP_SPMM_RUNS": "1", "JP_SPMM_RUNS_KT": "8"}),
     ("runs_kt4_cap1024", {"JP_SPMM_RUNS": "1", "JP_SPMM_RUNS_KT": "4", "JP_SPMM_RUNS_CAP": "1024"}),
+    ("runs_kt4_t256", {"JP_SPMM_RUNS": "1", "JP_SPMM_RUNS_KT": "4", "JP_SPMM_RUNS_THREADS": "256"}),
+    ("runs_kt8_t256", {"JP_SPMM_RUNS": "1", "JP_SPMM_RUNS_KT": "8", "JP_SPMM_RUNS_THREADS": "256"}),
+    # one lane per row (conflict-free shared reads for odd row lengths, no shuffles)
+    ("runs_kt4_rows128_t128", {"JP_SPMM_RUNS": "1", "JP_SPMM_RUNS_KT": "4", "JP_SPMM_RUNS_ROWS": "128", "JP_SPMM_RUNS_CAP": "3456"}),
+    ("runs_kt4_rows64_t64", {"JP_SPMM_RUNS": "1", "JP_SPMM_RUNS_KT": "4", "JP_SPMM_RUNS_THREADS": "64"}),
 ]
 
 
@@ -54,7 +59,7 @@ def main():
     for label, env in VARIANTS:
         if keep and label not in keep:
             continue
-        for key in ("JP_SPMM_RUNS", "JP_SPMM_RUNS_KT", "JP_SPMM_RUNS_CAP", "JP_SPMM_TILE"):
+        for key in ("JP_SPMM_RUNS", "JP_SPMM_RUNS_KT", "JP_SPMM_RUNS_CAP", "JP_SPMM_RUNS_THREADS", "JP_SPMM_RUNS_ROWS", "JP_SPMM_TILE"):
             os.environ.pop(key, None)
         os.environ.update(env)
         h = C.c_int64()
