@@ -206,7 +206,7 @@ struct Csr : Object {
   std::unique_ptr<MultiVector> import_mv;
   // GIDs of the column map in LID order, kept when the matrix was fill-completed on the device (jp_csr_fill_complete)
   DeviceBuffer colmap_gids;
-  // jp_apply_dot workspace: [block partials | result | ticket], zeroed once (the kernel re-arms the ticket)
+  // jp_apply_dot workspace: [block partials | result]
   DeviceBuffer dot_ws;
   // host-buffer path (jp_apply_host): the all-blocks list cut into chunks; chunk c covers blocks
   // [chunk_block[c], chunk_block[c+1]) = rows [chunk_row[c], chunk_row[c+1]) and reads columns <= chunk_maxcol[c]

@@ -196,17 +196,17 @@ void build_tiles(Csr& A) {
 
 // Build the tables of the SpMM runs path (lazily, at the first k > 1 apply); one-time host cost like build_tiles.
 void build_runs(Csr& A) {
-  if (A.nnz == 0 || A.n_rows == 0 || env_int("JP_SPMM_RUNS", 0) == 0) {  // opt-in until measured on the GPU (profiles/)
+  if (A.nnz == 0 || A.n_rows == 0 || env_int("JP_SPMM_RUNS", 1) == 0) {  // on by default; only banded matrices pass build_run_tables
     A.runs_state = -1;
     return;
   }
-  const int cap = env_int("JP_SPMM_RUNS_CAP", 2048);
+  const int cap = env_int("JP_SPMM_RUNS_CAP", 3456);
   const int kt = env_int("JP_SPMM_RUNS_KT", 4);
   JP_REQUIRE(cap >= 256 && cap <= 8192 && cap % 4 == 0, "JP_SPMM_RUNS_CAP must be a multiple of 4 in [256,8192]");
   JP_REQUIRE(kt == 4 || kt == 8, "JP_SPMM_RUNS_KT must be 4 or 8");
   const int threads = env_int("JP_SPMM_RUNS_THREADS", 128);
   JP_REQUIRE(threads == 64 || threads == 128 || threads == 256, "JP_SPMM_RUNS_THREADS must be 64, 128 or 256");
-  const int max_rows = env_int("JP_SPMM_RUNS_ROWS", 64);
+  const int max_rows = env_int("JP_SPMM_RUNS_ROWS", 128);  // one lane per row with 128 threads: measured best (profiles/)
   JP_REQUIRE(max_rows >= 16 && max_rows <= kRunsMaxRows, "JP_SPMM_RUNS_ROWS must be in [16,128]");
   std::vector<int32_t> ci((size_t)A.nnz), rp((size_t)A.n_rows + 1);
   JP_CUDA(cudaStreamSynchronize(ctx().compute));
@@ -307,14 +307,10 @@ void launch_spmv_fused(const Csr& A, const FusedHalo& h, const double* x, const 
 
 double* launch_spmv_dot(Csr& A, const double* x, double* y, double alpha, double beta, const double* w, cudaStream_t stream) {
   const int32_t nb = A.n_blocks_all;
-  const size_t ws_bytes = ((size_t)nb + 4) * 8;
-  if (A.dot_ws.bytes < ws_bytes) {
-    A.dot_ws.alloc(ws_bytes);
-    JP_CUDA(cudaMemsetAsync(A.dot_ws.p, 0, ws_bytes, stream));
-  }
+  const size_t ws_bytes = ((size_t)nb + 4) * 8;  // [block partials | result]
+  if (A.dot_ws.bytes < ws_bytes) A.dot_ws.alloc(ws_bytes);
   double* partials = A.dot_ws.as<double>();
   double* out = partials + nb;
-  unsigned int* ticket = reinterpret_cast<unsigned int*>(partials + nb + 1);
   if (nb == 0) {
     JP_CUDA(cudaMemsetAsync(out, 0, 8, stream));
     return out;
@@ -325,12 +321,14 @@ double* launch_spmv_dot(Csr& A, const double* x, double* y, double alpha, double
   if (tma) {
     set_smem_attr(spmv_dot_kernel<false, 1>, smem);
     spmv_dot_kernel<false, 1><<<nb, kSpmvThreads, smem, stream>>>(b, A.rowptr.as<int32_t>(), A.colind.as<int32_t>(), A.vals.as<double>(), x,
-                                                                   nullptr, A.n_cols, y, A.nnz_cap, alpha, beta, w, partials, ticket, out);
+                                                                   nullptr, A.n_cols, y, A.nnz_cap, alpha, beta, w, partials);
   } else {
     set_smem_attr(spmv_dot_kernel<false, 0>, smem);
     spmv_dot_kernel<false, 0><<<nb, kSpmvThreads, smem, stream>>>(b, A.rowptr.as<int32_t>(), A.colind.as<int32_t>(), A.vals.as<double>(), x,
-                                                                   nullptr, A.n_cols, y, A.nnz_cap, alpha, beta, w, partials, ticket, out);
+                                                                   nullptr, A.n_cols, y, A.nnz_cap, alpha, beta, w, partials);
   }
+  JP_LAUNCH_CHECK();
+  sum_partials_kernel<<<1, kSpmvThreads, 0, stream>>>(partials, (unsigned)nb, out);
   JP_LAUNCH_CHECK();
   return out;
 }
@@ -350,10 +348,14 @@ void launch_spmv_blocks(const Csr& A, const void* blocks_int4, int32_t n_blocks,
     build_tiles(const_cast<Csr&>(A));
   }
   if (k > 1 && A.runs_state == 0) build_runs(const_cast<Csr&>(A));
+  // the run-staged kernel serves launches over the WHOLE all-blocks or interior list (it has its own block lists with a
+  // different geometry; a chunk of a list, as jp_apply_host launches, stays with the gather kernel)
+  const bool whole_all = blocks_int4 == A.blocks_all.p && n_blocks == A.n_blocks_all;
+  const bool whole_interior = blocks_int4 == A.blocks_interior.p && n_blocks == A.n_blocks_interior;
   if (k > 1 && A.runs_state == 1 && !use_halo && (ldx & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
-      (blocks_int4 == A.blocks_all.p || blocks_int4 == A.blocks_interior.p)) {
-    // banded matrix, no halo columns in this launch: the run-staged kernel on its own (64-row) block list
-    const bool all = blocks_int4 == A.blocks_all.p;
+      (whole_all || whole_interior)) {
+    // banded matrix, no halo columns in this launch
+    const bool all = whole_all;
     const BlockDesc* rb = (all ? A.runs_blocks_all : A.runs_blocks_interior).as<BlockDesc>();
     const int32_t rn = all ? A.n_runs_blocks_all : A.n_runs_blocks_interior;
     if (rn > 0) {

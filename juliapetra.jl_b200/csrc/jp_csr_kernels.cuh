@@ -228,12 +228,11 @@ __device__ __forceinline__ double spmv_block(const BlockRange& b, const StageVie
   return dacc;
 }
 
-// Sum of every thread's `v` over the whole GRID, deterministic for a given launch geometry: block partials in block
-// order, added by the last block to finish (ticket counter), which re-arms the ticket for the next launch.
-// s_red: kSpmvThreads / 32 doubles of shared memory.  Called by every thread of every CTA of the launch.
-__device__ __forceinline__ void grid_sum_finish(double v, double* s_red, double* __restrict__ partials, unsigned int* __restrict__ ticket,
-                                                double* __restrict__ out, unsigned bid, unsigned nblocks) {
-  __shared__ bool s_last_block;
+// One partial per CTA: partials[bid] = sum of `v` over the CTA's threads.  s_red: kSpmvThreads / 32 doubles.
+// (A first version finished the grid-wide sum inside the same kernel with __threadfence + a ticket counter; measured
+// on 7-pt 128^3 that made the fused kernel 11 us slower than the plain SpMV -- more than the separate dot kernel
+// costs -- so the partials are now added by sum_partials_kernel, a one-CTA launch behind it.)
+__device__ __forceinline__ void block_partial_store(double v, double* s_red, double* __restrict__ partials, unsigned bid) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double s = warp_sum(v);
   __syncthreads();  // s_red may still be in use by the row block
@@ -242,55 +241,48 @@ __device__ __forceinline__ void grid_sum_finish(double v, double* s_red, double*
   if (warp == 0) {
     double t = lane < kSpmvThreads / 32 ? s_red[lane] : 0.0;
     t = warp_sum(t);
-    if (lane == 0) {
-      partials[bid] = t;
-      __threadfence();
-      s_last_block = atomicAdd(ticket, 1u) == nblocks - 1;
-    }
-  }
-  __syncthreads();
-  if (s_last_block) {  // block-uniform
-    __threadfence();
-    const volatile double* pv = partials;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    unsigned b = tid;
-    for (; b + 3 * kSpmvThreads < nblocks; b += 4 * kSpmvThreads) {
-      a0 += pv[b];
-      a1 += pv[b + kSpmvThreads];
-      a2 += pv[b + 2 * kSpmvThreads];
-      a3 += pv[b + 3 * kSpmvThreads];
-    }
-    for (; b < nblocks; b += kSpmvThreads) a0 += pv[b];
-    const double t = warp_sum((a0 + a1) + (a2 + a3));
-    __syncthreads();
-    if (lane == 0) s_red[warp] = t;
-    __syncthreads();
-    if (warp == 0) {
-      double u = lane < kSpmvThreads / 32 ? s_red[lane] : 0.0;
-      u = warp_sum(u);
-      if (lane == 0) {
-        out[0] = u;
-        *ticket = 0;
-      }
-    }
+    if (lane == 0) partials[bid] = t;
   }
 }
 
-// apply + dot in one pass: y = beta*y + alpha*A*x and out[0] = sum_r w[r] * y[r], so a CG
-// iteration's p'Ap costs no second sweep over p and Ap (16 bytes per row less HBM traffic, one launch less)
+// out[0] = sum of partials[0..n) in a fixed order (ONE CTA of kSpmvThreads threads)
+__global__ void __launch_bounds__(kSpmvThreads) sum_partials_kernel(const double* __restrict__ partials, unsigned n, double* __restrict__ out) {
+  __shared__ double s_red[kSpmvThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  unsigned b = tid;
+  for (; b + 3 * kSpmvThreads < n; b += 4 * kSpmvThreads) {
+    a0 += partials[b];
+    a1 += partials[b + kSpmvThreads];
+    a2 += partials[b + 2 * kSpmvThreads];
+    a3 += partials[b + 3 * kSpmvThreads];
+  }
+  for (; b < n; b += kSpmvThreads) a0 += partials[b];
+  const double t = warp_sum((a0 + a1) + (a2 + a3));
+  if (lane == 0) s_red[warp] = t;
+  __syncthreads();
+  if (warp == 0) {
+    double u = lane < kSpmvThreads / 32 ? s_red[lane] : 0.0;
+    u = warp_sum(u);
+    if (lane == 0) out[0] = u;
+  }
+}
+
+// apply + dot in one pass: y = beta*y + alpha*A*x and partials[block] = sum_r w[r] * y[r] over the
+// block's rows, so a CG iteration's p'Ap costs no second sweep over p and Ap (16 bytes per row less HBM traffic)
 template <bool HALO, int TMA>
 __global__ void __launch_bounds__(kSpmvThreads)
 spmv_dot_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
                 const double* __restrict__ vals, const double* __restrict__ x, const double* __restrict__ halo, int32_t nloc,
                 double* __restrict__ y, int32_t cap, double alpha, double beta, const double* __restrict__ w,
-                double* __restrict__ partials, unsigned int* __restrict__ ticket, double* __restrict__ out) {
+                double* __restrict__ partials) {
   JP_DYN_SMEM(smem_raw);
   __shared__ double s_red[kSpmvThreads / 32];
   __shared__ __align__(8) uint64_t s_bar;
   const StageView sv = stage_view(smem_raw, cap);
   const BlockRange b = decode_block(blocks, blockIdx.x);
   const double dacc = spmv_block<HALO, TMA, true>(b, sv, &s_bar, s_red, rowptr, colind, vals, x, halo, nloc, y, alpha, beta, w);
-  grid_sum_finish(dacc, s_red, partials, ticket, out, blockIdx.x, gridDim.x);
+  block_partial_store(dacc, s_red, partials, blockIdx.x);
 }
 
 template <bool HALO, int TMA>
@@ -684,7 +676,7 @@ spmm_pipe_kernel(const BlockDesc* __restrict__ blocks, int32_t n_blocks, const i
 //     CTAs wait for their copies.
 // X must be 16-byte aligned with an even leading dimension (the launcher checks; otherwise the gather kernel runs).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kRunsMaxRows = 128;  // upper bound of the rows-per-block setting (JP_SPMM_RUNS_ROWS, default 64)
+constexpr int kRunsMaxRows = 128;  // upper bound of the rows-per-block setting (JP_SPMM_RUNS_ROWS, default 128)
 
 // Tile columns a run of `len` columns occupies: padded so that consecutive runs start 10 (mod 16) doubles apart.  With
 // two lanes per row, the iteration in which a lane pair straddles two runs reads [base_q + r + 2] and [base_q+1 + r]

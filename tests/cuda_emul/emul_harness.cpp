@@ -131,12 +131,13 @@ int emul_local_apply(int32_t n_rows, int32_t n_cols, int32_t n_local_cols, const
     else if (use_halo) launch(spmv_kernel<true, 0>, spmm_kernel<KT, true, 0>);
     else if (tma) launch(spmv_kernel<false, 1>, spmm_kernel<KT, false, 1>);
     else launch(spmv_kernel<false, 0>, spmm_kernel<KT, false, 0>);
-  } else if (variant == 3 || variant == 4 || variant == 5) {
+  } else if (variant >= 3 && variant <= 6) {
     // spmm_runs_kernel on its own block list: variant 3: KT = 4, 64 rows, 128 threads (two lanes per row); variant 4:
-    // KT = 8, 128 rows, 256 threads; variant 5: KT = 4, 64 rows, 64 threads (one lane per row)
+    // KT = 8, 128 rows, 256 threads; variant 5: KT = 4, 64 rows, 64 threads (one lane per row); variant 6: the default
+    // configuration, KT = 4, 128 rows, 128 threads (one lane per row)
     if (use_halo || (x_rows & 1)) return -3;
     std::vector<BlockDesc> ri, rb, ra;
-    build_blocks(rp, cls, cap, variant == 4 ? kRunsMaxRows : 64, allow_direct != 0, ri, rb, ra);
+    build_blocks(rp, cls, cap, (variant == 4 || variant == 6) ? kRunsMaxRows : 64, allow_direct != 0, ri, rb, ra);
     const int kt = variant == 4 ? 8 : 4;
     const int max_tile_cols = (int)((110 * 1024 - (int64_t)runs_smem_bytes(cap, 0, kt)) / (8 * kt)) & ~1;
     std::vector<int32_t> ci(colind, colind + nnz);
@@ -211,7 +212,7 @@ int emul_local_apply(int32_t n_rows, int32_t n_cols, int32_t n_local_cols, const
 
 // ---- fused CG building blocks ----
 // y = beta*y + alpha*A*x and out = sum_r w[r]*y[r] (spmv_dot_kernel), `repeats` times with the same workspace so the
-// ticket re-arm is exercised; y is reset to y0 before every repeat.  x is the whole column-map vector.
+// workspace is reused; y is reset to y0 before every repeat.  x is the whole column-map vector.
 int emul_spmv_dot(int32_t n_rows, int32_t n_cols, const int32_t* rowptr, const int32_t* colind, const double* vals, const double* x,
                   const double* w, double* y, double alpha, double beta, int32_t cap, int32_t max_rows, int32_t tma, int32_t repeats,
                   double* out) {
@@ -241,10 +242,8 @@ int emul_spmv_dot(int32_t n_rows, int32_t n_cols, const int32_t* rowptr, const i
   std::memcpy(d_w.p, w, (size_t)n_rows * 8);
   d_y.alloc((size_t)n_rows * 8 + 64);
   ws.alloc(((size_t)nb + 4) * 8);
-  std::memset(ws.p, 0, ws.bytes);
   double* partials = ws.as<double>();
   double* d_out = partials + nb;
-  unsigned int* ticket = reinterpret_cast<unsigned int*>(partials + nb + 1);
   const size_t smem = stage_smem_bytes(cap);
   for (int rep = 0; rep < repeats; ++rep) {
     std::memcpy(d_y.p, y, (size_t)n_rows * 8);
@@ -254,14 +253,14 @@ int emul_spmv_dot(int32_t n_rows, int32_t n_cols, const int32_t* rowptr, const i
     } else if (tma) {
       JP_KLAUNCH((spmv_dot_kernel<false, 1>), nb, kSpmvThreads, smem, nullptr, d_blocks.as<BlockDesc>(), d_rp.as<int32_t>(),
                  d_ci.as<int32_t>(), d_va.as<double>(), d_x.as<double>(), (const double*)nullptr, n_cols, d_y.as<double>(), cap, alpha, beta,
-                 d_w.as<double>(), partials, ticket, d_out);
+                 d_w.as<double>(), partials);
     } else {
       JP_KLAUNCH((spmv_dot_kernel<false, 0>), nb, kSpmvThreads, smem, nullptr, d_blocks.as<BlockDesc>(), d_rp.as<int32_t>(),
                  d_ci.as<int32_t>(), d_va.as<double>(), d_x.as<double>(), (const double*)nullptr, n_cols, d_y.as<double>(), cap, alpha, beta,
-                 d_w.as<double>(), partials, ticket, d_out);
+                 d_w.as<double>(), partials);
     }
+    if (nb) JP_KLAUNCH(sum_partials_kernel, 1u, kSpmvThreads, 0, nullptr, partials, nb, d_out);
     out[rep] = *d_out;
-    if (*ticket != 0) return -2;  // the last block must re-arm the ticket
   }
   std::memcpy(y, d_y.p, (size_t)n_rows * 8);
   return 0;

@@ -65,7 +65,7 @@ def test_spmv_with_halo_buffer():
     assert (np.abs(got - ref) <= _bound(rp, ci, va, x, y0, 3.0, 0.5)).all()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])  # gather, tile, pipelined tile, runs (KT=4 T=2; KT=8 256 thr; KT=4 T=1)
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])  # gather, tile, pipelined tile, runs (KT=4 T=2; KT=8 256 thr; KT=4 T=1; default)
 @pytest.mark.parametrize("k", [2, 8, 11])
 def test_spmm_kernels(variant, k):
     rp, ci, va = _problem("27pt", 6)
@@ -97,7 +97,7 @@ def test_spmm_runs_kernel_other_stencils(kind, N):
     rp, ci, va = _problem(kind, N)
     n = len(rp) - 1
     x, y0 = _vectors(n, n, 5)
-    for variant, cap in ((3, 2048), (4, 256), (5, 2048)):
+    for variant, cap in ((3, 2048), (4, 256), (5, 2048), (6, 3456)):
         got, st = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, variant=variant, cap=cap)
         ref = _oracle(rp, ci, va, x, y0, 3.0, 0.5)
         assert (np.abs(got - ref) <= _bound(rp, ci, va, x, y0, 3.0, 0.5)).all()
