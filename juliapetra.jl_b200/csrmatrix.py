@@ -23,6 +23,34 @@ from .multivector import DenseMultiVector
 from .utils import computeOffsets
 
 
+# ---- the four C-ABI calls of the device fillComplete, as module-level functions so that the CPU tests can run the
+#      multi-rank glue around them against the CPU execution model of the kernels (tests/dist_cases.py) ----
+def _device_fill_complete(n_rows, ptr0, gcols, vals, gmin, gmax, dom_min, n_dom):
+    """jp_csr_fill_complete -> (csr handle, [n_cols, n_local_used, n_same, nnz]); InvalidArgumentError for a bad GID"""
+    h, info = C.c_int64(), np.zeros(4, dtype=np.int64)
+    _lib.check(_lib.lib().jp_csr_fill_complete(n_rows, _lib.ptr(ptr0), _lib.ptr(gcols), _lib.ptr(vals), gmin, gmax, dom_min, n_dom,
+                                               C.byref(h), _lib.ptr(info)))
+    return h.value, [int(v) for v in info]
+
+
+def _device_col_map(h, n_cols):
+    gids = np.empty(n_cols, dtype=np.int64)
+    _lib.check(_lib.lib().jp_csr_col_map(h, _lib.ptr(gids)))
+    return gids
+
+
+def _device_csr_download(h, n_rows, nnz):
+    rp = np.empty(n_rows + 1, dtype=np.int32)
+    ci = np.empty(nnz, dtype=np.int32)
+    va = np.empty(nnz, dtype=np.float64)
+    _lib.check(_lib.lib().jp_csr_download(h, _lib.ptr(rp), _lib.ptr(ci), _lib.ptr(va)))
+    return rp, ci, va
+
+
+def _device_csr_destroy(h):
+    _lib.lib().jp_csr_destroy(h)
+
+
 class TransposeMode(enum.IntEnum):  # src/Operator.jl:10
     NO_TRANS = 1
     TRANS = 2
@@ -144,11 +172,7 @@ class CSRMatrix:
 
     def _host_csr(self):
         if self._csr_host is None and self._fillComplete and self.h:
-            n = self.getLocalNumRows()
-            rp = np.empty(n + 1, dtype=np.int32)
-            ci = np.empty(self._nnz, dtype=np.int32)
-            va = np.empty(self._nnz, dtype=np.float64)
-            _lib.check(_lib.lib().jp_csr_download(self.h, _lib.ptr(rp), _lib.ptr(ci), _lib.ptr(va)))
+            rp, ci, va = _device_csr_download(self.h, self.getLocalNumRows(), self._nnz)
             self._csr_host = (rp + 1, ci + 1, va)
         return self._csr_host
 
@@ -197,41 +221,39 @@ class CSRMatrix:
         ptr0, gcols, vals = self._packed_global()
         ptr0, gcols, vals = _lib.as_i64(ptr0), _lib.as_i64(gcols), _lib.as_f64(vals)
         n_rows, n_dom = self.getLocalNumRows(), dom.numMyElements()
-        h, info = C.c_int64(), np.zeros(4, dtype=np.int64)
+        h, info = 0, [0, 0, 0, 0]
         error = False
         try:
-            _lib.check(_lib.lib().jp_csr_fill_complete(n_rows, _lib.ptr(ptr0), _lib.ptr(gcols), _lib.ptr(vals), dom.minAllGID(), dom.maxAllGID(),
-                                                       dom.minMyGID() if n_dom else dom.minAllGID(), n_dom, C.byref(h), _lib.ptr(info)))
+            h, info = _device_fill_complete(n_rows, ptr0, gcols, vals, dom.minAllGID(), dom.maxAllGID(),
+                                            dom.minMyGID() if n_dom else dom.minAllGID(), n_dom)
         except InvalidArgumentError:
             error = True  # a column GID nobody owns: remotePIDs == 0 in the reference (:936-939)
-        n_cols, n_local_used, n_same, nnz = (int(v) for v in info)
+        n_cols, n_local_used, n_same, nnz = info
         serial = comm.numProc() == 1
         if not error and serial and n_cols > n_local_used:
             error = True  # remote GIDs on one process, :918-921
         if bool(comm.maxAllScalar(int(error))):
-            if h.value:
-                _lib.lib().jp_csr_destroy(h.value)
+            if h:
+                _device_csr_destroy(h)
             raise RuntimeError("makeColMap reports an error on at least one process")
         if serial and n_local_used == n_rows and n_local_used != n_dom:
-            _lib.lib().jp_csr_destroy(h.value)
+            _device_csr_destroy(h)
             return False
         self.domainMap = dom
         self.rangeMap = rangeMap if rangeMap is not None else self.rowMap
         if serial and n_local_used == n_rows:
             self.colMap = dom  # :922-924
         else:
-            gids = np.empty(n_cols, dtype=np.int64)
-            _lib.check(_lib.lib().jp_csr_col_map(h.value, _lib.ptr(gids)))
-            self.colMap = BlockMap(dom.numGlobalElements(), gids, comm)  # :981
+            self.colMap = BlockMap(dom.numGlobalElements(), _device_col_map(h, n_cols), comm)  # :981
         if not self.domainMap.sameAs(self.colMap):
             self.importer = Import(self.domainMap, self.colMap)
         if not self.rangeMap.sameAs(self.rowMap):
             self.exporter = Export(self.rowMap, self.rangeMap)
         expect_same = self.importer.numSameIDs() if self.importer is not None else n_cols
         if expect_same != n_same:
-            _lib.lib().jp_csr_destroy(h.value)
+            _device_csr_destroy(h)
             raise BackendError(f"device fillComplete: numSameIDs {n_same} disagrees with the Import ({expect_same})")
-        self.h = h.value
+        self.h = h
         self._nnz = nnz
         self._globalIndices1D = self._values = None
         self._fillComplete = True

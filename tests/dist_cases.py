@@ -236,3 +236,55 @@ def case_export_plan(rank, world):
     osrc = O.OMap.from_gids(oc, -1, [src_gids(p) for p in range(1, P + 1)])
     assert src.numGlobalElements() == osrc.info(pid)["numGlobalElements"] == N
     assert_plan_equal(jp.Export(src, tgt), O.OPlan.make_export(osrc, otgt), pid)
+
+
+def case_device_fill_glue(rank, world, kind, N, max_len):
+    """CSRMatrix.fillComplete(device=True) on every rank, with the four C-ABI calls behind it served by the CPU execution
+    model of the fillComplete kernels (tests/emul.py): the multi-rank glue (error consensus, column-map BlockMap, Import)
+    and the kernels' results against the oracle and against the host path"""
+    import emul
+    import jpetra_b200 as jp
+    from jpetra_b200 import csrmatrix, synthetic
+    from helpers import assert_plan_equal, global_rows, oracle_problem
+    store = {}
+
+    def fake_fill(n_rows, ptr0, gcols, vals, gmin, gmax, dom_min, n_dom):
+        try:
+            out = emul.fill_complete(ptr0, gcols, vals, gmin, gmax, dom_min, n_dom)
+        except emul.EmulError as e:
+            raise jp.InvalidArgumentError(str(e))
+        h = len(store) + 1
+        store[h] = out
+        return h, [out["n_cols"], out["n_local_used"], out["n_same"], out["nnz"]]
+
+    csrmatrix._device_fill_complete = fake_fill
+    csrmatrix._device_col_map = lambda h, n_cols: store[h]["colmap"]
+    csrmatrix._device_csr_download = lambda h, n_rows, nnz: (store[h]["rowptr"], store[h]["colind"], store[h]["vals"])
+    csrmatrix._device_csr_destroy = lambda h: store.pop(h, None)
+    jp.Import.device_plan = lambda self: 0
+    comm = jp.TorchDistComm()
+    pid, P = comm.myPid(), comm.numProc()
+    m = jp.BlockMap(global_rows(kind, N), comm)
+    A = synthetic.build_matrix(jp, m, kind, N, chunk_rows=1000, fill=False, max_len=max_len)
+    A.fillComplete(m, m, device=True)
+    assert A.isFillComplete() and A.h in store  # the device path was taken
+    Ah = synthetic.build_matrix(jp, m, kind, N, chunk_rows=1000, fill=False, max_len=max_len)
+    Ah._fillCompleteHost(m, m)
+    _, _, OA = oracle_problem(kind, N, P, max_len=max_len)
+    rp, ci, va = OA.csr(pid)
+    for B in (A, Ah):
+        assert np.array_equal(B.rowOffsets, rp) and np.array_equal(B.localIndices1D, ci) and np.array_equal(B.values, va)
+        assert np.array_equal(B.colMap.myGlobalElements(), OA.col_map.my_gids(pid))
+        assert (B.importer is None) == (OA.importer is None)
+        if B.importer is not None:
+            assert_plan_equal(B.importer, OA.importer, pid)
+    assert A.getLocalNumEntries() == Ah.getLocalNumEntries() == len(va)
+    # a column GID nobody owns: every rank raises, whichever rank saw it (maxAll of the error flag)
+    B = jp.CSRMatrix(m, 2, jp.STATIC_PROFILE)
+    for g in m.myGlobalElements():
+        B.insertGlobalValues(int(g), [int(g), int(g) if pid != P else m.numGlobalElements() + 5], [1.0, 2.0])
+    try:
+        B.fillComplete(m, m, device=True)
+        raise AssertionError("expected makeColMap to report an error")
+    except RuntimeError as e:
+        assert "makeColMap" in str(e)

@@ -127,6 +127,26 @@ def main():
         nref = OY.norm(2)
         ngot = Yj.norm(2)[0]
         assert (np.abs(ngot - nref) <= TOL * nref).all()
+        # device-side fillComplete on every rank: same column map, Import lists, CSR and result
+        Ad = synthetic.build_matrix(jp, rm, kind, size, fill=False, max_len=3000)
+        Ad.fillComplete(rm, rm, device=True)
+        assert Ad._csr_host is None  # nothing was packed on the host
+        assert np.array_equal(Ad.colMap.myGlobalElements(), OA.col_map.my_gids(pid))
+        assert np.array_equal(Ad.rowOffsets, rp) and np.array_equal(Ad.localIndices1D, ci) and np.array_equal(Ad.values, va)
+        if OA.importer is not None:
+            assert_plan_equal(Ad.importer, OA.importer, pid)
+        Yd = jp.DenseMultiVector(rm, ys[rank])
+        Ad.apply_(Yd, Xj, jp.NO_TRANS, 3.0, 0.5)
+        assert np.array_equal(Yd.data, got), (kind, pid, "device fillComplete")
+        # fused building blocks: apply!+dot and axpby+norm2, against the separate calls
+        Yf = jp.DenseMultiVector(rm, ys[rank])
+        df = Aj.apply_dot_(Yf, Xj, None, jp.NO_TRANS, 3.0, 0.5)[0]
+        assert np.array_equal(Yf.data, got) and (np.abs(df - dref) <= TOL * dscale).all(), (kind, df, dref)
+        R1, R2 = jp.DenseMultiVector(rm, ys[rank]), jp.DenseMultiVector(rm, ys[rank])
+        R1.axpby_(-0.37, Xj, 1.0)
+        n1 = R1.norm(2)[0]
+        n2 = R2.axpby_norm2_(-0.37, Xj, 1.0)[0]
+        assert np.array_equal(R1.data, R2.data) and (np.abs(n1 - n2) <= TOL * n1).all()
         # generic doImport into a column-map multivector == the oracle's
         if Aj.importer is not None:
             XC = jp.DenseMultiVector(Aj.colMap, k)
@@ -182,6 +202,15 @@ def main():
         Yt = jp.DenseMultiVector(mg, ys[rank])
         Ag.apply_(Yt, Xj, jp.TRANS, 3.0, 0.5)
         assert np.abs(Yt.data - OY2.get(pid)).max() <= 100 * TOL * (np.abs(OY2.get(pid)).max() + 1.0), (pid, k, "trans")
+    # ---- CG on the distributed 7-point Laplacian with the fused building blocks ----
+    rm = jp.BlockMap(20 ** 3, comm)
+    Ac = synthetic.build_matrix(jp, rm, "7pt", 20)
+    xs_true = synthetic.vector_block(rm.minMyGID(), rm.numMyElements(), 1, seed=7)
+    Bc = Ac.apply(jp.DenseMultiVector(rm, xs_true))
+    for fused in (True, False):
+        Xc = jp.DenseMultiVector(rm, 1)
+        its, rel = jp.cg(Ac, Bc, Xc, tol=1e-12, maxiter=400, fused=fused)
+        assert rel <= 1e-12 and np.abs(Xc.data - xs_true).max() <= 1e-9, (fused, its, rel)
     # commReduce on a replicated map (test/DenseMultiVectorTests.jl:96-99)
     rep = jp.BlockMap(6, 6, comm)
     v = jp.DenseMultiVector(rep, (10.0 ** pid) * np.ones((6, 3)))
