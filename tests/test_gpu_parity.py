@@ -428,20 +428,43 @@ def test_transposed_apply_with_importer_serial():
 def test_spmm_shared_memory_tile_path(monkeypatch, k):
     """opt-in SpMM kernel that stages the block's X tile in shared memory (unique-column lists, JP_SPMM_TILE=1)"""
     monkeypatch.setenv("JP_SPMM_TILE", "1")
+    monkeypatch.setenv("JP_SPMM_RUNS", "0")  # the run-staged kernel (default for banded matrices) would take precedence
     c, m, A = serial_matrix("27pt", 20)
     n = m.numMyElements()
     x = synthetic.vector_block(1, n, k, seed=1)
     y0 = synthetic.vector_block(1, n, k, seed=2)
     check_apply(A, x, y0, 3.0, 0.5, exact=False)
     check_apply(A, x, y0, 1.0, 0.0, exact=False)
+    assert A.spmm_info()["tile_state"] == 1 and A.spmm_info()["runs_state"] == -1
+
+
+def test_spmm_default_path_selection():
+    """banded matrices take the run-staged kernel by default, random ones and odd leading dimensions the gather kernel"""
+    c, m, A = serial_matrix("27pt", 16)
+    n = m.numMyElements()
+    check_apply(A, synthetic.vector_block(1, n, 5, seed=1), synthetic.vector_block(1, n, 5, seed=2), 3.0, 0.5, exact=False)
+    assert A.spmm_info()["runs_state"] == 1
+    c, m, A = serial_matrix("27pt", 15)  # n = 3375 is odd: X's columns are not all 16-byte aligned -> gather kernel
+    n = m.numMyElements()
+    check_apply(A, synthetic.vector_block(1, n, 5, seed=1), synthetic.vector_block(1, n, 5, seed=2), 3.0, 0.5, exact=False)
+    c, m, A = serial_matrix("powerlaw", 20000)
+    n = m.numMyElements()
+    check_apply(A, synthetic.vector_block(1, n, 5, seed=1), synthetic.vector_block(1, n, 5, seed=2), 3.0, 0.5, exact=False)
+    assert A.spmm_info()["runs_state"] == -1
 
 
 @pytest.mark.parametrize("kt", ["4", "8"])
-@pytest.mark.parametrize("kind,N,k", [("27pt", 20, 8), ("27pt", 20, 11), ("7pt", 24, 3), ("5pt", 60, 32)])
-def test_spmm_run_staged_path(monkeypatch, kind, N, k, kt):
-    """opt-in SpMM kernel that stages the block's X tile through aligned column runs with cp.async (JP_SPMM_RUNS=1)"""
+@pytest.mark.parametrize("rows_threads", [("128", "128"), ("64", "128"), ("64", "64"), ("64", "256")])
+@pytest.mark.parametrize("kind,N,k", [("27pt", 20, 8), ("27pt", 20, 11), ("27pt", 12, 32)])
+def test_spmm_run_staged_path(monkeypatch, kind, N, k, kt, rows_threads):
+    """SpMM kernel that stages the block's X tile through aligned column runs with TMA bulk copies, in every
+    configuration of vector tile, rows per block and lanes per row"""
+    if kt == "8" and rows_threads[1] == "64":
+        pytest.skip("KT = 8 is built for 128 and 256 threads")
     monkeypatch.setenv("JP_SPMM_RUNS", "1")
     monkeypatch.setenv("JP_SPMM_RUNS_KT", kt)
+    monkeypatch.setenv("JP_SPMM_RUNS_ROWS", rows_threads[0])
+    monkeypatch.setenv("JP_SPMM_RUNS_THREADS", rows_threads[1])
     c, m, A = serial_matrix(kind, N)
     n = m.numMyElements()
     x = synthetic.vector_block(1, n, k, seed=1)

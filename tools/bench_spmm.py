@@ -18,7 +18,8 @@ import jpetra_b200 as jp  # noqa: E402
 from jpetra_b200 import _lib, synthetic  # noqa: E402
 
 VARIANTS = [
-    ("gather", {}),
+    ("gather", {"JP_SPMM_RUNS": "0"}),
+    ("default", {}),
     ("runs_kt4", {"JP_SPMM_RUNS": "1", "JP_SPMM_RUNS_KT": "4"}),
     ("runs_kt8", {"JP_SPMM_RUNS": "1", "JP_SPMM_RUNS_KT": "8"}),
     ("runs_kt4_cap1024", {"JP_SPMM_RUNS": "1", "JP_SPMM_RUNS_KT": "4", "JP_SPMM_RUNS_CAP": "1024"}),
@@ -37,15 +38,28 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--ks", default="8,32")
     ap.add_argument("--variants", default="")
+    ap.add_argument("--direct", action="store_true", help="time the CSRMatrix's own handle (device fillComplete, default "
+                    "path selection) instead of re-uploading the matrix per variant")
     args = ap.parse_args()
     lib = _lib.init(0)
     comm = jp.SerialComm()
     N, kind = args.N, args.kind
     n = N ** synthetic.STENCILS[kind][0]
     m = jp.BlockMap(n, comm)
-    A = synthetic.build_matrix(jp, m, kind, N)
-    rp, ci, va = A.rowOffsets, A.localIndices1D, A.values
-    nnz = len(va)
+    fill = "host"
+    if args.direct:
+        A = synthetic.build_matrix(jp, m, kind, N, fill=False)
+        try:
+            A.fillComplete(m, m, device=True)
+            fill = "device"
+        except Exception as e:  # noqa: BLE001 -- keep the measurement alive
+            print(f"device fillComplete failed ({e}); falling back to the host path", file=sys.stderr)
+            A = synthetic.build_matrix(jp, m, kind, N)
+        nnz = A.getLocalNumEntries()
+    else:
+        A = synthetic.build_matrix(jp, m, kind, N)
+        rp, ci, va = A.rowOffsets, A.localIndices1D, A.values
+        nnz = len(va)
     peak = 6531.9
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
@@ -53,17 +67,18 @@ def main():
     e0, e1 = C.c_int64(), C.c_int64()
     _lib.check(lib.jp_event_create(C.byref(e0)))
     _lib.check(lib.jp_event_create(C.byref(e1)))
-    out = {"kind": kind, "N": N, "n": n, "nnz": nnz, "peak_gbs": peak, "cases": []}
+    out = {"kind": kind, "N": N, "n": n, "nnz": nnz, "peak_gbs": peak, "fill": fill, "cases": []}
     ref = {}
     keep = [v for v in args.variants.split(",") if v]
-    for label, env in VARIANTS:
-        if keep and label not in keep:
+    for label, env in ([("default_direct", {})] if args.direct else VARIANTS):
+        if not args.direct and keep and label not in keep:
             continue
         for key in ("JP_SPMM_RUNS", "JP_SPMM_RUNS_KT", "JP_SPMM_RUNS_CAP", "JP_SPMM_RUNS_THREADS", "JP_SPMM_RUNS_ROWS", "JP_SPMM_TILE"):
             os.environ.pop(key, None)
         os.environ.update(env)
-        h = C.c_int64()
-        _lib.check(lib.jp_csr_create(n, n, n, nnz, _lib.ptr(rp), _lib.ptr(ci), _lib.ptr(va), 1, C.byref(h)))
+        h = C.c_int64(A.h if args.direct else 0)
+        if not args.direct:
+            _lib.check(lib.jp_csr_create(n, n, n, nnz, _lib.ptr(rp), _lib.ptr(ci), _lib.ptr(va), 1, C.byref(h)))
         for k in (int(s) for s in args.ks.split(",")):
             X = jp.DenseMultiVector(m, synthetic.vector_block(1, n, k, seed=1))
             Y = jp.DenseMultiVector(m, k)
@@ -87,7 +102,8 @@ def main():
                                  "gflops": 2.0 * nnz * k / t / 1e6, "runs_state": int(info[1]), "widest_tile": int(info[3]),
                                  "max_abs_diff_vs_gather": float(np.abs(y - ref[k]).max()) if k in ref else None})
             del X, Y
-        _lib.check(lib.jp_csr_destroy(h.value))
+        if not args.direct:
+            _lib.check(lib.jp_csr_destroy(h.value))
     print(json.dumps(out))
 
 
