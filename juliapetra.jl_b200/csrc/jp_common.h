@@ -271,6 +271,7 @@ void launch_spmv(const Csr& A, const DeviceBuffer& blocks, int32_t n_blocks, boo
                  cudaStream_t stream);
 void launch_spmv_trans(const Csr& A, const double* x, int64_t ldx, double* y, int64_t ldy, int32_t ny, int32_t k, double alpha,
                        double beta, cudaStream_t stream);
+void csr_prepare_spmm(Csr& A);  // builds the SpMM tile / run tables if that has not been decided yet
 void csr_finalize_structure(Csr& A, const std::vector<int32_t>& rp, const std::vector<int32_t>& rowmax);
 void launch_scale_fill(double* y, int64_t n, double beta, cudaStream_t stream);  // y = beta==0 ? 0 : beta*y
 void plan_ensure_buffers(Plan& p, int32_t k);

@@ -305,6 +305,12 @@ void launch_spmv_fused(const Csr& A, const FusedHalo& h, const double* x, const 
   JP_LAUNCH_CHECK();
 }
 
+// decide (once per matrix) which SpMM path k > 1 applies take
+void csr_prepare_spmm(Csr& A) {
+  if (A.tile_state == 0) build_tiles(A);
+  if (A.runs_state == 0) build_runs(A);
+}
+
 double* launch_spmv_dot(Csr& A, const double* x, double* y, double alpha, double beta, const double* w, cudaStream_t stream) {
   const int32_t nb = A.n_blocks_all;
   const size_t ws_bytes = ((size_t)nb + 4) * 8;  // [block partials | result]
@@ -343,11 +349,8 @@ void launch_spmv_blocks(const Csr& A, const void* blocks_int4, int32_t n_blocks,
                         const double* halo, int32_t halo_k, double* y, int64_t ldy, int32_t k, double alpha, double beta,
                         cudaStream_t stream) {
   if (n_blocks == 0 || k == 0) return;
-  if (k > 1 && A.tile_state == 0) {
-    // lazily build the SpMM tile tables; the block lists are re-uploaded in place (same buffers, same order)
-    build_tiles(const_cast<Csr&>(A));
-  }
-  if (k > 1 && A.runs_state == 0) build_runs(const_cast<Csr&>(A));
+  // lazily build the SpMM tables (tile path: the block lists are re-uploaded in place -- same buffers, same order)
+  if (k > 1) csr_prepare_spmm(const_cast<Csr&>(A));
   // the run-staged kernel serves launches over the WHOLE all-blocks or interior list (it has its own block lists with a
   // different geometry; a chunk of a list, as jp_apply_host launches, stays with the gather kernel)
   const bool whole_all = blocks_int4 == A.blocks_all.p && n_blocks == A.n_blocks_all;

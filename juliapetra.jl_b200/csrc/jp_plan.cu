@@ -831,8 +831,11 @@ int32_t jp_apply_host(jp_handle comm, jp_handle A, jp_handle plan, const double*
       const char* v = std::getenv("JP_HOST_PIPELINE");
       return !(v && *v == '0');
     }();
+    // The run-staged SpMM kernel works on its own row blocks, not on chunks of the all-blocks list; when a matrix takes
+    // it, a k > 1 host apply is one launch (like jp_apply), so both entry points give bit-identical results.
+    if (k > 1 && !trans) csr_prepare_spmm(*a);
     const bool pipelined = pipeline_enabled && !trans && p == nullptr && beta == 0.0 && alpha != 0.0 && nch > 1 && xb >= ((size_t)4 << 20) &&
-                           nx == a->n_cols && ny == a->n_rows;
+                           nx == a->n_cols && ny == a->n_rows && (k == 1 || a->runs_state != 1);
     if (!pipelined) {
       if (xb) JP_CUDA(cudaMemcpyAsync(x->d(), x_host, xb, cudaMemcpyHostToDevice, c.compute));
       if (beta != 0.0 && yb) JP_CUDA(cudaMemcpyAsync(y->d(), y_host, yb, cudaMemcpyHostToDevice, c.compute));
