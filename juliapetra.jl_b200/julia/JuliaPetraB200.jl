@@ -235,6 +235,20 @@ function axpby!(y::DeviceMultiVector{Float64}, a, x::DeviceMultiVector{Float64},
     check(ccall((:jp_mv_axpby, LIB), Int32, (Handle, Float64, Handle, Float64), y.handle, a, x.handle, b)); y.hostStale = true; y
 end
 
+"""
+    axpbyNorm2!(y, a, x, b)
+
+`y = a*x + b*y` and `norm(y, 2)` of the result in one pass (`jp_mv_axpby_norm2`): the residual update of a CG
+iteration fused with its norm (broadcast copyto!, src/MultiVector.jl:497-502, + norm, :122-133).
+"""
+function axpbyNorm2!(y::DeviceMultiVector{Float64}, a, x::DeviceMultiVector{Float64}, b)
+    out = Matrix{Float64}(undef, 1, numVectors(y))
+    check(ccall((:jp_mv_axpby_norm2, LIB), Int32, (Handle, Handle, Float64, Handle, Float64, Ptr{Float64}),
+                commhandle(y), y.handle, a, x.handle, b, out))
+    y.hostStale = true
+    out
+end
+
 # ---- device CSR + plan, created once at the end of fillComplete (src/CSRMatrix.jl:706-747) ----------------------------
 const DEVICE_CSR = IdDict{Any, Handle}()     # CSRMatrix => jp csr handle
 const DEVICE_PLAN = IdDict{Any, Handle}()    # Import     => jp plan handle
@@ -265,6 +279,66 @@ function upload!(A::CSRMatrix{Float64, GID, PID, LID}) where {GID, PID, LID}
         DEVICE_PLAN[imp] = p[]
     end
     A
+end
+
+"""
+    fillCompleteDevice!(A, domainMap, rangeMap)
+
+`fillComplete` with the O(nnz) part on the device (`jp_csr_fill_complete`): the entries inserted so far go over as they
+are (global column ids, insertion order); the column map (src/CSRGraphInternalMethods.jl:852-982), the GID -> LID remap
+(:636-712), the per-row sort + duplicate merge (src/CSRMatrix.jl:549-606) and the CSR packing (:403-484) run as
+kernels.  The host then only builds the column-map `BlockMap` from the returned GIDs and the `Import` from it, as
+`fillComplete` does today.  Needs a contiguous domain map (`BlockMap(n, comm)` / `BlockMap(n, nMy, comm)`).
+"""
+function fillCompleteDevice!(A::CSRMatrix{Float64, GID, PID, LID}, domainMap::BlockMap{GID, PID, LID},
+                             rangeMap::BlockMap{GID, PID, LID}) where {GID, PID, LID}
+    g = A.myGraph
+    nrows = getLocalNumRows(A)
+    counts = g.numRowEntries                                # entries actually inserted per row
+    ptr0 = Vector{Int64}(undef, nrows + 1); ptr0[1] = 0
+    for r in 1:nrows ptr0[r+1] = ptr0[r] + counts[r] end
+    gcols = Vector{Int64}(undef, ptr0[end]); vals = Vector{Float64}(undef, ptr0[end])
+    for r in 1:nrows                                        # pack the STATIC_PROFILE storage (src/CSRMatrix.jl:617-665)
+        s = g.rowOffsets[r]
+        gcols[ptr0[r]+1:ptr0[r+1]] = g.globalIndices1D[s:s+counts[r]-1]
+        vals[ptr0[r]+1:ptr0[r+1]] = A.values[s:s+counts[r]-1]
+    end
+    h = Ref{Handle}(0); info = Vector{Int64}(undef, 4)
+    rc = ccall((:jp_csr_fill_complete, LIB), Int32,
+               (Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64, Int64, Int64, Int32, Ref{Handle}, Ptr{Int64}),
+               nrows, ptr0, gcols, vals, minAllGID(domainMap), maxAllGID(domainMap),
+               numMyElements(domainMap) > 0 ? minMyGID(domainMap) : minAllGID(domainMap), numMyElements(domainMap), h, info)
+    comm = JuliaPetra.getComm(A)
+    err = rc == 1                                           # a column GID nobody owns (src/CSRGraphInternalMethods.jl:936-939)
+    rc > 1 && check(rc)
+    maxAll(comm, err ? 1 : 0) != 0 && error("makeColMap reports an error on at least one process")
+    colGIDs = Vector{GID}(undef, info[1])
+    check(ccall((:jp_csr_col_map, LIB), Int32, (Handle, Ptr{Int64}), h[], colGIDs))
+    colMap = BlockMap(numGlobalElements(domainMap), colGIDs, comm)      # src/CSRGraphInternalMethods.jl:981
+    # ... set A's colMap / domainMap / rangeMap / importer / exporter exactly as fillComplete does (makeImportExport,
+    # src/CSRGraphInternalMethods.jl:351-366), then remember the device matrix instead of calling upload!:
+    DEVICE_CSR[A] = h[]
+    colMap
+end
+
+"""
+    applyDot!(Y, A, X, W, mode, alpha, beta)
+
+`apply!(Y, A, X, mode, alpha, beta)` followed by `dot(W, Y)` as one call (`jp_apply_dot`); for one vector without an
+importer the SpMV kernel accumulates the dot product itself (the p'Ap of CG with W = X).
+"""
+function applyDot!(Y::DeviceMultiVector{Float64, GID, PID, LID}, A::CSRMatrix{Float64, GID, PID, LID},
+                   X::DeviceMultiVector{Float64, GID, PID, LID}, W::DeviceMultiVector{Float64, GID, PID, LID},
+                   mode::TransposeMode, alpha::Float64, beta::Float64) where {GID, PID, LID}
+    isFillActive(A) && throw(InvalidStateError("Cannot call apply(...) until fillComplete(...)"))
+    haskey(DEVICE_CSR, A) || upload!(A)
+    imp = getImporter(A)
+    out = Matrix{Float64}(undef, 1, numVectors(Y))
+    check(ccall((:jp_apply_dot, LIB), Int32, (Handle, Handle, Handle, Handle, Handle, Int32, Float64, Float64, Handle, Ptr{Float64}),
+                JuliaPetra.getComm(A).handle, Y.handle, DEVICE_CSR[A], X.handle, imp === nothing ? 0 : DEVICE_PLAN[imp], Int32(mode),
+                alpha, beta, W.handle, out))
+    Y.hostStale = true
+    out
 end
 
 # ---- Operator: apply! (src/RowMatrix.jl:261-357) on device multivectors ---------------------------------------------------
