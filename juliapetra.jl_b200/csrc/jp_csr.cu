@@ -208,6 +208,10 @@ void build_runs(Csr& A) {
   JP_REQUIRE(threads == 64 || threads == 128 || threads == 256, "JP_SPMM_RUNS_THREADS must be 64, 128 or 256");
   const int max_rows = env_int("JP_SPMM_RUNS_ROWS", 128);  // one lane per row with 128 threads: measured best (profiles/)
   JP_REQUIRE(max_rows >= 16 && max_rows <= kRunsMaxRows, "JP_SPMM_RUNS_ROWS must be in [16,128]");
+  if (A.max_row_len > cap) {  // a row longer than the stage would be a LONGROW block: not this kernel's matrix (no download needed)
+    A.runs_state = -1;
+    return;
+  }
   std::vector<int32_t> ci((size_t)A.nnz), rp((size_t)A.n_rows + 1);
   JP_CUDA(cudaStreamSynchronize(ctx().compute));
   JP_CUDA(cudaMemcpy(ci.data(), A.colind.p, (size_t)A.nnz * 4, cudaMemcpyDeviceToHost));

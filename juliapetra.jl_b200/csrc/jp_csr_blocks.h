@@ -126,15 +126,30 @@ inline bool build_run_tables(const std::vector<int32_t>& ci, std::vector<BlockDe
   std::vector<std::vector<int32_t>> block_runs(nb);
   std::vector<int32_t> width(nb, 0), ncopied(nb, 0);
   const int nthreads = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  for (const BlockDesc& b : all)
+    if ((b.nrows_kind >> 16) == KIND_LONGROW) return false;
+  // cheap early answer for matrices that are not banded (a random 10^9-nonzero matrix must not pay a full sort of
+  // every block just to be turned away): distinct aligned column pairs of up to 256 evenly spaced blocks
+  {
+    int64_t s_w = 0, s_nnz = 0;
+    std::vector<int32_t> u;
+    const size_t step = std::max<size_t>(1, nb / 256);
+    for (size_t bi = 0; bi < nb; bi += step) {
+      const BlockDesc& b = all[bi];
+      u.assign(ci.begin() + b.p0, ci.begin() + b.p1);
+      for (int32_t& c : u) c >>= 1;
+      std::sort(u.begin(), u.end());
+      s_w += 2 * (int64_t)(std::unique(u.begin(), u.end()) - u.begin());
+      s_nnz += b.p1 - b.p0;
+    }
+    if (s_nnz == 0 || (double)s_w > 0.7 * (double)s_nnz) return false;
+  }
   bool reject = false;  // (benign race: only ever set to true)
   auto worker = [&](int tix) {
     std::vector<int32_t> u, base;
     for (size_t bi = tix; bi < nb; bi += nthreads) {
       const BlockDesc& b = all[bi];
-      if ((b.nrows_kind >> 16) == KIND_LONGROW) {
-        reject = true;
-        continue;
-      }
+      if (reject) return;
       u.assign(ci.begin() + b.p0, ci.begin() + b.p1);
       std::sort(u.begin(), u.end());
       u.erase(std::unique(u.begin(), u.end()), u.end());
