@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--cpu-iters", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--fused", action="store_true", help="cg workloads: apply! + dot through the fused jp_apply_dot call")
     ap.add_argument("--ref-ranks", type=int, default=0, help="--impl reference: simulated MPI ranks (default: host cores, max 32)")
     return ap.parse_args()
 
@@ -229,9 +230,13 @@ def main():
         args.no_e2e = True
 
     def step():
-        _lib.check(lib.jp_apply(comm.handle, Y.h, A.h, X.h, plan, jp.NO_TRANS, 1.0, 0.0))
+        if cg and args.fused:
+            pAp = A.apply_dot_(Y, X)  # jp_apply_dot: no host round trip between apply! and dot
+        else:
+            _lib.check(lib.jp_apply(comm.handle, Y.h, A.h, X.h, plan, jp.NO_TRANS, 1.0, 0.0))
         if cg:
-            pAp = X.dot(Y)
+            if not args.fused:
+                pAp = X.dot(Y)
             R.norm(2)
             XS.axpby_(1e-3 / (abs(pAp[0, 0]) + 1.0), X, 1.0)
 
