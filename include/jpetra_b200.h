@@ -163,6 +163,13 @@ int32_t jp_local_apply(jp_handle Y, jp_handle A, jp_handle X, int32_t mode, doub
  * (the semantics of src/RowMatrix.jl:324-352, i.e. Tpetra's applyTranspose).  Collective over the plan's comm. */
 int32_t jp_apply(jp_handle comm, jp_handle Y, jp_handle A, jp_handle X, jp_handle plan, int32_t mode, double alpha,
                  double beta);
+/* apply! of a matrix whose range map differs from its row map (the exporter branch, src/RowMatrix.jl:298-308, 324-330,
+ * with the semantics of Tpetra::CrsMatrix::apply that those lines transcribe; the reference's own lines cannot run).
+ * export_plan is the plan of Export(rowMap, rangeMap).  NO_TRANS: the product is formed on the row map and ADDED into
+ * Y (range map) -- rows held by several ranks are summed; TRANS: X (range map) is first brought onto the row map.
+ * import_plan as in jp_apply (0 when the importer is `nothing`).  Collective over the plans' comm. */
+int32_t jp_apply_export(jp_handle comm, jp_handle Y, jp_handle A, jp_handle X, jp_handle import_plan, jp_handle export_plan,
+                        int32_t mode, double alpha, double beta);
 /* apply! followed by dot(W, Y) (src/MultiVector.jl:84-108) without a host round trip in between; for k = 1, NO_TRANS
  * and no importer the dot product is accumulated by the SpMV kernel itself (p'Ap of a CG iteration: W = X). */
 int32_t jp_apply_dot(jp_handle comm, jp_handle Y, jp_handle A, jp_handle X, jp_handle plan, int32_t mode, double alpha,

@@ -81,6 +81,7 @@ PROTOTYPES = {
     "jp_transfer_wait": [c_i64],
     "jp_local_apply": [c_i64, c_i64, c_i64, c_i32, c_f64, c_f64],
     "jp_apply": [c_i64, c_i64, c_i64, c_i64, c_i64, c_i32, c_f64, c_f64],
+    "jp_apply_export": [c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i32, c_f64, c_f64],
     "jp_apply_dot": [c_i64, c_i64, c_i64, c_i64, c_i64, c_i32, c_f64, c_f64, c_i64, c_vp],
     "jp_apply_host": [c_i64, c_i64, c_i64, c_vp, c_vp, c_i32, c_i32, c_f64, c_f64],
 }

@@ -204,6 +204,8 @@ struct Csr : Object {
   // cache of the column-map multivector (A.importMV, src/CSRMatrix.jl:10,772-781); only used when the column
   // map is not [domain prefix | remote tail] and the fused apply path does not apply
   std::unique_ptr<MultiVector> import_mv;
+  // cache of the row-map multivector (A.exportMV, src/CSRMatrix.jl:11): the exporter branch of apply! (rangeMap != rowMap)
+  std::unique_ptr<MultiVector> export_mv;
   // GIDs of the column map in LID order, kept when the matrix was fill-completed on the device (jp_csr_fill_complete)
   DeviceBuffer colmap_gids;
   // jp_apply_dot workspace: [block partials | result]

@@ -624,6 +624,107 @@ void apply_no_trans(Csr* a, Plan* p, MultiVector* y, MultiVector* x, double alph
   body(false);
 }
 
+// apply! when rangeMap != rowMap (src/RowMatrix.jl:298-308 and 324-330).  The reference's lines
+// cannot run (undefined names; ADD ignored by unpackAndCombine; reverse mode passes the forward lists unswapped), so
+// this follows Tpetra::CrsMatrix::apply, which they transcribe -- and the oracle's exportAdd / exportReverseInsert:
+//   NO_TRANS: YRowMap = alpha * A * XColMap (the ordinary apply, into the cached row-map multivector, beta = 0);
+//             Y = beta * Y; every row-map entry is ADDED to the range-map entry with the same GID: in place for same /
+//             permuted ids, through the Export's distributor (pack -> send/recv -> scatter-add) for the others.
+//   TRANS:    X (range map) is brought onto the row map first -- the Export run backwards with INSERT -- then the
+//             ordinary transposed apply runs from the row-map multivector.
+// Only kernels of the importer / transposed paths are involved (add_rows, add_permute, pack, scatter_add, permute,
+// unpack); `ex` is the plan made from Export(rowMap, rangeMap).
+void apply_impl(Csr* a, Plan* p, MultiVector* y, MultiVector* x, int32_t mode, double alpha, double beta);
+
+void apply_with_exporter(Csr* a, Plan* imp, Plan* ex, MultiVector* y, MultiVector* x, int32_t mode, double alpha, double beta) {
+  Context& c = ctx();
+  JP_REQUIRE(mode == JP_NO_TRANS || mode == JP_TRANS || mode == JP_CONJ_TRANS, "apply!: bad TransposeMode");
+  JP_REQUIRE(x != y, "apply!: X and Y must be different multivectors");
+  JP_REQUIRE(x->k == y->k, "apply!: X and Y must have the same number of vectors");
+  JP_REQUIRE(ex->n_src == a->n_rows, "apply!: the exporter's source map is not the matrix's row map");
+  const int32_t k = x->k;
+  if (alpha == 0.0) {  // src/RowMatrix.jl:271-278
+    launch_scale_fill(y->d(), (int64_t)y->n * k, beta, c.compute);
+    return;
+  }
+  if (!a->export_mv || a->export_mv->k != k) {  // createRowMapMultiVector, src/RowMatrix.jl:236-259
+    JP_CUDA(cudaStreamSynchronize(c.compute));
+    JP_CUDA(cudaStreamSynchronize(c.comm));
+    a->export_mv = std::make_unique<MultiVector>();
+    a->export_mv->n = a->n_rows;
+    a->export_mv->k = k;
+    a->export_mv->data.alloc((size_t)a->n_rows * k * 8 + 64);
+    JP_CUDA(cudaMemsetAsync(a->export_mv->d(), 0, (size_t)a->n_rows * k * 8 + 64, c.compute));
+  }
+  MultiVector* rowmv = a->export_mv.get();
+  plan_ensure_buffers(*ex, k);
+  if (mode == JP_NO_TRANS) {
+    JP_REQUIRE(y->n == ex->n_tgt, "apply!: Y does not match the exporter's target (range) map");
+    apply_impl(a, imp, rowmv, x, JP_NO_TRANS, alpha, 0.0);  // leaves the compute stream ordered after all of it
+    launch_scale_fill(y->d(), (int64_t)y->n * k, beta, c.compute);
+    if (k == 0) return;
+    if (ex->num_same > 0) {
+      add_rows_kernel<<<grid_for((int64_t)ex->num_same * k), kThreads, 0, c.compute>>>(y->d(), y->n, rowmv->d(), rowmv->n, ex->num_same, k);
+      JP_LAUNCH_CHECK();
+    }
+    if (ex->n_permute > 0) {
+      add_permute_kernel<<<grid_for((int64_t)ex->n_permute * k), kThreads, 0, c.compute>>>(y->d(), y->n, rowmv->d(), rowmv->n,
+                                                                                          ex->permute_to.as<int32_t>(),
+                                                                                          ex->permute_from.as<int32_t>(), ex->n_permute, k);
+      JP_LAUNCH_CHECK();
+    }
+    JP_CUDA(cudaEventRecord(c.ev_x_ready, c.compute));
+    JP_CUDA(cudaStreamWaitEvent(c.comm, c.ev_x_ready, 0));
+    if (ex->n_export > 0) {
+      pack_kernel<<<grid_for((int64_t)ex->n_export * k), kThreads, 0, c.comm>>>(rowmv->d(), rowmv->n, ex->export_lids.as<int32_t>(),
+                                                                               ex->n_export, k, ex->sendbuf.as<double>());
+      JP_LAUNCH_CHECK();
+    }
+    exchange(*ex, k, /*reverse=*/false, c.comm);
+    JP_CUDA(cudaEventRecord(ex->ev_done, c.comm));
+    JP_CUDA(cudaStreamWaitEvent(c.compute, ex->ev_done, 0));
+    if (ex->n_remote > 0) {
+      scatter_add_kernel<<<grid_for((int64_t)ex->n_remote * k), kThreads, 0, c.compute>>>(y->d(), y->n, ex->remote_lids.as<int32_t>(),
+                                                                                         ex->n_remote, k, ex->recvbuf.as<double>());
+      JP_LAUNCH_CHECK();
+    }
+    JP_CUDA(cudaEventRecord(c.ev_tmp, c.compute));
+    JP_CUDA(cudaStreamWaitEvent(c.comm, c.ev_tmp, 0));
+    return;
+  }
+  // TRANS / CONJ_TRANS: XRowMap = the Export run backwards with INSERT
+  JP_REQUIRE(x->n == ex->n_tgt, "apply!: X does not match the exporter's target (range) map");
+  if (k > 0) {
+    if (ex->num_same > 0)
+      JP_CUDA(cudaMemcpy2DAsync(rowmv->d(), (size_t)rowmv->n * 8, x->d(), (size_t)x->n * 8, (size_t)ex->num_same * 8, (size_t)k,
+                                cudaMemcpyDeviceToDevice, c.compute));
+    if (ex->n_permute > 0) {  // rowmv[permuteFrom] = x[permuteTo]: the forward permutation inverted
+      permute_kernel<<<grid_for((int64_t)ex->n_permute * k), kThreads, 0, c.compute>>>(rowmv->d(), rowmv->n, x->d(), x->n,
+                                                                                      ex->permute_from.as<int32_t>(),
+                                                                                      ex->permute_to.as<int32_t>(), ex->n_permute, k);
+      JP_LAUNCH_CHECK();
+    }
+    JP_CUDA(cudaEventRecord(c.ev_x_ready, c.compute));
+    JP_CUDA(cudaStreamWaitEvent(c.comm, c.ev_x_ready, 0));
+    if (ex->n_remote > 0) {  // what the forward export delivers here travels back to the ranks that hold the row
+      pack_kernel<<<grid_for((int64_t)ex->n_remote * k), kThreads, 0, c.comm>>>(x->d(), x->n, ex->remote_lids.as<int32_t>(), ex->n_remote, k,
+                                                                               ex->sendbuf.as<double>());
+      JP_LAUNCH_CHECK();
+    }
+    exchange(*ex, k, /*reverse=*/true, c.comm);
+    JP_CUDA(cudaEventRecord(ex->ev_done, c.comm));
+    JP_CUDA(cudaStreamWaitEvent(c.compute, ex->ev_done, 0));
+    if (ex->n_export > 0) {
+      unpack_kernel<<<grid_for((int64_t)ex->n_export * k), kThreads, 0, c.compute>>>(rowmv->d(), rowmv->n, ex->export_lids.as<int32_t>(),
+                                                                                    ex->n_export, k, ex->recvbuf.as<double>());
+      JP_LAUNCH_CHECK();
+    }
+    JP_CUDA(cudaEventRecord(c.ev_tmp, c.compute));
+    JP_CUDA(cudaStreamWaitEvent(c.comm, c.ev_tmp, 0));
+  }
+  apply_impl(a, imp, y, rowmv, mode, alpha, beta);
+}
+
 void apply_impl(Csr* a, Plan* p, MultiVector* y, MultiVector* x, int32_t mode, double alpha, double beta) {
   JP_REQUIRE(mode == JP_NO_TRANS || mode == JP_TRANS || mode == JP_CONJ_TRANS, "apply!: bad TransposeMode");
   JP_REQUIRE(x != y, "apply!: X and Y must be different multivectors");
@@ -780,6 +881,20 @@ int32_t jp_apply(jp_handle comm, jp_handle Y, jp_handle A, jp_handle X, jp_handl
     MultiVector* x = get<MultiVector>(X, Kind::MultiVector, "multivector");
     Plan* p = plan ? get<Plan>(plan, Kind::Plan, "plan") : nullptr;
     apply_impl(a, p, y, x, mode, alpha, beta);
+  });
+}
+
+int32_t jp_apply_export(jp_handle comm, jp_handle Y, jp_handle A, jp_handle X, jp_handle import_plan, jp_handle export_plan, int32_t mode,
+                        double alpha, double beta) {
+  return guarded([&] {
+    require_init();
+    (void)get<Comm>(comm, Kind::Comm, "comm");
+    Csr* a = get<Csr>(A, Kind::Csr, "csr matrix");
+    MultiVector* y = get<MultiVector>(Y, Kind::MultiVector, "multivector");
+    MultiVector* x = get<MultiVector>(X, Kind::MultiVector, "multivector");
+    Plan* imp = import_plan ? get<Plan>(import_plan, Kind::Plan, "plan") : nullptr;
+    Plan* ex = get<Plan>(export_plan, Kind::Plan, "plan");
+    apply_with_exporter(a, imp, ex, y, x, mode, alpha, beta);
   });
 }
 

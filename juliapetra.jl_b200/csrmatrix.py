@@ -402,16 +402,18 @@ class CSRMatrix:
         """apply!(Y, A, X, mode, alpha, beta): Y = beta*Y + alpha*op(A)*X"""
         if self.isFillActive():
             raise InvalidStateError("Cannot call apply(...) until fillComplete(...)")
-        if self.exporter is not None:
-            # the exporter branch uses undefined names in the reference (src/RowMatrix.jl:247,302)
-            raise InvalidStateError("apply!: rangeMap != rowMap is non-functional in the reference (out of scope)")
         comm = self.comm
         alpha, beta = float(alpha), float(beta)
         YIsReplicated = not Y.getMap().distributedGlobal()
         if alpha != 0.0 and YIsReplicated and comm.myPid() != 1:
             beta = 0.0  # src/RowMatrix.jl:283-287
         plan = self.importer.device_plan() if self.importer is not None else 0
-        _lib.check(_lib.lib().jp_apply(comm.handle, Y.h, self.h, X.h, plan, int(mode), alpha, beta))
+        if self.exporter is not None:
+            # rangeMap != rowMap (src/RowMatrix.jl:298-308, 324-330; the reference's lines use undefined names, so the
+            # semantics are Tpetra's): the product is formed on the row map and exported into Y with ADD
+            _lib.check(_lib.lib().jp_apply_export(comm.handle, Y.h, self.h, X.h, plan, self.exporter.device_plan(), int(mode), alpha, beta))
+        else:
+            _lib.check(_lib.lib().jp_apply(comm.handle, Y.h, self.h, X.h, plan, int(mode), alpha, beta))
         if alpha != 0.0 and YIsReplicated and comm.numProc() > 1:
             Y.commReduce()  # src/RowMatrix.jl:353-355 (identity on SerialComm)
         return Y
@@ -422,12 +424,11 @@ class CSRMatrix:
         accumulates the dot product itself.  Returns the 1 x numVectors array `dot` returns (src/MultiVector.jl:84-108)."""
         if self.isFillActive():
             raise InvalidStateError("Cannot call apply(...) until fillComplete(...)")
-        if self.exporter is not None:
-            raise InvalidStateError("apply!: rangeMap != rowMap is non-functional in the reference (out of scope)")
         W = X if W is None else W
         comm = self.comm
-        if not Y.getMap().distributedGlobal() and comm.numProc() > 1:
-            # replicated Y needs the commReduce between apply! and dot (src/RowMatrix.jl:353-355): not fusable
+        if self.exporter is not None or (not Y.getMap().distributedGlobal() and comm.numProc() > 1):
+            # the exporter's ADD, or the commReduce of a replicated Y (src/RowMatrix.jl:353-355), sits between apply! and
+            # dot: not fusable
             self.apply_(Y, X, mode, alpha, beta)
             return W.dot(Y)
         out = np.empty((1, Y.numVectors()), dtype=np.float64)
@@ -450,6 +451,8 @@ class CSRMatrix:
         H2D copy of X, the kernels and the D2H copy of Y all happen inside this one C-ABI call (jp_apply_host)."""
         if self.isFillActive():
             raise InvalidStateError("Cannot call apply(...) until fillComplete(...)")
+        if self.exporter is not None:
+            raise InvalidStateError("apply_host: a matrix whose range map differs from its row map needs device multivectors (apply_)")
         X = np.asfortranarray(X, dtype=np.float64)
         if X.ndim == 1:
             X = X.reshape(-1, 1, order="F")

@@ -1199,6 +1199,7 @@ struct Matrix {
   TransferPlan* exporter = nullptr;
   bool fillComplete = false;
   MultiVec* importMV = nullptr;  // src/CSRMatrix.jl:10, cache of the column-map MV
+  MultiVec* exportMV = nullptr;  // src/CSRMatrix.jl:11, cache of the row-map MV (exporter branch)
 };
 
 Matrix* matrixCreate(Map* rowMap, const PerRank<std::vector<LID>>& numEntPerRow) {
@@ -1468,10 +1469,89 @@ MultiVec* createColumnMapMultiVector(Matrix* A, MultiVec* X) {
   return A->importMV;
 }
 
-// src/RowMatrix.jl:261-357.  Paths restated: alpha==0 shortcut; NO_TRANS with or
+// src/RowMatrix.jl:236-259
+MultiVec* createRowMapMultiVector(Matrix* A, MultiVec* Y) {
+  if (A->exportMV == nullptr || A->exportMV->k != Y->k) {
+    delete A->exportMV;
+    A->exportMV = mvCreate(A->rowMap, Y->k);
+  }
+  return A->exportMV;
+}
+
+// doExport(YRowMap, Y, exporter, ADD), forward mode (src/RowMatrix.jl:298-308).  The reference's unpackAndCombine
+// ignores the combine mode (src/MultiVector.jl:359-371) and its exporter branch cannot run (undefined names,
+// src/RowMatrix.jl:247,302), so this restates the semantics of Tpetra::CrsMatrix::applyNonTranspose, which those
+// lines transcribe: every row-map entry is ADDED to the range-map entry with the same GID -- in place for same /
+// permuted ids, through the distributor for rows whose range-map owner is another rank (received contributions are
+// added in arrival order).  NOT pinned by any reference test; tests/test_oracle_golden.py checks it against a dense
+// operator assembled from every rank's rows.
+void exportAdd(MultiVec* src, MultiVec* tgt, TransferPlan* plan) {
+  int P = src->map->comm->P;
+  int k = src->k;
+  PerRank<std::vector<uint8_t>> exports(P);
+  for (int p = 0; p < P; ++p) {
+    const PlanData& d = plan->d[p];
+    const int64_t ns = src->n(p), nt = tgt->n(p);
+    const double* s = src->data[p].data();
+    double* t = tgt->data[p].data();
+    for (int v = 0; v < k; ++v) {
+      for (LID i = 1; i <= d.numSameIDs; ++i) t[(size_t)v * nt + i - 1] += s[(size_t)v * ns + i - 1];
+      for (size_t i = 0; i < d.permuteToLIDs.size(); ++i)
+        t[(size_t)v * nt + d.permuteToLIDs[i] - 1] += s[(size_t)v * ns + d.permuteFromLIDs[i] - 1];
+    }
+    std::vector<double> ex;
+    packAndPrepare(s, ns, k, d.exportLIDs, ex);
+    exports[p].resize(ex.size() * sizeof(double));
+    if (!ex.empty()) std::memcpy(exports[p].data(), ex.data(), exports[p].size());
+  }
+  PerRank<std::vector<uint8_t>> imports = distResolve(plan->dist, exports, sizeof(double) * k, /*reverse=*/false);
+  for (int p = 0; p < P; ++p) {
+    const PlanData& d = plan->d[p];
+    const int64_t nt = tgt->n(p);
+    if (imports[p].size() != d.remoteLIDs.size() * sizeof(double) * k) throwState("export: received length does not match remoteLIDs");
+    const double* in = reinterpret_cast<const double*>(imports[p].data());
+    double* t = tgt->data[p].data();
+    for (size_t i = 0; i < d.remoteLIDs.size(); ++i)
+      for (int v = 0; v < k; ++v) t[(size_t)v * nt + d.remoteLIDs[i] - 1] += in[i * k + v];
+  }
+}
+
+// doImport(X, XRowMap, exporter, INSERT): the Export run backwards (src/RowMatrix.jl:324-330) -- every row-map entry
+// receives the range-map entry with the same GID (a row held by several ranks gets a copy on each).  Same remark as
+// exportAdd: the reference passes the forward lists unswapped in reverse mode (src/DistObject.jl:122-129), which is
+// only meaningful for trivial plans; this is the Tpetra semantics with the lists swapped.
+void exportReverseInsert(MultiVec* src /*range map*/, MultiVec* tgt /*row map*/, TransferPlan* plan) {
+  int P = src->map->comm->P;
+  int k = src->k;
+  PerRank<std::vector<uint8_t>> exports(P);
+  for (int p = 0; p < P; ++p) {
+    const PlanData& d = plan->d[p];
+    const int64_t ns = src->n(p), nt = tgt->n(p);
+    const double* s = src->data[p].data();
+    double* t = tgt->data[p].data();
+    for (int v = 0; v < k; ++v) {
+      for (LID i = 1; i <= d.numSameIDs; ++i) t[(size_t)v * nt + i - 1] = s[(size_t)v * ns + i - 1];
+      for (size_t i = 0; i < d.permuteToLIDs.size(); ++i)
+        t[(size_t)v * nt + d.permuteFromLIDs[i] - 1] = s[(size_t)v * ns + d.permuteToLIDs[i] - 1];
+    }
+    std::vector<double> ex;
+    packAndPrepare(s, ns, k, d.remoteLIDs, ex);  // what the forward export delivers here travels back
+    exports[p].resize(ex.size() * sizeof(double));
+    if (!ex.empty()) std::memcpy(exports[p].data(), ex.data(), exports[p].size());
+  }
+  PerRank<std::vector<uint8_t>> imports = distResolve(plan->dist, exports, sizeof(double) * k, /*reverse=*/true);
+  for (int p = 0; p < P; ++p) {
+    const PlanData& d = plan->d[p];
+    if (imports[p].size() != d.exportLIDs.size() * sizeof(double) * k) throwState("reverse export: received length does not match exportLIDs");
+    unpackAndCombine(tgt->data[p].data(), tgt->n(p), k, d.exportLIDs, reinterpret_cast<const double*>(imports[p].data()));
+  }
+}
+
+// src/RowMatrix.jl:261-357.  Paths pinned by the reference's tests: alpha==0 shortcut; NO_TRANS with or
 // without importer and exporter===nothing; TRANS/CONJ_TRANS with importer and
-// exporter both nothing (serial, pinned by test/CSRMatrixTests.jl:152-158).  The
-// other branches are non-functional in the reference.
+// exporter both nothing (serial, test/CSRMatrixTests.jl:152-158).  The other
+// branches (distributed TRANS, exporter) are non-functional in the reference
+//  and restated with the Tpetra semantics they transcribe.
 void applyMatrix(MultiVec* Y, Matrix* A, MultiVec* X, int mode, double alpha, double beta) {
   if (!A->fillComplete) throwState("Cannot call apply(...) until fillComplete(...)");
   int P = A->rowMap->comm->P;
@@ -1485,20 +1565,38 @@ void applyMatrix(MultiVec* Y, Matrix* A, MultiVec* X, int mode, double alpha, do
   }
   bool YIsReplicated = !Y->map->d[0].distributedGlobal;
   if (mode == NO_TRANS) {
-    if (A->exporter != nullptr) throwState("apply!: the exporter branch is non-functional in the reference (out of scope)");
     MultiVec* XColMap = X;
     if (A->importer != nullptr) {
       XColMap = createColumnMapMultiVector(A, X);
       doTransfer(X, XColMap, A->importer, false, INSERT);
     }
     if (XColMap == Y) throwState("apply!: in-place apply is non-functional in the reference (XColmap typo, src/RowMatrix.jl:318)");
-    for (int p = 0; p < P; ++p) {
-      double b = (YIsReplicated && p + 1 != 1) ? 0.0 : beta;  // :285-287
-      localApply(Y->data[p].data(), Y->n(p), A->d[p], A->rowMap->d[p].numMyElements, XColMap->data[p].data(), XColMap->n(p), Y->k, mode, alpha, b);
+    if (A->exporter != nullptr) {
+      // rangeMap != rowMap, src/RowMatrix.jl:298-308: the product lands on the row map, Y is
+      // scaled, and the row-map result is exported into it with ADD
+      MultiVec* YRowMap = createRowMapMultiVector(A, Y);
+      for (int p = 0; p < P; ++p)
+        localApply(YRowMap->data[p].data(), YRowMap->n(p), A->d[p], A->rowMap->d[p].numMyElements, XColMap->data[p].data(), XColMap->n(p), Y->k,
+                   mode, alpha, 0.0);
+      for (int p = 0; p < P; ++p) {
+        double b = (YIsReplicated && p + 1 != 1) ? 0.0 : beta;  // :285-287
+        for (double& y : Y->data[p]) y = (b == 0.0) ? 0.0 : y * b;
+      }
+      exportAdd(YRowMap, Y, A->exporter);
+    } else {
+      for (int p = 0; p < P; ++p) {
+        double b = (YIsReplicated && p + 1 != 1) ? 0.0 : beta;  // :285-287
+        localApply(Y->data[p].data(), Y->n(p), A->d[p], A->rowMap->d[p].numMyElements, XColMap->data[p].data(), XColMap->n(p), Y->k, mode, alpha, b);
+      }
     }
   } else {
-    if (A->exporter != nullptr) throwState("apply!: rangeMap != rowMap is non-functional in the reference (out of scope)");
     if (X == Y) throwState("apply!: X and Y must differ");
+    if (A->exporter != nullptr) {
+      // X lives on the range map: bring it onto the row map first (src/RowMatrix.jl:324-330)
+      MultiVec* XRowMap = createRowMapMultiVector(A, X);
+      exportReverseInsert(X, XRowMap, A->exporter);
+      X = XRowMap;
+    }
     if (A->importer == nullptr) {
       for (int p = 0; p < P; ++p) {
         double b = (YIsReplicated && p + 1 != 1) ? 0.0 : beta;
@@ -1960,6 +2058,7 @@ void orc_matrix_destroy(void* mv) {
   delete m->importer;
   delete m->exporter;
   delete m->importMV;
+  delete m->exportMV;
   if (m->ownsColMap) delete m->colMap;
   delete m;
 }

@@ -288,3 +288,29 @@ def case_device_fill_glue(rank, world, kind, N, max_len):
         raise AssertionError("expected makeColMap to report an error")
     except RuntimeError as e:
         assert "makeColMap" in str(e)
+
+
+def case_overlapping_rows_fill(rank, world):
+    """a matrix assembled on an overlapping row map with domain = range = the uniform map (rangeMap != rowMap, SURVEY.md
+    8f item 4): column map, Import AND Export lists, CSR bit-exact against the oracle"""
+    import jpetra_b200 as jp
+    from fill_cases import overlapping_rows_problem
+    from helpers import assert_plan_equal
+    comm = jp.TorchDistComm()
+    pid, P = comm.myPid(), comm.numProc()
+    c, ouni, orow, OA, per_rank, dense = overlapping_rows_problem(P, 6)
+    rows, rp, cols, vals = per_rank[pid - 1]
+    uni = jp.BlockMap(P * 6, comm)
+    rowmap = jp.BlockMap(-1, rows, comm)
+    assert rowmap.numGlobalElements() == orow.info(pid)["numGlobalElements"]
+    A = jp.CSRMatrix(rowmap, np.diff(rp), jp.STATIC_PROFILE)
+    A.insertGlobalValuesBatch(rows, rp, cols, vals)
+    A._fillCompleteHost(uni, uni)
+    orp, oci, ova = OA.csr(pid)
+    assert np.array_equal(A.rowOffsets, orp) and np.array_equal(A.localIndices1D, oci) and np.array_equal(A.values, ova)
+    assert np.array_equal(A.colMap.myGlobalElements(), OA.col_map.my_gids(pid))
+    assert A.exporter is not None and OA.exporter is not None
+    assert_plan_equal(A.exporter, OA.exporter, pid)
+    assert (A.importer is None) == (OA.importer is None)
+    if A.importer is not None:
+        assert_plan_equal(A.importer, OA.importer, pid)

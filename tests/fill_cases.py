@@ -102,3 +102,42 @@ def empty_and_bad_gid_case(fill, error_type):
         assert "outside" in str(e)
     else:
         raise AssertionError("a column GID outside the global range must be rejected")
+
+
+def overlapping_rows_problem(P, n_per, seed=5, width=3):
+    """A matrix assembled on an OVERLAPPING row map (every rank holds its own n_per rows plus the first two rows of the
+    next rank, with its own partial contributions to them -- finite-element style), domain = range = the uniform map:
+    rangeMap != rowMap, so apply! takes the exporter branch.  Returns (comm, uniform map, row map,
+    filled OMatrix, per-rank (rows, rowptr0, cols, vals), dense global operator)."""
+    rng = np.random.default_rng(seed)
+    N = P * n_per
+    c = O.OComm(P)
+    uni = O.OMap.uniform(c, N)
+
+    def row_gids(p):
+        own = list(range((p - 1) * n_per + 1, p * n_per + 1))
+        nxt = [(p % P) * n_per + 1, (p % P) * n_per + 2] if P > 1 else []
+        return own + nxt
+
+    rowmap = O.OMap.from_gids(c, -1, [row_gids(p) for p in range(1, P + 1)])
+    dense = np.zeros((N, N))
+    per_rank, counts = [], []
+    for p in range(1, P + 1):
+        rows = np.array(row_gids(p), dtype=np.int64)
+        lens = rng.integers(1, 2 * width + 2, size=len(rows))
+        rp = np.zeros(len(rows) + 1, dtype=np.int64)
+        np.cumsum(lens, out=rp[1:])
+        # the diagonal first (every global column is referenced, as the serial column map requires), then scattered columns
+        cols = np.concatenate([np.concatenate([[g], np.clip(g + rng.integers(-width * n_per // 2, width * n_per // 2 + 1, size=l - 1), 1, N)])
+                               for g, l in zip(rows, lens)])
+        vals = rng.standard_normal(len(cols))
+        for r, g in enumerate(rows):
+            for i in range(rp[r], rp[r + 1]):
+                dense[g - 1, cols[i] - 1] += vals[i]
+        per_rank.append((rows, rp, cols.astype(np.int64), vals))
+        counts.append(lens)
+    A = O.OMatrix(rowmap, counts)
+    for p, (rows, rp, cols, vals) in enumerate(per_rank, start=1):
+        A.insert_rows(p, rows, rp, cols, vals)
+    A.fill_complete(uni, uni)
+    return c, uni, rowmap, A, per_rank, dense

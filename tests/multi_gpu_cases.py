@@ -211,6 +211,31 @@ def main():
         Xc = jp.DenseMultiVector(rm, 1)
         its, rel = jp.cg(Ac, Bc, Xc, tol=1e-12, maxiter=400, fused=fused)
         assert rel <= 1e-12 and np.abs(Xc.data - xs_true).max() <= 1e-9, (fused, its, rel)
+    # ---- rangeMap != rowMap: an operator assembled on an overlapping row map (opt-in until the
+    #      device path has been run on a GPU once, see tests/test_gpu_exporter.py) ----
+    if os.environ.get("JP_TEST_UNVALIDATED") == "1":
+        from fill_cases import overlapping_rows_problem
+        oc, ouni, orow, OAe, per_rank, dense = overlapping_rows_problem(P, 40)
+        rows_e, rp_e, cols_e, vals_e = per_rank[rank]
+        uni = jp.BlockMap(P * 40, comm)
+        rowmap = jp.BlockMap(-1, rows_e, comm)
+        Ae = jp.CSRMatrix(rowmap, np.diff(rp_e), jp.STATIC_PROFILE)
+        Ae.insertGlobalValuesBatch(rows_e, rp_e, cols_e, vals_e)
+        Ae.fillComplete(uni, uni)
+        assert Ae.getExporter() is not None
+        assert_plan_equal(Ae.exporter, OAe.exporter, pid)
+        for k in (1, 3):
+            xs = [synthetic.vector_block(ouni.info(p)["minMyGID"], ouni.info(p)["numMyElements"], k, seed=1) for p in everyone]
+            ys = [synthetic.vector_block(ouni.info(p)["minMyGID"], ouni.info(p)["numMyElements"], k, seed=2) for p in everyone]
+            for mode, omode in ((jp.NO_TRANS, O.NO_TRANS), (jp.TRANS, O.TRANS)):
+                OX, OY = O.OMV.from_arrays(ouni, xs), O.OMV.from_arrays(ouni, ys)
+                OAe.apply(OY, OX, omode, 3.0, 0.5)
+                Xe, Ye = jp.DenseMultiVector(uni, xs[rank]), jp.DenseMultiVector(uni, ys[rank])
+                for _ in range(2):
+                    Ye.data = ys[rank]
+                    Ae.apply_(Ye, Xe, mode, 3.0, 0.5)
+                ref = OY.get(pid)
+                assert np.abs(Ye.data - ref).max() <= 100 * TOL * (np.abs(ref).max() + 1.0), ("exporter", pid, k, int(mode))
     # commReduce on a replicated map (test/DenseMultiVectorTests.jl:96-99)
     rep = jp.BlockMap(6, 6, comm)
     v = jp.DenseMultiVector(rep, (10.0 ** pid) * np.ones((6, 3)))

@@ -43,3 +43,8 @@ def test_nontrivial_export_plan(world):
 @pytest.mark.parametrize("world,kind,N", [(2, "7pt", 6), (4, "27pt", 5), (4, "powerlaw", 900), (3, "5pt", 11)])
 def test_device_fill_complete_glue_on_the_cpu_model(world, kind, N):
     dist_cases.run("case_device_fill_glue", world, kind, N, 150)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_overlapping_row_map_fill_complete_and_export_plan(world):
+    dist_cases.run("case_overlapping_rows_fill", world)

@@ -491,3 +491,28 @@ def test_distributed_trans_matches_dense(kind, N, P, k):
     A.apply(Y2, X, O.TRANS, 1.0, 0.0)
     got2 = np.vstack([Y2.get(p) for p in range(1, P + 1)])
     assert (np.abs(got2 - dense.T @ xg) <= 1e-12 * (np.abs(dense).T @ np.abs(xg)) + 1e-300).all()
+
+
+@pytest.mark.parametrize("P,k", [(1, 1), (2, 2), (4, 3)])
+def test_exporter_branch_matches_dense(P, k):
+    """rangeMap != rowMap (src/RowMatrix.jl:298-308, 324-330 with Tpetra's semantics): an operator
+    assembled on an overlapping row map, NO_TRANS (product on the row map, exported into Y with ADD) and TRANS (X
+    imported onto the row map first), against the dense global operator"""
+    from fill_cases import overlapping_rows_problem
+    c, uni, rowmap, A, per_rank, dense = overlapping_rows_problem(P, 6)
+    assert (A.exporter is not None) == (P > 1)
+    n = dense.shape[0]
+    rng = np.random.default_rng(7)
+    xg, yg = rng.standard_normal((n, k)), rng.standard_normal((n, k))
+    split = lambda g: [g[uni.info(p)["minMyGID"] - 1: uni.info(p)["maxMyGID"], :] for p in range(1, P + 1)]
+    for mode, op in ((O.NO_TRANS, dense), (O.TRANS, dense.T)):
+        X, Y = O.OMV.from_arrays(uni, split(xg)), O.OMV.from_arrays(uni, split(yg))
+        A.apply(Y, X, mode, 3.0, 0.5)
+        got = np.vstack([Y.get(p) for p in range(1, P + 1)])
+        ref = 0.5 * yg + 3.0 * (op @ xg)
+        scale = 0.5 * np.abs(yg) + 3.0 * (np.abs(op) @ np.abs(xg))
+        assert (np.abs(got - ref) <= 1e-12 * scale + 1e-300).all(), (mode, np.abs(got - ref).max())
+        Y2 = O.OMV.from_arrays(uni, split(np.full((n, k), np.nan)))  # beta == 0 overwrites
+        A.apply(Y2, X, mode, 1.0, 0.0)
+        got2 = np.vstack([Y2.get(p) for p in range(1, P + 1)])
+        assert (np.abs(got2 - op @ xg) <= 1e-12 * (np.abs(op) @ np.abs(xg)) + 1e-300).all()
