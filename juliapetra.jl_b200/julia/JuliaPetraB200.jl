@@ -352,8 +352,17 @@ function apply!(Y::DeviceMultiVector{Float64, GID, PID, LID}, A::CSRMatrix{Float
     if alpha != 0 && YIsReplicated && myPid(comm) != 1
         beta = 0.0                                   # src/RowMatrix.jl:283-287
     end
-    check(ccall((:jp_apply, LIB), Int32, (Handle, Handle, Handle, Handle, Handle, Int32, Float64, Float64),
-                comm.handle, Y.handle, DEVICE_CSR[A], X.handle, imp === nothing ? 0 : DEVICE_PLAN[imp], Int32(mode), alpha, beta))
+    ex = getExporter(A)
+    if ex === nothing
+        check(ccall((:jp_apply, LIB), Int32, (Handle, Handle, Handle, Handle, Handle, Int32, Float64, Float64),
+                    comm.handle, Y.handle, DEVICE_CSR[A], X.handle, imp === nothing ? 0 : DEVICE_PLAN[imp], Int32(mode), alpha, beta))
+    else
+        # rangeMap != rowMap (src/RowMatrix.jl:298-308, 324-330): DEVICE_PLAN[ex] is made from the Export's lists with the
+        # same jp_plan_create call upload! uses for the Import
+        check(ccall((:jp_apply_export, LIB), Int32, (Handle, Handle, Handle, Handle, Handle, Handle, Int32, Float64, Float64),
+                    comm.handle, Y.handle, DEVICE_CSR[A], X.handle, imp === nothing ? 0 : DEVICE_PLAN[imp], DEVICE_PLAN[ex], Int32(mode),
+                    alpha, beta))
+    end
     Y.hostStale = true
     alpha != 0 && YIsReplicated && commReduce(Y)     # src/RowMatrix.jl:353-355
     Y
