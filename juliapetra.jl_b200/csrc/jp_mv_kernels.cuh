@@ -1,5 +1,6 @@
-// jp_mv_kernels.cuh -- fused MultiVector kernels of the CG building blocks, device code only, in
-// the CUDA subset tests/cuda_emul can execute on the CPU.  The plain fill!/scale!/axpby/dot/norm kernels are in jp_mv.cu.
+// jp_mv_kernels.cuh -- the MultiVector kernels (src/MultiVector.jl:52-161, 497-502): fill!, scale!, axpby, dot, norm and
+// the fused axpby+norm2 of the CG building blocks.  Device code only, in the CUDA subset
+// tests/cuda_emul can execute on the CPU; launches and the reduction workspace are in jp_mv.cu (see its header).
 #pragma once
 #include <cstdint>
 
@@ -12,6 +13,119 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// MODE 0: dot  sum x*y      (src/MultiVector.jl:99-105)
+// MODE 1: norm2 sum x*x     (src/MultiVector.jl:122-131)
+// MODE 2: normp sum x^p     (src/MultiVector.jl:135-142)
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) reduce_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t n,
+                                                            double p, double* __restrict__ partials,
+                                                            unsigned int* __restrict__ tickets, double* __restrict__ out) {
+  const int vec = blockIdx.y;
+  const double* xv = x + (size_t)vec * n;
+  const double* yv = MODE == 0 ? y + (size_t)vec * n : nullptr;
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (MODE == 1) {
+    // a single input stream: eight loads in flight per thread to cover the HBM latency
+    for (; i + 7 * stride < n; i += 8 * stride) {
+      const double x0 = xv[i], x1 = xv[i + stride], x2 = xv[i + 2 * stride], x3 = xv[i + 3 * stride];
+      const double x4 = xv[i + 4 * stride], x5 = xv[i + 5 * stride], x6 = xv[i + 6 * stride], x7 = xv[i + 7 * stride];
+      a0 += x0 * x0; a1 += x1 * x1; a2 += x2 * x2; a3 += x3 * x3;
+      a0 += x4 * x4; a1 += x5 * x5; a2 += x6 * x6; a3 += x7 * x7;
+    }
+  }
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    double x0 = xv[i], x1 = xv[i + stride], x2 = xv[i + 2 * stride], x3 = xv[i + 3 * stride];
+    if (MODE == 0) {
+      double y0 = yv[i], y1 = yv[i + stride], y2 = yv[i + 2 * stride], y3 = yv[i + 3 * stride];
+      a0 += x0 * y0; a1 += x1 * y1; a2 += x2 * y2; a3 += x3 * y3;
+    } else if (MODE == 1) {
+      a0 += x0 * x0; a1 += x1 * x1; a2 += x2 * x2; a3 += x3 * x3;
+    } else {
+      a0 += pow(x0, p); a1 += pow(x1, p); a2 += pow(x2, p); a3 += pow(x3, p);
+    }
+  }
+  for (; i < n; i += stride) {
+    double x0 = xv[i];
+    if (MODE == 0) a0 += x0 * yv[i];
+    else if (MODE == 1) a0 += x0 * x0;
+    else a0 += pow(x0, p);
+  }
+  double s = warp_sum((a0 + a1) + (a2 + a3));
+  __shared__ double warp_part[kThreads / 32];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) warp_part[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    double t = lane < kThreads / 32 ? warp_part[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) {
+      partials[(size_t)vec * gridDim.x + blockIdx.x] = t;
+      __threadfence();
+      unsigned int ticket = atomicAdd(&tickets[vec], 1u);
+      is_last = (ticket == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (is_last && warp == 0) {
+    __threadfence();
+    // fixed-order final sum over the blocks of this vector
+    double t = 0.0;
+    const volatile double* pv = partials + (size_t)vec * gridDim.x;
+    for (unsigned int b = lane; b < gridDim.x; b += 32) t += pv[b];
+    t = warp_sum(t);
+    if (lane == 0) {
+      out[vec] = t;
+      tickets[vec] = 0;  // re-arm for the next call
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) fill_kernel(double* __restrict__ y, int64_t n, double v) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) y[i] = v;
+}
+
+// y *= alpha  (rmul!, src/MultiVector.jl:63)
+__global__ void __launch_bounds__(kThreads) scale_kernel(double* __restrict__ y, int64_t n, double alpha) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {  // four independent loads in flight per thread
+    const double a0 = y[i], a1 = y[i + stride], a2 = y[i + 2 * stride], a3 = y[i + 3 * stride];
+    y[i] = __dmul_rn(a0, alpha);
+    y[i + stride] = __dmul_rn(a1, alpha);
+    y[i + 2 * stride] = __dmul_rn(a2, alpha);
+    y[i + 3 * stride] = __dmul_rn(a3, alpha);
+  }
+  for (; i < n; i += stride) y[i] = __dmul_rn(y[i], alpha);
+}
+
+// column v scaled by alpha[v]  (src/MultiVector.jl:72-77)
+__global__ void __launch_bounds__(kThreads) scale_vec_kernel(double* __restrict__ y, int64_t n, const double* __restrict__ alpha) {
+  const double a = alpha[blockIdx.y];
+  double* col = y + (size_t)blockIdx.y * n;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    const double a0 = col[i], a1 = col[i + stride], a2 = col[i + 2 * stride], a3 = col[i + 3 * stride];
+    col[i] = __dmul_rn(a0, a);
+    col[i + stride] = __dmul_rn(a1, a);
+    col[i + 2 * stride] = __dmul_rn(a2, a);
+    col[i + 3 * stride] = __dmul_rn(a3, a);
+  }
+  for (; i < n; i += stride) col[i] = __dmul_rn(col[i], a);
+}
+
+// y = (a*x) + (b*y), unfused  (broadcast copyto!, src/MultiVector.jl:497-502)
+__global__ void __launch_bounds__(kThreads) axpby_kernel(double* __restrict__ y, const double* __restrict__ x, int64_t n, double a,
+                                                           double b) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride)
+    y[i] = __dadd_rn(__dmul_rn(a, x[i]), __dmul_rn(b, y[i]));
 }
 
 // y = (a*x) + (b*y) with the unfused arithmetic of the broadcast `@. y = a*x + b*y` (src/MultiVector.jl:497-502), and in

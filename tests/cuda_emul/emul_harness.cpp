@@ -6,6 +6,7 @@
 #include "../../juliapetra.jl_b200/csrc/jp_csr_blocks.h"
 #include "../../juliapetra.jl_b200/csrc/jp_fill_pipeline.h"
 #include "../../juliapetra.jl_b200/csrc/jp_mv_kernels.cuh"
+#include "../../juliapetra.jl_b200/csrc/jp_plan_kernels.cuh"
 
 namespace {
 std::string g_error;
@@ -285,6 +286,109 @@ int emul_axpby_norm2(double* y, const double* x, int64_t n, int32_t k, double a,
     for (int v = 0; v < k; ++v) out[(size_t)rep * k + v] = d_out[v];
   }
   std::memcpy(y, d_y.p, (size_t)n * k * 8);
+  return 0;
+}
+
+
+// ---- MultiVector kernels (csrc/jp_mv_kernels.cuh) ----
+// op: 0 dot(x, y), 1 sum x^2, 2 sum x^p -> out[k] (the local sums before the allreduce), `repeats` launches on one
+// workspace (the ticket must re-arm); x, y: n x k column-major
+int emul_mv_reduce(int32_t op, const double* x, const double* y, int64_t n, int32_t k, double p, int32_t blocks, int32_t repeats, double* out) {
+  using namespace jp;
+  using namespace jp::mvk;
+  DeviceBuffer d_x, d_y, ws;
+  d_x.alloc((size_t)n * k * 8 + 64);
+  d_y.alloc((size_t)n * k * 8 + 64);
+  std::memcpy(d_x.p, x, (size_t)n * k * 8);
+  if (y) std::memcpy(d_y.p, y, (size_t)n * k * 8);
+  ws.alloc(((size_t)k * blocks + 2 * (size_t)k) * 8);
+  std::memset(ws.p, 0, ws.bytes);
+  double* partials = ws.as<double>();
+  double* d_out = partials + (size_t)k * blocks;
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(d_out + k);
+  for (int rep = 0; rep < repeats; ++rep) {
+    if (op == 0)
+      JP_KLAUNCH(reduce_kernel<0>, dim3(blocks, k), kThreads, 0, nullptr, d_x.as<double>(), d_y.as<double>(), n, p, partials, tickets, d_out);
+    else if (op == 1)
+      JP_KLAUNCH(reduce_kernel<1>, dim3(blocks, k), kThreads, 0, nullptr, d_x.as<double>(), (const double*)nullptr, n, p, partials, tickets, d_out);
+    else
+      JP_KLAUNCH(reduce_kernel<2>, dim3(blocks, k), kThreads, 0, nullptr, d_x.as<double>(), (const double*)nullptr, n, p, partials, tickets, d_out);
+    for (int v = 0; v < k; ++v) out[(size_t)rep * k + v] = d_out[v];
+  }
+  return 0;
+}
+
+// op: 0 fill(y, a), 1 scale(y, a), 2 scale_vec(y, alpha_k), 3 axpby(y, a, x, b); y is n x k column-major, updated in place
+int emul_mv_elementwise(int32_t op, double* y, const double* x, const double* alpha_k, int64_t n, int32_t k, double a, double b, int32_t blocks) {
+  using namespace jp;
+  using namespace jp::mvk;
+  DeviceBuffer d_y, d_x, d_a;
+  d_y.alloc((size_t)n * k * 8 + 64);
+  d_x.alloc((size_t)n * k * 8 + 64);
+  d_a.alloc((size_t)k * 8 + 64);
+  std::memcpy(d_y.p, y, (size_t)n * k * 8);
+  if (x) std::memcpy(d_x.p, x, (size_t)n * k * 8);
+  if (alpha_k) std::memcpy(d_a.p, alpha_k, (size_t)k * 8);
+  const int64_t total = n * k;
+  if (op == 0) JP_KLAUNCH(fill_kernel, (unsigned)blocks, kThreads, 0, nullptr, d_y.as<double>(), total, a);
+  else if (op == 1) JP_KLAUNCH(scale_kernel, (unsigned)blocks, kThreads, 0, nullptr, d_y.as<double>(), total, a);
+  else if (op == 2) JP_KLAUNCH(scale_vec_kernel, dim3(blocks, k), kThreads, 0, nullptr, d_y.as<double>(), n, d_a.as<double>());
+  else JP_KLAUNCH(axpby_kernel, (unsigned)blocks, kThreads, 0, nullptr, d_y.as<double>(), d_x.as<double>(), total, a, b);
+  std::memcpy(y, d_y.p, (size_t)n * k * 8);
+  return 0;
+}
+
+// ---- transfer kernels (csrc/jp_plan_kernels.cuh); LIDs are 0-based ----
+// op: 0 pack (buf <- src[lids]), 1 unpack (tgt[lids] <- buf), 2 scatter_add (tgt[lids] += buf), 3 permute (tgt[to] <- src[from]),
+//     4 add_permute (tgt[to] += src[from]), 5 add_rows (tgt[0:n_ids] += src[0:n_ids]).  mv: n_mv x k (tgt for 1, 2; src for 0);
+//     other: the second multivector of ops 3-5 (n_other x k) or the LID-major buffer (n_ids x k, vector-minor) of ops 0-2.
+int emul_plan_op(int32_t op, double* mv, int64_t n_mv, double* other, int64_t n_other, const int32_t* lids_a, const int32_t* lids_b,
+                 int32_t n_ids, int32_t k, int32_t blocks) {
+  using namespace jp;
+  using namespace jp::plank;
+  DeviceBuffer d_mv, d_other, d_a, d_b;
+  const size_t other_elems = op <= 2 ? (size_t)n_ids * k : (size_t)n_other * k;
+  d_mv.alloc((size_t)n_mv * k * 8 + 64);
+  d_other.alloc(other_elems * 8 + 64);
+  d_a.alloc((size_t)n_ids * 4 + 64);
+  d_b.alloc((size_t)n_ids * 4 + 64);
+  std::memcpy(d_mv.p, mv, (size_t)n_mv * k * 8);
+  std::memcpy(d_other.p, other, other_elems * 8);
+  if (lids_a) std::memcpy(d_a.p, lids_a, (size_t)n_ids * 4);
+  if (lids_b) std::memcpy(d_b.p, lids_b, (size_t)n_ids * 4);
+  const unsigned g = (unsigned)blocks;
+  if (op == 0) JP_KLAUNCH(pack_kernel, g, kThreads, 0, nullptr, d_mv.as<double>(), n_mv, d_a.as<int32_t>(), n_ids, k, d_other.as<double>());
+  else if (op == 1) JP_KLAUNCH(unpack_kernel, g, kThreads, 0, nullptr, d_mv.as<double>(), n_mv, d_a.as<int32_t>(), n_ids, k, d_other.as<double>());
+  else if (op == 2) JP_KLAUNCH(scatter_add_kernel, g, kThreads, 0, nullptr, d_mv.as<double>(), n_mv, d_a.as<int32_t>(), n_ids, k, d_other.as<double>());
+  else if (op == 3) JP_KLAUNCH(permute_kernel, g, kThreads, 0, nullptr, d_mv.as<double>(), n_mv, d_other.as<double>(), n_other, d_a.as<int32_t>(), d_b.as<int32_t>(), n_ids, k);
+  else if (op == 4) JP_KLAUNCH(add_permute_kernel, g, kThreads, 0, nullptr, d_mv.as<double>(), n_mv, d_other.as<double>(), n_other, d_a.as<int32_t>(), d_b.as<int32_t>(), n_ids, k);
+  else JP_KLAUNCH(add_rows_kernel, g, kThreads, 0, nullptr, d_mv.as<double>(), n_mv, d_other.as<double>(), n_other, n_ids, k);
+  std::memcpy(mv, d_mv.p, (size_t)n_mv * k * 8);
+  std::memcpy(other, d_other.p, other_elems * 8);
+  return 0;
+}
+
+// ---- localApply TRANS (spmv_trans_kernel): y (n_cols x k) += (alpha * x[row]) * val, y pre-scaled by the caller ----
+int emul_spmv_trans(int32_t n_rows, int32_t n_cols, const int32_t* rowptr, const int32_t* colind, const double* vals, const double* x, double* y,
+                    int32_t k, double alpha, int32_t blocks) {
+  using namespace jp;
+  using namespace jp::csrk;
+  const int64_t nnz = rowptr[n_rows];
+  DeviceBuffer d_rp, d_ci, d_va, d_x, d_y;
+  d_rp.alloc(((size_t)n_rows + 1) * 4);
+  d_ci.alloc((size_t)nnz * 4 + 16);
+  d_va.alloc((size_t)nnz * 8 + 16);
+  d_x.alloc((size_t)n_rows * k * 8 + 64);
+  d_y.alloc((size_t)n_cols * k * 8 + 64);
+  std::memcpy(d_rp.p, rowptr, ((size_t)n_rows + 1) * 4);
+  std::memcpy(d_ci.p, colind, (size_t)nnz * 4);
+  std::memcpy(d_va.p, vals, (size_t)nnz * 8);
+  std::memcpy(d_x.p, x, (size_t)n_rows * k * 8);
+  std::memcpy(d_y.p, y, (size_t)n_cols * k * 8);
+  if (n_rows > 0 && nnz > 0)
+    JP_KLAUNCH(spmv_trans_kernel, (unsigned)blocks, kSpmvThreads, 0, nullptr, d_rp.as<int32_t>(), d_ci.as<int32_t>(), d_va.as<double>(),
+               d_x.as<double>(), (int64_t)n_rows, d_y.as<double>(), (int64_t)n_cols, n_rows, k, alpha);
+  std::memcpy(y, d_y.p, (size_t)n_cols * k * 8);
   return 0;
 }
 

@@ -113,3 +113,67 @@ def axpby_norm2(y, a, x, b, blocks=3, repeats=1):
                                 C.c_int32(repeats), _p(out))
     assert rc == 0
     return yy, out
+
+
+def _f(a, shape=None):
+    a = np.asfortranarray(np.array(a, dtype=np.float64))
+    if a.ndim == 1:
+        a = a.reshape(-1, 1, order="F")
+    return a.copy(order="F")
+
+
+def mv_reduce(op, x, y=None, p=2.0, blocks=3, repeats=2):
+    """reduce_kernel<op> (0 dot, 1 sum of squares, 2 sum of p-th powers) -> sums[repeats, k]"""
+    x = _f(x)
+    n, k = x.shape
+    yy = _f(y) if y is not None else None
+    out = np.zeros((repeats, k), dtype=np.float64)
+    rc = lib().emul_mv_reduce(C.c_int32(op), _p(x), _p(yy) if yy is not None else None, C.c_int64(n), C.c_int32(k), C.c_double(p),
+                              C.c_int32(blocks), C.c_int32(repeats), _p(out))
+    assert rc == 0
+    return out
+
+
+def mv_elementwise(op, y, x=None, alpha_k=None, a=0.0, b=0.0, blocks=3):
+    """0 fill(y, a), 1 scale(y, a), 2 scale_vec(y, alpha_k), 3 axpby(y, a, x, b) -> new y"""
+    yy = _f(y)
+    n, k = yy.shape
+    xx = _f(x) if x is not None else None
+    ak = np.ascontiguousarray(alpha_k, dtype=np.float64) if alpha_k is not None else None
+    rc = lib().emul_mv_elementwise(C.c_int32(op), _p(yy), _p(xx) if xx is not None else None, _p(ak) if ak is not None else None,
+                                   C.c_int64(n), C.c_int32(k), C.c_double(a), C.c_double(b), C.c_int32(blocks))
+    assert rc == 0
+    return yy
+
+
+def plan_op(op, mv, other, lids_a=None, lids_b=None, n_ids=None, blocks=2):
+    """transfer kernels with 0-based LIDs (see emul_plan_op); returns (mv, other) after the launch.  For ops 0-2 `other`
+    is the (n_ids, k) LID-major buffer; for ops 3-5 the second multivector."""
+    m = _f(mv)
+    n_mv, k = m.shape
+    la = np.ascontiguousarray(lids_a, dtype=np.int32) if lids_a is not None else None
+    lb = np.ascontiguousarray(lids_b, dtype=np.int32) if lids_b is not None else None
+    if n_ids is None:
+        n_ids = len(la)
+    if op <= 2:
+        o = np.ascontiguousarray(np.array(other, dtype=np.float64).reshape(n_ids, k))  # row-major = LID-major, vector-minor
+        n_other = n_ids
+    else:
+        o = _f(other)
+        n_other = o.shape[0]
+    rc = lib().emul_plan_op(C.c_int32(op), _p(m), C.c_int64(n_mv), _p(o), C.c_int64(n_other), _p(la) if la is not None else None,
+                            _p(lb) if lb is not None else None, C.c_int32(n_ids), C.c_int32(k), C.c_int32(blocks))
+    assert rc == 0
+    return m, o
+
+
+def spmv_trans(rowptr0, colind0, vals, x, y, alpha=1.0, blocks=2):
+    """spmv_trans_kernel: y (n_cols, k) += (alpha * x[row]) * val"""
+    rp = np.ascontiguousarray(rowptr0, dtype=np.int32)
+    ci = np.ascontiguousarray(colind0, dtype=np.int32)
+    va = np.ascontiguousarray(vals, dtype=np.float64)
+    xx, yy = _f(x), _f(y)
+    rc = lib().emul_spmv_trans(C.c_int32(len(rp) - 1), C.c_int32(yy.shape[0]), _p(rp), _p(ci), _p(va), _p(xx), _p(yy), C.c_int32(xx.shape[1]),
+                               C.c_double(alpha), C.c_int32(blocks))
+    assert rc == 0
+    return yy
