@@ -282,6 +282,8 @@ void plan_unpack(Plan& p, MultiVector& tgt, cudaStream_t stream);
 struct FusedHalo;
 void launch_spmv_fused(const Csr& A, const FusedHalo& h, const double* x, const double* halo, double* y, double alpha, double beta,
                        cudaStream_t stream);
+double* launch_spmv_fused_dot(Csr& A, const FusedHalo& h, const double* x, const double* halo, double* y, double alpha, double beta,
+                              const double* w, cudaStream_t stream);
 const double* plan_post_p2p(Plan& p, const MultiVector& src);
 void plan_p2p_ack(Plan& p);
 bool p2p_setup_public(Plan& p, int32_t k);

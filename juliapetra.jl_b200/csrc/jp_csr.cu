@@ -66,7 +66,10 @@ struct FusedSpmvArgs {
   FusedHalo h;
 };
 
-__global__ void __launch_bounds__(kSpmvThreads) spmv_fused_halo_kernel(const FusedSpmvArgs a) {
+// DOT: every CTA also leaves sum_r w[r] * y_new[r] over its rows in partials[blockIdx.x] (0 for the pack CTAs), the
+// multi-GPU form of spmv_dot_kernel (jp_apply_dot with a peer-memory halo)
+template <bool DOT>
+__device__ __forceinline__ void fused_halo_body(const FusedSpmvArgs& a, const double* __restrict__ w, double* __restrict__ partials) {
   JP_DYN_SMEM(smem_raw);
   __shared__ double s_red[kSpmvThreads / 32];
   __shared__ __align__(8) uint64_t s_bar;
@@ -74,6 +77,7 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_fused_halo_kernel(const Fus
   const int tid = threadIdx.x;
   const int bid = blockIdx.x;
   const uint64_t epoch = a.h.epoch;
+  double dacc = 0.0;
   if (bid < a.n_pack) {
     // ---- pack + send ----
     if (tid < a.h.n_sends && epoch > 1)  // back-pressure: the receiver consumed the previous halo
@@ -97,14 +101,16 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_fused_halo_kernel(const Fus
   } else if (bid < a.n_pack + a.n_interior) {
     const StageView sv = stage_view(smem_raw, a.cap);
     const BlockRange b = decode_block(a.interior, bid - a.n_pack);
-    spmv_block<false, 1>(b, sv, &s_bar, s_red, a.rowptr, a.colind, a.vals, a.x, nullptr, a.nloc, a.y, a.alpha, a.beta);
+    if (DOT) dacc = spmv_block<false, 1, true>(b, sv, &s_bar, s_red, a.rowptr, a.colind, a.vals, a.x, nullptr, a.nloc, a.y, a.alpha, a.beta, w);
+    else spmv_block<false, 1>(b, sv, &s_bar, s_red, a.rowptr, a.colind, a.vals, a.x, nullptr, a.nloc, a.y, a.alpha, a.beta);
   } else {
     // ---- boundary rows: wait for the neighbours' halos first ----
     if (tid < a.h.n_sources) wait_flag_ge(a.h.sources[tid].ready_flag, epoch, a.h.timeout_flag);
     __syncthreads();
     const StageView sv = stage_view(smem_raw, a.cap);
     const BlockRange b = decode_block(a.boundary, bid - a.n_pack - a.n_interior);
-    spmv_block<true, 1>(b, sv, &s_bar, s_red, a.rowptr, a.colind, a.vals, a.x, a.halo, a.nloc, a.y, a.alpha, a.beta);
+    if (DOT) dacc = spmv_block<true, 1, true>(b, sv, &s_bar, s_red, a.rowptr, a.colind, a.vals, a.x, a.halo, a.nloc, a.y, a.alpha, a.beta, w);
+    else spmv_block<true, 1>(b, sv, &s_bar, s_red, a.rowptr, a.colind, a.vals, a.x, a.halo, a.nloc, a.y, a.alpha, a.beta);
     __syncthreads();
     if (tid == 0) s_last = (atomicAdd(a.h.tickets + 1, 1u) == (unsigned)a.n_boundary - 1);
     __syncthreads();
@@ -113,6 +119,14 @@ __global__ void __launch_bounds__(kSpmvThreads) spmv_fused_halo_kernel(const Fus
       if (tid == 0) a.h.tickets[1] = 0;
     }
   }
+  if (DOT) block_partial_store(dacc, s_red, partials, blockIdx.x);
+}
+
+__global__ void __launch_bounds__(kSpmvThreads) spmv_fused_halo_kernel(const FusedSpmvArgs a) { fused_halo_body<false>(a, nullptr, nullptr); }
+
+__global__ void __launch_bounds__(kSpmvThreads) spmv_fused_halo_dot_kernel(const FusedSpmvArgs a, const double* __restrict__ w,
+                                                                             double* __restrict__ partials) {
+  fused_halo_body<true>(a, w, partials);
 }
 
 int env_int(const char* name, int dflt) {
@@ -339,6 +353,40 @@ double* launch_spmv_dot(Csr& A, const double* x, double* y, double alpha, double
   }
   JP_LAUNCH_CHECK();
   sum_partials_kernel<<<1, kSpmvThreads, 0, stream>>>(partials, (unsigned)nb, out);
+  JP_LAUNCH_CHECK();
+  return out;
+}
+
+// the fused halo + SpMV launch of launch_spmv_fused with the dot product of jp_apply_dot accumulated on the way
+double* launch_spmv_fused_dot(Csr& A, const FusedHalo& h, const double* x, const double* halo, double* y, double alpha, double beta,
+                              const double* w, cudaStream_t stream) {
+  FusedSpmvArgs a;
+  a.interior = A.blocks_interior.as<BlockDesc>();
+  a.boundary = A.blocks_boundary.as<BlockDesc>();
+  a.n_interior = A.n_blocks_interior;
+  a.n_boundary = A.n_blocks_boundary;
+  a.n_pack = std::max(1, std::min(64, (h.n_export + 1023) / 1024));
+  a.rowptr = A.rowptr.as<int32_t>();
+  a.colind = A.colind.as<int32_t>();
+  a.vals = A.vals.as<double>();
+  a.x = x;
+  a.halo = halo;
+  a.nloc = A.n_local_cols;
+  a.y = y;
+  a.cap = A.nnz_cap;
+  a.alpha = alpha;
+  a.beta = beta;
+  a.h = h;
+  const int grid = a.n_pack + a.n_interior + a.n_boundary;
+  const size_t ws_bytes = ((size_t)grid + 4) * 8;  // [CTA partials | result]
+  if (A.dot_ws.bytes < ws_bytes) A.dot_ws.alloc(ws_bytes);
+  double* partials = A.dot_ws.as<double>();
+  double* out = partials + grid;
+  const size_t smem = stage_smem_bytes(A.nnz_cap);
+  set_smem_attr(spmv_fused_halo_dot_kernel, smem);
+  spmv_fused_halo_dot_kernel<<<grid, kSpmvThreads, smem, stream>>>(a, w, partials);
+  JP_LAUNCH_CHECK();
+  sum_partials_kernel<<<1, kSpmvThreads, 0, stream>>>(partials, (unsigned)grid, out);
   JP_LAUNCH_CHECK();
   return out;
 }

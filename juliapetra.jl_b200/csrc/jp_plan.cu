@@ -859,6 +859,31 @@ int32_t jp_apply_dot(jp_handle comm, jp_handle Y, jp_handle A, jp_handle X, jp_h
       mv_finish_reduction(*c, dev, 1, out_k);
       return;
     }
+    // multi-GPU, k = 1, peer-memory halo: the fused halo + SpMV kernel carries the dot product as well.  Opt-in
+    // (JP_FUSED_DOT=1) until it has been run on several GPUs; the conditions are those of apply_no_trans' fused path,
+    // and the peer-memory plan must already be active (the plain jp_apply sets it up collectively).
+    static const bool fused_dot_enabled = []() {
+      const char* v = std::getenv("JP_FUSED_DOT");
+      return v && *v == '1';
+    }();
+    if (fused_dot_enabled && mode == JP_NO_TRANS && alpha != 0.0 && y->k == 1 && p != nullptr && w != y && y->n == a->n_rows &&
+        x->n == p->n_src && p->n_tgt == a->n_cols && p->remote_is_tail && p->n_permute == 0 && p->num_same == a->n_local_cols &&
+        p->num_same == x->n && p->num_same + p->n_remote == a->n_cols && p->p2p_state == 1 && p->p2p_k == 1) {
+      FusedHalo h;
+      h.lids = p->export_lids.as<int32_t>();
+      h.n_export = p->n_export;
+      h.sends = p->send_table.as<P2PSend>();
+      h.n_sends = p->n_send_blocks;
+      h.sources = p->wait_table.as<P2PSource>();
+      h.n_sources = p->n_sources;
+      h.epoch = ++p->epoch;
+      h.tickets = p->p2p_tickets.as<unsigned int>();
+      h.timeout_flag = p2p_timeout_flag_device();
+      const double* halo = reinterpret_cast<const double*>(static_cast<const char*>(p->arena.p) + kArenaFlagBytes);
+      double* dev = launch_spmv_fused_dot(*a, h, x->d(), halo, y->d(), alpha, beta, w->d(), ctx().compute);
+      mv_finish_reduction(*c, dev, 1, out_k);
+      return;
+    }
     apply_impl(a, p, y, x, mode, alpha, beta);
     double* dev = mv_dot_local(*w, *y);  // stream-ordered after the apply: no host round trip in between
     mv_finish_reduction(*c, dev, y->k, out_k);

@@ -15,6 +15,8 @@ TOL = 1e-12
 
 
 def main():
+    if os.environ.get("JP_TEST_UNVALIDATED") == "1":
+        os.environ.setdefault("JP_FUSED_DOT", "1")  # apply_dot_ with k = 1 then takes spmv_fused_halo_dot_kernel (not yet run on GPUs)
     import torch.distributed as dist
     dist.init_process_group("gloo")
     import jpetra_b200 as jp
