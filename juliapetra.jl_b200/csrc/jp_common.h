@@ -199,6 +199,7 @@ struct Csr : Object {
   // aligned column runs of every block and the uint16 tile position of every nonzero
   int runs_state = 0;        // 0 = not built, 1 = active, -1 = not usable / disabled
   int32_t runs_wmax = 0, runs_cap = 0, runs_kt = 4, runs_threads = 128;
+  bool runs_db = false;      // JP_SPMM_RUNS_DB=1: double-buffered tiles (spmm_runs_db_kernel)
   DeviceBuffer runs, runs_lidx, runs_blocks_all, runs_blocks_interior;
   int32_t n_runs_blocks_all = 0, n_runs_blocks_interior = 0;
   // cache of the column-map multivector (A.importMV, src/CSRMatrix.jl:10,772-781); only used when the column

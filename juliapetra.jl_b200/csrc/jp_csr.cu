@@ -260,6 +260,7 @@ void build_runs(Csr& A) {
   A.runs_cap = cap;
   A.runs_kt = kt;
   A.runs_threads = threads;
+  A.runs_db = env_int("JP_SPMM_RUNS_DB", 0) != 0;
   A.runs_state = 1;
 }
 
@@ -271,6 +272,17 @@ void launch_spmm_runs_impl(const Csr& A, const BlockDesc* b, int32_t n_blocks, c
   set_smem_attr(spmm_runs_kernel<KT, THREADS>, smem);
   spmm_runs_kernel<KT, THREADS><<<n_blocks, THREADS, smem, stream>>>(b, A.rowptr.as<int32_t>(), A.vals.as<double>(), A.runs_lidx.as<uint16_t>(),
                                                                       A.runs.as<int2>(), x, ldx, y, ldy, k, A.runs_cap, wpad, alpha, beta);
+}
+
+template <int KT, int THREADS>
+void launch_spmm_runs_db_impl(const Csr& A, const BlockDesc* b, int32_t n_blocks, const double* x, int64_t ldx, double* y, int64_t ldy,
+                              int32_t k, double alpha, double beta, cudaStream_t stream) {
+  const int wpad = (A.runs_wmax + 1) & ~1;
+  const size_t smem = runs_db_smem_bytes(A.runs_cap, wpad, KT);
+  set_smem_attr(spmm_runs_db_kernel<KT, THREADS>, smem);
+  spmm_runs_db_kernel<KT, THREADS><<<n_blocks, THREADS, smem, stream>>>(b, A.rowptr.as<int32_t>(), A.vals.as<double>(),
+                                                                         A.runs_lidx.as<uint16_t>(), A.runs.as<int2>(), x, ldx, y, ldy, k,
+                                                                         A.runs_cap, wpad, alpha, beta);
 }
 
 template <bool HALO>
@@ -413,7 +425,15 @@ void launch_spmv_blocks(const Csr& A, const void* blocks_int4, int32_t n_blocks,
     const bool all = whole_all;
     const BlockDesc* rb = (all ? A.runs_blocks_all : A.runs_blocks_interior).as<BlockDesc>();
     const int32_t rn = all ? A.n_runs_blocks_all : A.n_runs_blocks_interior;
-    if (rn > 0) {
+    // double-buffered tiles (round-2 candidate, JP_SPMM_RUNS_DB=1): KT = 4 with 128 or 256 threads, when two tile
+    // buffers fit the shared memory
+    const bool db = A.runs_db && A.runs_kt == 4 && A.runs_threads != 64 && k > 4 &&
+                    runs_db_smem_bytes(A.runs_cap, (A.runs_wmax + 1) & ~1, 4) <= 220 * 1024;
+    if (rn > 0 && db) {
+      if (A.runs_threads == 256) launch_spmm_runs_db_impl<4, 256>(A, rb, rn, x, ldx, y, ldy, k, alpha, beta, stream);
+      else launch_spmm_runs_db_impl<4, 128>(A, rb, rn, x, ldx, y, ldy, k, alpha, beta, stream);
+      JP_LAUNCH_CHECK();
+    } else if (rn > 0) {
       if (A.runs_kt == 8 && A.runs_threads == 256) launch_spmm_runs_impl<8, 256>(A, rb, rn, x, ldx, y, ldy, k, alpha, beta, stream);
       else if (A.runs_kt == 8) launch_spmm_runs_impl<8, 128>(A, rb, rn, x, ldx, y, ldy, k, alpha, beta, stream);
       else if (A.runs_threads == 256) launch_spmm_runs_impl<4, 256>(A, rb, rn, x, ldx, y, ldy, k, alpha, beta, stream);

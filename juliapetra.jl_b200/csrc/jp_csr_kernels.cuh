@@ -794,6 +794,167 @@ spmm_runs_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// spmm_runs_kernel with the X tile DOUBLE-BUFFERED across the vector tiles of a block (round-2 candidate, opt-in with
+// JP_SPMM_RUNS_DB=1; written from the phase analysis in DESIGN.md 3.2b, not yet measured).  In spmm_runs_kernel every
+// (block, vector tile) phase pays the whole chain  run list from global -> TMA issue -> arrival -> barrier  before its
+// ~0.5 us of arithmetic.  Here
+//   * the run list and the tile bases are read ONCE per block and stay in registers (one run per lane of warp 0);
+//   * while the CTA computes vector tile t out of tile buffer t & 1, warp 0 has already issued the bulk copies of tile
+//     t + 1 into the other buffer (its own mbarrier), so from the second tile on a phase costs its arithmetic only;
+//   * the extra tile buffer takes the CTA from 73 KB to 110 KB: two CTAs per SM instead of three.
+// Blocks with more than 32 runs keep re-reading their run list (rare: a banded block has 3..18 runs).
+// ---------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t runs_db_smem_bytes(int cap, int wpad, int KT) {
+  return (size_t)(cap + 8) * 8 + 2 * (size_t)KT * wpad * 8 + (size_t)(kRunsMaxRows + 8) * 4 + (size_t)(cap + 16) * 2;
+}
+
+template <int KT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+spmm_runs_db_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ rowptr, const double* __restrict__ vals,
+                    const uint16_t* __restrict__ lidx, const int2* __restrict__ runs, const double* __restrict__ x, int64_t ldx,
+                    double* __restrict__ y, int64_t ldy, int32_t k, int32_t cap, int32_t wpad, double alpha, double beta) {
+  JP_DYN_SMEM(smem_raw);
+  __shared__ __align__(8) uint64_t s_bar[2];  // one per tile buffer; the first phase of s_bar[0] also covers the matrix stage
+  double* s_val = reinterpret_cast<double*>(smem_raw);                         // [cap + 8]
+  double* xs_base = s_val + cap + 8;                                            // [2][KT][wpad]
+  int32_t* s_rp = reinterpret_cast<int32_t*>(xs_base + 2 * KT * wpad);          // [kRunsMaxRows + 8]
+  uint16_t* s_lidx = reinterpret_cast<uint16_t*>(s_rp + kRunsMaxRows + 8);      // [cap + 16]
+  const BlockRange b = decode_block(blocks, blockIdx.x);
+  const int4 aux = __ldg(reinterpret_cast<const int4*>(blocks + blockIdx.x) + 1);
+  const int run0 = aux.x, nruns = aux.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ngrp = (b.p1 - b.a0 + 3) >> 2;
+  const int al0 = b.p0 & ~7;
+  const int nl8 = (b.p1 - al0 + 7) & ~7;
+  const int ra0 = b.row0 & ~3;
+  const int nrp = (b.row0 + b.nrows + 1 - ra0 + 3) & ~3;
+  const int ntiles = (k + KT - 1) / KT;
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+  }
+  __syncthreads();
+  // warp 0, lane q: run q of the block and its position in the tile (kept for every vector tile)
+  int2 my_run = make_int2(0, 0);
+  int my_base = 0;
+  if (warp == 0 && nruns <= 32) {
+    if (lane < nruns) my_run = __ldg(runs + run0 + lane);
+    const int stride = lane < nruns ? run_stride(my_run.y) : 0;
+    int incl = stride;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    my_base = incl - stride;
+  }
+  // issue the bulk copies of vector tile t into tile buffer t & 1 (warp 0 only; the barrier has been armed by lane 0)
+  auto issue_tile = [&](int t) {
+    const int v0 = t * KT;
+    const int kt = k - v0 < KT ? k - v0 : KT;
+    double* xs = xs_base + (size_t)(t & 1) * KT * wpad;
+    uint64_t* bar = &s_bar[t & 1];
+    const uint64_t pol_x = policy_evict_last();
+    if (nruns <= 32) {
+      if (my_run.y > 0) {
+        const double* src = x + (size_t)v0 * ldx + my_run.x;
+        double* dst = xs + my_base;
+        for (int j = 0; j < kt; ++j) {
+          bulk_g2s(dst, src, (unsigned)my_run.y * 8, bar, pol_x);
+          src += ldx;
+          dst += wpad;
+        }
+      }
+    } else {
+      int carry = 0;
+      for (int q0 = 0; q0 < nruns; q0 += 32) {  // warp-uniform
+        const int q = q0 + lane;
+        int2 run = make_int2(0, 0);
+        if (q < nruns) run = __ldg(runs + run0 + q);
+        const int stride = q < nruns ? run_stride(run.y) : 0;
+        int incl = stride;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int tt = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += tt;
+        }
+        const int base = carry + incl - stride;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+        if (run.y > 0) {
+          const double* src = x + (size_t)v0 * ldx + run.x;
+          double* dst = xs + base;
+          for (int j = 0; j < kt; ++j) {
+            bulk_g2s(dst, src, (unsigned)run.y * 8, bar, pol_x);
+            src += ldx;
+            dst += wpad;
+          }
+        }
+      }
+    }
+  };
+  const int kt0 = k < KT ? k : KT;
+  if (tid == 0) {  // matrix stage + first tile on s_bar[0]
+    const uint64_t pol = policy_evict_first();
+    mbar_expect_tx(&s_bar[0], (unsigned)(ngrp * 32 + nl8 * 2 + nrp * 4 + aux.w * 8 * kt0));
+    if (ngrp > 0) bulk_g2s(s_val, vals + b.a0, (unsigned)ngrp * 32, &s_bar[0], pol);
+    if (nl8 > 0) bulk_g2s(s_lidx, lidx + al0, (unsigned)nl8 * 2, &s_bar[0], pol);
+    bulk_g2s(s_rp, rowptr + ra0, (unsigned)nrp * 4, &s_bar[0], pol);
+  }
+  if (warp == 0) {
+    __syncwarp();  // s_bar[0] is armed before any lane's copy can complete on it
+    issue_tile(0);
+  }
+  int T = 1;
+  while (T < 4 && b.nrows * (T << 1) <= THREADS) T <<= 1;
+  const int lane_t = tid & (T - 1), group = tid / T, ngroups = THREADS / T;
+  const double* val0 = s_val - b.a0;
+  const uint16_t* lidx0 = s_lidx - al0;
+  for (int t = 0; t < ntiles; ++t) {
+    const int v0 = t * KT;
+    const int kt = k - v0 < KT ? k - v0 : KT;
+    if (warp == 0 && t + 1 < ntiles) {
+      // prefetch the next vector tile into the other buffer: every thread left it at the __syncthreads that ended
+      // phase t - 1
+      const int ktn = k - (v0 + KT) < KT ? k - (v0 + KT) : KT;
+      if (lane == 0) mbar_expect_tx(&s_bar[(t + 1) & 1], (unsigned)(aux.w * 8 * ktn));
+      __syncwarp();
+      issue_tile(t + 1);
+    }
+    mbar_wait(&s_bar[t & 1], (unsigned)((t >> 1) & 1));
+    const double* xs = xs_base + (size_t)(t & 1) * KT * wpad;
+    const int32_t* rp = s_rp + b.rpo;
+    for (int rbase = 0; rbase < b.nrows; rbase += ngroups) {  // warp-uniform trip count (shuffles below)
+      const int r = rbase + group;
+      const bool valid = r < b.nrows;
+      const int s = valid ? rp[r] : 0, e = valid ? rp[r + 1] : 0;
+      double acc[KT];
+#pragma unroll
+      for (int j = 0; j < KT; ++j) acc[j] = 0.0;
+#pragma unroll 2
+      for (int i = s + lane_t; i < e; i += T) {
+        const int li = lidx0[i];
+        const double v = val0[i];
+#pragma unroll
+        for (int j = 0; j < KT; ++j) acc[j] = fma(v, xs[j * wpad + li], acc[j]);
+      }
+      for (int o = T >> 1; o > 0; o >>= 1) {
+#pragma unroll
+        for (int j = 0; j < KT; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+      }
+      if (valid && lane_t == 0) {
+#pragma unroll
+        for (int j = 0; j < KT; ++j)
+          if (j < kt) {
+            double* yp = y + b.row0 + r + (size_t)(v0 + j) * ldy;
+            *yp = combine(beta == 0.0 ? 0.0 : *yp, acc[j], alpha, beta);
+          }
+      }
+    }
+    __syncthreads();  // tile buffer t & 1 is free for vector tile t + 2
+  }
+}
+
 // TRANS / CONJ_TRANS (src/CSRMatrix.jl:1147-1160): Y[ind, v] += (alpha * X[row, v]) * val, after Y *= beta.
 // Scatter with fp64 atomics (RED.ADD.F64): the summation order differs from the reference's row sweep, within
 // the 1e-12 contract.  Warp per row, lanes over the row's entries.

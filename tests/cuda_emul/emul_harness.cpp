@@ -132,13 +132,14 @@ int emul_local_apply(int32_t n_rows, int32_t n_cols, int32_t n_local_cols, const
     else if (use_halo) launch(spmv_kernel<true, 0>, spmm_kernel<KT, true, 0>);
     else if (tma) launch(spmv_kernel<false, 1>, spmm_kernel<KT, false, 1>);
     else launch(spmv_kernel<false, 0>, spmm_kernel<KT, false, 0>);
-  } else if (variant >= 3 && variant <= 6) {
+  } else if (variant >= 3 && variant <= 8) {
     // spmm_runs_kernel on its own block list: variant 3: KT = 4, 64 rows, 128 threads (two lanes per row); variant 4:
     // KT = 8, 128 rows, 256 threads; variant 5: KT = 4, 64 rows, 64 threads (one lane per row); variant 6: the default
-    // configuration, KT = 4, 128 rows, 128 threads (one lane per row)
+    // configuration, KT = 4, 128 rows, 128 threads (one lane per row); variants 7 / 8: spmm_runs_db_kernel (double-buffered
+    // tiles), KT = 4, 128 rows with 128 threads / 64 rows with 256 threads
     if (use_halo || (x_rows & 1)) return -3;
     std::vector<BlockDesc> ri, rb, ra;
-    build_blocks(rp, cls, cap, (variant == 4 || variant == 6) ? kRunsMaxRows : 64, allow_direct != 0, ri, rb, ra);
+    build_blocks(rp, cls, cap, (variant == 4 || variant == 6 || variant == 7) ? kRunsMaxRows : 64, allow_direct != 0, ri, rb, ra);
     const int kt = variant == 4 ? 8 : 4;
     const int max_tile_cols = (int)((110 * 1024 - (int64_t)runs_smem_bytes(cap, 0, kt)) / (8 * kt)) & ~1;
     std::vector<int32_t> ci(colind, colind + nnz);
@@ -155,7 +156,18 @@ int emul_local_apply(int32_t n_rows, int32_t n_cols, int32_t n_local_cols, const
       std::memcpy(d_lidx.p, t.lidx.data(), t.lidx.size() * 2);
       const int wpad = (t.wmax + 1) & ~1;
       const size_t sm = runs_smem_bytes(cap, wpad, kt);
-      if (variant == 5)
+      if (variant == 7 || variant == 8) {
+        const size_t smdb = runs_db_smem_bytes(cap, wpad, 4);
+        if (smdb > 220 * 1024) return -4;
+        if (variant == 7)
+          JP_KLAUNCH((spmm_runs_db_kernel<4, 128>), (unsigned)ra.size(), 128, smdb, nullptr, d_blocks.as<BlockDesc>(), d_rp.as<int32_t>(),
+                     d_va.as<double>(), d_lidx.as<uint16_t>(), d_ucols.as<int2>(), d_x.as<double>(), (int64_t)x_rows, d_y.as<double>(),
+                     (int64_t)n_rows, k, cap, wpad, alpha, beta);
+        else
+          JP_KLAUNCH((spmm_runs_db_kernel<4, 256>), (unsigned)ra.size(), 256, smdb, nullptr, d_blocks.as<BlockDesc>(), d_rp.as<int32_t>(),
+                     d_va.as<double>(), d_lidx.as<uint16_t>(), d_ucols.as<int2>(), d_x.as<double>(), (int64_t)x_rows, d_y.as<double>(),
+                     (int64_t)n_rows, k, cap, wpad, alpha, beta);
+      } else if (variant == 5)
         JP_KLAUNCH((spmm_runs_kernel<4, 64>), (unsigned)ra.size(), 64, sm, nullptr, d_blocks.as<BlockDesc>(), d_rp.as<int32_t>(),
                    d_va.as<double>(), d_lidx.as<uint16_t>(), d_ucols.as<int2>(), d_x.as<double>(), (int64_t)x_rows, d_y.as<double>(),
                    (int64_t)n_rows, k, cap, wpad, alpha, beta);

@@ -65,8 +65,9 @@ def test_spmv_with_halo_buffer():
     assert (np.abs(got - ref) <= _bound(rp, ci, va, x, y0, 3.0, 0.5)).all()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])  # gather, tile, pipelined tile, runs (KT=4 T=2; KT=8 256 thr; KT=4 T=1; default)
-@pytest.mark.parametrize("k", [2, 8, 11])
+# gather, tile, pipelined tile, runs (KT=4 T=2; KT=8 256 thr; KT=4 T=1; default), double-buffered runs (128 / 256 threads)
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("k", [2, 8, 11, 32])
 def test_spmm_kernels(variant, k):
     rp, ci, va = _problem("27pt", 6)
     n = len(rp) - 1
@@ -97,7 +98,27 @@ def test_spmm_runs_kernel_other_stencils(kind, N):
     rp, ci, va = _problem(kind, N)
     n = len(rp) - 1
     x, y0 = _vectors(n, n, 5)
-    for variant, cap in ((3, 2048), (4, 256), (5, 2048), (6, 3456)):
+    for variant, cap in ((3, 2048), (4, 256), (5, 2048), (6, 3456), (7, 3456), (8, 2048)):
         got, st = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, variant=variant, cap=cap)
         ref = _oracle(rp, ci, va, x, y0, 3.0, 0.5)
         assert (np.abs(got - ref) <= _bound(rp, ci, va, x, y0, 3.0, 0.5)).all()
+
+
+def test_spmm_runs_kernels_with_more_than_32_runs_per_block():
+    """40 far-apart double diagonals: every row block references 40 separate column runs, so the tile copy walks the
+    run list in two passes of 32 lanes (and the double-buffered kernel re-reads it per vector tile)"""
+    n, ndiag = 16000, 40
+    rows = np.arange(n)
+    offs = (np.arange(ndiag) - ndiag // 2) * 391
+    cols = (rows[:, None, None] + offs[None, :, None] + np.arange(2)[None, None, :]).reshape(n, -1)
+    ok = (cols >= 0) & (cols < n)
+    rp = np.zeros(n + 1, dtype=np.int32)
+    np.cumsum(ok.sum(axis=1), out=rp[1:])
+    ci = cols[ok].astype(np.int32)
+    rng = np.random.default_rng(2)
+    va = rng.standard_normal(len(ci))
+    x, y0 = _vectors(n, n, 6)
+    ref = _oracle(rp, ci, va, x, y0, 3.0, 0.5)
+    for variant in (6, 7):
+        got, st = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, variant=variant, cap=3456)
+        assert got is not None and (np.abs(got - ref) <= _bound(rp, ci, va, x, y0, 3.0, 0.5)).all()

@@ -475,6 +475,24 @@ def test_spmm_run_staged_path(monkeypatch, kind, N, k, kt, rows_threads):
     assert info["runs_state"] == 1 and info["runs_blocks"] > 0, info  # the run-staged kernel really ran
 
 
+@pytest.mark.skipif(__import__("os").environ.get("JP_TEST_UNVALIDATED") != "1",
+                    reason="spmm_runs_db_kernel has not been run on a GPU yet (set JP_TEST_UNVALIDATED=1)")
+@pytest.mark.parametrize("rows_threads", [("128", "128"), ("64", "256")])
+@pytest.mark.parametrize("kind,N,k", [("27pt", 20, 8), ("27pt", 20, 11), ("27pt", 12, 32)])
+def test_spmm_double_buffered_tiles(monkeypatch, kind, N, k, rows_threads):
+    """round-2 candidate (JP_SPMM_RUNS_DB=1): the X tile of the run-staged kernel double-buffered across vector tiles"""
+    monkeypatch.setenv("JP_SPMM_RUNS_DB", "1")
+    monkeypatch.setenv("JP_SPMM_RUNS_ROWS", rows_threads[0])
+    monkeypatch.setenv("JP_SPMM_RUNS_THREADS", rows_threads[1])
+    c, m, A = serial_matrix(kind, N)
+    n = m.numMyElements()
+    x = synthetic.vector_block(1, n, k, seed=1)
+    y0 = synthetic.vector_block(1, n, k, seed=2)
+    check_apply(A, x, y0, 3.0, 0.5, exact=False)
+    check_apply(A, x, y0, 1.0, 0.0, exact=False)
+    assert A.spmm_info()["runs_state"] == 1
+
+
 def test_full_size_7pt_256_properties_and_oracle():
     """BASELINE configs[1] at full size on one GPU: size-independent properties, then the whole vector against the
     oracle (bit-exact: every block of a stencil is thread-per-row in the reference's summation order)."""

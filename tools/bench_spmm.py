@@ -28,6 +28,9 @@ VARIANTS = [
     # one lane per row (conflict-free shared reads for odd row lengths, no shuffles)
     ("runs_kt4_rows128_t128", {"JP_SPMM_RUNS": "1", "JP_SPMM_RUNS_KT": "4", "JP_SPMM_RUNS_ROWS": "128", "JP_SPMM_RUNS_CAP": "3456"}),
     ("runs_kt4_rows64_t64", {"JP_SPMM_RUNS": "1", "JP_SPMM_RUNS_KT": "4", "JP_SPMM_RUNS_THREADS": "64"}),
+    # round-2 candidates: X tile double-buffered across the vector tiles of a block (spmm_runs_db_kernel)
+    ("runs_db", {"JP_SPMM_RUNS_DB": "1"}),
+    ("runs_db_rows64_t256", {"JP_SPMM_RUNS_DB": "1", "JP_SPMM_RUNS_ROWS": "64", "JP_SPMM_RUNS_THREADS": "256", "JP_SPMM_RUNS_CAP": "2048"}),
 ]
 
 
@@ -73,7 +76,7 @@ def main():
     for label, env in ([("default_direct", {})] if args.direct else VARIANTS):
         if not args.direct and keep and label not in keep:
             continue
-        for key in ("JP_SPMM_RUNS", "JP_SPMM_RUNS_KT", "JP_SPMM_RUNS_CAP", "JP_SPMM_RUNS_THREADS", "JP_SPMM_RUNS_ROWS", "JP_SPMM_TILE"):
+        for key in ("JP_SPMM_RUNS", "JP_SPMM_RUNS_KT", "JP_SPMM_RUNS_CAP", "JP_SPMM_RUNS_THREADS", "JP_SPMM_RUNS_ROWS", "JP_SPMM_RUNS_DB", "JP_SPMM_TILE"):
             os.environ.pop(key, None)
         os.environ.update(env)
         h = C.c_int64(A.h if args.direct else 0)
