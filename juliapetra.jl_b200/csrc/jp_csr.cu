@@ -418,7 +418,10 @@ void launch_spmv_blocks(const Csr& A, const void* blocks_int4, int32_t n_blocks,
   // the run-staged kernel serves launches over the WHOLE all-blocks or interior list (it has its own block lists with a
   // different geometry; a chunk of a list, as jp_apply_host launches, stays with the gather kernel)
   const bool whole_all = blocks_int4 == A.blocks_all.p && n_blocks == A.n_blocks_all;
-  const bool whole_interior = blocks_int4 == A.blocks_interior.p && n_blocks == A.n_blocks_interior;
+  // (interior-only launches are the multi-GPU two-stream path: the run-staged kernel has not been run there yet, so it
+  // is opt-in with JP_SPMM_RUNS_INTERIOR=1 and the validated gather kernel stays the default)
+  static const bool runs_interior = env_int("JP_SPMM_RUNS_INTERIOR", 0) != 0;
+  const bool whole_interior = runs_interior && blocks_int4 == A.blocks_interior.p && n_blocks == A.n_blocks_interior;
   if (k > 1 && A.runs_state == 1 && !use_halo && (ldx & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
       (whole_all || whole_interior)) {
     // banded matrix, no halo columns in this launch
