@@ -9,8 +9,6 @@ of the scalars differs (within the 1e-12 contract).
 """
 from __future__ import annotations
 
-import numpy as np
-
 from .multivector import DenseMultiVector
 
 

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import fill_cases
-from helpers import O, jp, synthetic
+from helpers import jp, synthetic
 
 pytestmark = pytest.mark.gpu
 
