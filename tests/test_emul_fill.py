@@ -33,7 +33,7 @@ def test_random_small_matrices_against_the_host_mirror():
     from hypothesis import given, settings, strategies as st
     from jpetra_b200.csrmatrix import CSRMatrix
 
-    @settings(max_examples=60, deadline=None)
+    @settings(max_examples=int(__import__("os").environ.get("JP_HYPOTHESIS_EXAMPLES", "60")), deadline=None, derandomize=True)
     @given(st.integers(0, 2 ** 31), st.integers(1, 40), st.integers(0, 12), st.integers(1, 60))
     def run(seed, n_rows, max_len, n_global):
         rng = np.random.default_rng(seed)
