@@ -122,3 +122,77 @@ def test_spmm_runs_kernels_with_more_than_32_runs_per_block():
     for variant in (6, 7):
         got, st = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, variant=variant, cap=3456)
         assert got is not None and (np.abs(got - ref) <= _bound(rp, ci, va, x, y0, 3.0, 0.5)).all()
+
+
+def test_random_csr_structures_every_block_kind():
+    """property test: random row-length profiles (empty rows, rows exactly as long as the stage, rows longer than it),
+    random stage sizes / rows per block, with and without the halo split, TMA and cp.async staging, k = 1 and k > 1 --
+    the gather kernels against the oracle"""
+    import os
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=int(os.environ.get("JP_HYPOTHESIS_EXAMPLES", "40")), deadline=None, derandomize=True)
+    @given(st.integers(0, 2 ** 31), st.integers(1, 400), st.sampled_from([256, 512, 2048]), st.sampled_from([1, 7, 32, 256]),
+           st.sampled_from([1, 3]), st.booleans(), st.booleans(), st.sampled_from([1, 2, 8, 32]))
+    def run(seed, n_rows, cap, max_rows, k, tma, halo, T):
+        rng = np.random.default_rng(seed)
+        n_cols = int(rng.integers(1, 600))
+        profile = rng.integers(0, 4)
+        if profile == 0:
+            lens = rng.integers(0, 9, size=n_rows)
+        elif profile == 1:
+            lens = rng.integers(0, 70, size=n_rows)
+        elif profile == 2:
+            lens = np.where(rng.random(n_rows) < 0.03, rng.integers(cap - 2, cap + 40, size=n_rows), rng.integers(0, 12, size=n_rows))
+        else:
+            lens = np.where(rng.random(n_rows) < 0.1, cap, rng.integers(0, 40, size=n_rows))
+        rp = np.zeros(n_rows + 1, dtype=np.int32)
+        np.cumsum(lens, out=rp[1:])
+        ci = rng.integers(0, n_cols, size=int(rp[-1])).astype(np.int32)
+        va = rng.standard_normal(len(ci))
+        x = rng.standard_normal((n_cols, k))
+        y0 = rng.standard_normal((n_rows, k))
+        alpha, beta = (3.0, 0.5) if seed % 3 else (1.0, 0.0)
+        nloc = int(rng.integers(0, n_cols + 1)) if halo else None
+        got, stats = emul.local_apply(rp, ci, va, x, y0, alpha, beta, n_local_cols=nloc, halo_split=halo, cap=cap, max_rows=max_rows, T=T,
+                                      tma=int(tma), allow_direct=int(seed % 2))
+        ref = _oracle(rp, ci, va, x, y0, alpha, beta)
+        assert (np.abs(got - ref) <= _bound(rp, ci, va, x, y0, alpha, beta)).all(), (stats, np.abs(got - ref).max())
+
+    run()
+
+
+def test_random_banded_structures_run_staged_kernels():
+    """property test: random banded matrices (random band width, fill density, row count; empty rows; several bands) through
+    the run-staged SpMM kernels (default configuration and the double-buffered variant); structures the run-table
+    builder turns away (not banded enough) must be turned away, never mis-computed"""
+    import os
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=int(os.environ.get("JP_HYPOTHESIS_EXAMPLES", "30")), deadline=None, derandomize=True)
+    @given(st.integers(0, 2 ** 31), st.integers(1, 300), st.integers(1, 12), st.sampled_from([2, 5, 9]), st.sampled_from([6, 7, 3, 8]))
+    def run(seed, half_rows, width, k, variant):
+        rng = np.random.default_rng(seed)
+        n = 2 * half_rows  # even: X's columns stay 16-byte aligned
+        nbands = int(rng.integers(1, 4))
+        centers = np.concatenate([[0], rng.integers(-n, n, size=nbands - 1)])
+        density = rng.uniform(0.5, 1.0)
+        rows_cols = []
+        for r in range(n):
+            cols = np.concatenate([np.arange(r + c - width, r + c + width + 1) for c in centers])
+            cols = np.unique(cols[(cols >= 0) & (cols < n)])
+            keep = rng.random(len(cols)) < density
+            rows_cols.append(cols[keep] if r % 17 else cols[:0])  # every 17th row is empty
+        rp = np.zeros(n + 1, dtype=np.int32)
+        np.cumsum([len(c) for c in rows_cols], out=rp[1:])
+        ci = np.concatenate(rows_cols + [np.zeros(0, dtype=np.int64)]).astype(np.int32)
+        va = rng.standard_normal(len(ci))
+        x = rng.standard_normal((n, k))
+        y0 = rng.standard_normal((n, k))
+        got, stats = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, variant=variant, cap=3456 if variant in (6, 7) else 2048)
+        if got is None:
+            return
+        ref = _oracle(rp, ci, va, x, y0, 3.0, 0.5)
+        assert (np.abs(got - ref) <= _bound(rp, ci, va, x, y0, 3.0, 0.5)).all(), (variant, np.abs(got - ref).max())
+
+    run()
