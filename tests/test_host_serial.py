@@ -190,6 +190,13 @@ def test_no_cpu_fallback():
         pytest.skip("GPU present")
     with pytest.raises(jp.BackendError):
         jp.DenseMultiVector(jp.BlockMap(4, jp.SerialComm()), 1)
+    m = jp.BlockMap(4, jp.SerialComm())
+    A = jp.CSRMatrix(m, 1, jp.STATIC_PROFILE)
+    for g in range(1, 5):
+        A.insertGlobalValues(g, [g], [1.0])
+    with pytest.raises(jp.BackendError):
+        A.fillComplete(device=True)  # the device fillComplete does not quietly take the host path either
+    assert A.isFillActive()
 
 
 # ---- committed golden fixtures (tests/golden/fixtures.json, generated from the oracle by make_fixtures.py) ----------
