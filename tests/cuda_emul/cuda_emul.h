@@ -8,7 +8,8 @@
 // runs until it reaches a block barrier or a warp collective, where it yields; a barrier releases when every live
 // thread of the block (warp) has arrived, exactly the CUDA rule, and a round in which no fiber can make progress is
 // reported as a deadlock (divergent __syncthreads / missing lane in a *_sync collective).  Scheduling is round-robin
-// and deterministic: this checks logic, not memory-model races.  Asynchronous copies (cp.async, TMA bulk copies)
+// and deterministic, in forward, reverse or (seeded) random thread order (JP_EMUL_SCHEDULE): order-dependent results
+// expose missing synchronisation, but this is not a memory-model checker.  Asynchronous copies (cp.async, TMA bulk copies)
 // complete at issue; mbarrier waits therefore pass.
 #pragma once
 #include <ucontext.h>
@@ -155,9 +156,50 @@ inline unsigned ballot(bool pred) {
   return bits;
 }
 
+// The order in which the runnable fibers of a block get their turn in one scheduling round.  JP_EMUL_SCHEDULE =
+// "forward" (default), "reverse", or "random[:seed]" (a fresh permutation every round): a kernel whose result depends
+// on the order -- a missing __syncthreads between a shared-memory write and its read, a buffer reused before every
+// reader is done -- gives different answers under different schedules, which the tests run under all three.
+inline int& schedule_mode() {
+  static int mode = -1;  // -1: read JP_EMUL_SCHEDULE at first use
+  return mode;
+}
+inline uint64_t& schedule_rng() {
+  static uint64_t rng = 0x9E3779B97F4A7C15ull;
+  return rng;
+}
+inline void schedule_order(std::vector<int>& order, int nthreads) {
+  int& mode = schedule_mode();
+  uint64_t& rng = schedule_rng();
+  if (mode < 0) {
+    const char* v = std::getenv("JP_EMUL_SCHEDULE");
+    mode = 0;
+    if (v && std::strncmp(v, "reverse", 7) == 0) mode = 1;
+    if (v && std::strncmp(v, "random", 6) == 0) {
+      mode = 2;
+      if (v[6] == ':') rng ^= std::strtoull(v + 7, nullptr, 10) * 0xBF58476D1CE4E5B9ull;
+    }
+  }
+  if ((int)order.size() != nthreads) {
+    order.resize(nthreads);
+    for (int i = 0; i < nthreads; ++i) order[i] = mode == 1 ? nthreads - 1 - i : i;
+  }
+  if (mode == 2) {
+    for (int i = nthreads - 1; i > 0; --i) {  // Fisher-Yates with splitmix64
+      rng += 0x9E3779B97F4A7C15ull;
+      uint64_t z = rng;
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+      z ^= z >> 31;
+      std::swap(order[i], order[(int)(z % (uint64_t)(i + 1))]);
+    }
+  }
+}
+
 // run one grid: body() is the kernel call with its arguments bound
 inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body) {
   State& s = state();
+  std::vector<int> order;
   if (s.cur != -1) {
     std::fprintf(stderr, "cuda_emul: nested launch\n");
     std::abort();
@@ -206,7 +248,9 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function
         while (remaining > 0) {
           const uint64_t before = s.progress;
           remaining = 0;
-          for (int t = 0; t < nthreads; ++t) {
+          schedule_order(order, nthreads);
+          for (int oi = 0; oi < nthreads; ++oi) {
+            const int t = order[oi];
             if (s.fibers[t].done) continue;
             s.cur = t;
             s.threadIdx = uint3{(unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y)};

@@ -28,6 +28,27 @@ extern "C" {
 const char* emul_last_error() { return g_error.c_str(); }
 uint64_t emul_launch_count() { return emul::state().launches; }
 void emul_set_sm_count(int n) { jp::ctx().sm_count = n; }
+// 0 forward, 1 reverse, 2 random (seeded): the order in which a block's runnable threads get their turn
+void emul_set_schedule(int mode, uint64_t seed) {
+  emul::schedule_mode() = mode;
+  emul::schedule_rng() = 0x9E3779B97F4A7C15ull ^ (seed * 0xBF58476D1CE4E5B9ull);
+}
+
+// self-test of the model: out[t] = value written by thread t+1 into (dynamic, garbage-initialised) shared memory, with or
+// without the barrier that makes it well defined
+static void neighbour_kernel(int* out, int with_barrier) {
+  JP_DYN_SMEM(smem_raw);
+  int* s_v = reinterpret_cast<int*>(smem_raw);
+  const int t = threadIdx.x, n = blockDim.x;
+  s_v[t] = 1000 + t;
+  if (with_barrier) __syncthreads();
+  out[t] = s_v[(t + 1) % n];
+}
+int emul_selftest_neighbour(int* out, int nthreads, int with_barrier) {
+  int* p = out;
+  emul::launch(dim3(1), dim3(nthreads), (size_t)nthreads * 4, [&] { neighbour_kernel(p, with_barrier); });
+  return 0;
+}
 
 // ---- fillComplete ----
 int emul_fill_complete(int32_t n_rows, const int64_t* ptr, const int64_t* gids, const double* vals, int64_t gmin, int64_t gmax,

@@ -177,3 +177,14 @@ def spmv_trans(rowptr0, colind0, vals, x, y, alpha=1.0, blocks=2):
                                C.c_double(alpha), C.c_int32(blocks))
     assert rc == 0
     return yy
+
+
+def set_schedule(mode: str = "forward", seed: int = 0):
+    """order in which a block's runnable threads get their turn: forward | reverse | random (seeded)"""
+    lib().emul_set_schedule(C.c_int({"forward": 0, "reverse": 1, "random": 2}[mode]), C.c_uint64(seed))
+
+
+def selftest_neighbour(nthreads: int, with_barrier: bool):
+    out = np.full(nthreads, -1, dtype=np.int32)
+    lib().emul_selftest_neighbour(_p(out), C.c_int(nthreads), C.c_int(int(with_barrier)))
+    return out
