@@ -196,3 +196,21 @@ def test_random_banded_structures_run_staged_kernels():
         assert (np.abs(got - ref) <= _bound(rp, ci, va, x, y0, 3.0, 0.5)).all(), (variant, np.abs(got - ref).max())
 
     run()
+
+
+def test_reference_golden_2x2_through_the_kernels():
+    """test/CSRMatrixTests.jl:120-174: A = [[2,3],[5,7]], X = 2s (2 vectors): A*X == [10 10; 24 24], and the 1-D
+    Laplacian-like rows of test/CSRMatrixMPITests.jl:29-63 on one rank (alpha = 3, beta = 0.5, Y0 = diag(1, 2))"""
+    rp, ci, va = np.array([0, 2, 4]), np.array([0, 1, 0, 1]), np.array([2.0, 3.0, 5.0, 7.0])
+    x = np.full((2, 2), 2.0)
+    for variant in (0,):
+        got, _ = emul.local_apply(rp, ci, va, x, np.zeros((2, 2)), 1.0, 0.0, variant=variant)
+        assert np.array_equal(got, np.array([[10.0, 10.0], [24.0, 24.0]]))
+    got, _ = emul.local_apply(rp, ci, va, x[:, :1], np.zeros((2, 1)), 1.0, 0.0)
+    assert np.array_equal(got, np.array([[10.0], [24.0]]))
+    # rank 1 of the 4-rank golden case: rows {1: [2, -1], 2: [-1, 2, -1]} on the column map [1, 2, 3]
+    rp, ci, va = np.array([0, 2, 5]), np.array([0, 1, 0, 1, 2]), np.array([2.0, -1.0, -1.0, 2.0, -1.0])
+    xcol = np.full((3, 2), 2.0)
+    y0 = np.diag([1.0, 2.0])
+    got, _ = emul.local_apply(rp, ci, va, xcol, y0, 3.0, 0.5, n_local_cols=2, halo_split=True)
+    assert np.array_equal(got, 0.5 * y0 + np.array([[6.0, 6.0], [0.0, 0.0]]))  # test/CSRMatrixMPITests.jl:52-63
