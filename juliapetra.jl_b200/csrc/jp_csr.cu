@@ -316,7 +316,8 @@ void launch_spmv_fused(const Csr& A, const FusedHalo& h, const double* x, const 
   a.boundary = A.blocks_boundary.as<BlockDesc>();
   a.n_interior = A.n_blocks_interior;
   a.n_boundary = A.n_blocks_boundary;
-  a.n_pack = std::max(1, std::min(64, (h.n_export + 1023) / 1024));
+  static const int pack_rows = std::max(64, env_int("JP_FUSED_PACK_ROWS", 1024));  // exported rows per pack CTA
+  a.n_pack = std::max(1, std::min(64, (h.n_export + pack_rows - 1) / pack_rows));
   a.rowptr = A.rowptr.as<int32_t>();
   a.colind = A.colind.as<int32_t>();
   a.vals = A.vals.as<double>();
@@ -377,7 +378,8 @@ double* launch_spmv_fused_dot(Csr& A, const FusedHalo& h, const double* x, const
   a.boundary = A.blocks_boundary.as<BlockDesc>();
   a.n_interior = A.n_blocks_interior;
   a.n_boundary = A.n_blocks_boundary;
-  a.n_pack = std::max(1, std::min(64, (h.n_export + 1023) / 1024));
+  static const int pack_rows = std::max(64, env_int("JP_FUSED_PACK_ROWS", 1024));  // exported rows per pack CTA
+  a.n_pack = std::max(1, std::min(64, (h.n_export + pack_rows - 1) / pack_rows));
   a.rowptr = A.rowptr.as<int32_t>();
   a.colind = A.colind.as<int32_t>();
   a.vals = A.vals.as<double>();
@@ -516,7 +518,12 @@ void csr_finalize_structure(Csr& A, const std::vector<int32_t>& rp, const std::v
   int max_rows = env_int("JP_SPMV_ROWS", kSpmvThreads);
   JP_REQUIRE(max_rows >= 1 && max_rows <= kMaxRowsPerBlock, "JP_SPMV_ROWS must be in [1,512]");
   std::vector<BlockDesc>&bi = A.h_blocks_interior, &bb = A.h_blocks_boundary, &ba = A.h_blocks_all;
-  build_blocks(rp, cls, cap, max_rows, env_int("JP_SPMV_DIRECT", 1) != 0, bi, bb, ba);
+  DirectRule rule;
+  rule.maxlen = env_int("JP_SPMV_DIRECT_MAXLEN", rule.maxlen);
+  if (const char* v = std::getenv("JP_SPMV_DIRECT_RATIO"))
+    if (*v) rule.ratio = std::atof(v);
+  JP_REQUIRE(rule.maxlen >= 1 && rule.ratio >= 1.0, "JP_SPMV_DIRECT_MAXLEN must be >= 1 and JP_SPMV_DIRECT_RATIO >= 1");
+  build_blocks(rp, cls, cap, max_rows, env_int("JP_SPMV_DIRECT", 1) != 0, bi, bb, ba, rule);
   upload_blocks(bi, A.blocks_interior, A.n_blocks_interior);
   upload_blocks(bb, A.blocks_boundary, A.n_blocks_boundary);
   upload_blocks(ba, A.blocks_all, A.n_blocks_all);

@@ -14,8 +14,17 @@ namespace csrk {
 inline size_t stage_smem_bytes(int cap) { return (size_t)(cap + 8) * 12 + (size_t)(kMaxRowsPerBlock + 8) * 4; }
 
 // cut rows into blocks; cls[r] = 1 when the row touches a remote column
+// Which blocks go thread-per-row straight from the stage (KIND_DIRECT): longest row <= direct_maxlen and
+// longest row <= direct_ratio * mean row length of the block.  32 and 2 are what round 1 measured on stencils; both are
+// tuning knobs (JP_SPMV_DIRECT_MAXLEN, JP_SPMV_DIRECT_RATIO) because irregular short-row blocks may be better off
+// without the shared-memory round trip of the two-phase path even at some lane divergence.
+struct DirectRule {
+  int32_t maxlen = 32;
+  double ratio = 2.0;
+};
+
 inline void build_blocks(const std::vector<int32_t>& rp, const std::vector<uint8_t>& cls, int32_t cap, int32_t max_rows, bool allow_direct,
-                  std::vector<BlockDesc>& interior, std::vector<BlockDesc>& boundary, std::vector<BlockDesc>& all) {
+                  std::vector<BlockDesc>& interior, std::vector<BlockDesc>& boundary, std::vector<BlockDesc>& all, const DirectRule& rule = DirectRule()) {
   const int32_t n = (int32_t)rp.size() - 1;
   int32_t r = 0;
   while (r < n) {
@@ -33,7 +42,7 @@ inline void build_blocks(const std::vector<int32_t>& rp, const std::vector<uint8
       }
       const int64_t nrows = r - start, nnzb = rp[r] - nnz0;
       // near-uniform short rows: max <= 2 * mean  ->  thread-per-row straight from the stage
-      if (allow_direct && maxlen <= 32 && (int64_t)maxlen * nrows <= 2 * nnzb + 32) kind = KIND_DIRECT;
+      if (allow_direct && maxlen <= rule.maxlen && (double)maxlen * (double)nrows <= rule.ratio * (double)nnzb + 32.0) kind = KIND_DIRECT;
       else kind = maxlen > kLongRowLen ? KIND_WARPROW : KIND_TWOPHASE;
     }
     BlockDesc b;
