@@ -134,6 +134,27 @@ int32_t jp_mv_norm2(jp_handle comm, jp_handle x, double* out_k);               /
 int32_t jp_mv_normp(jp_handle comm, jp_handle x, double p, double* out_k);     /* norm(.,p), :135-144 */
 int32_t jp_mv_comm_reduce(jp_handle comm, jp_handle mv);                       /* commReduce, :154-161 */
 
+/* ---- device-resident scalars for solver loops (no reference counterpart: the reference returns every dot / norm to
+ *      the host, src/MultiVector.jl:84-146, which costs two host synchronisations per CG iteration).  A `scalars` object
+ *      is a small device array; the *_dev calls leave their (all-reduced) result in one of its slots and take update
+ *      coefficients as  scale * s[num] / s[den]  (num / den = -1: factor 1), evaluated on the device.  Single vectors
+ *      (k = 1).  Everything is stream-ordered; only jp_scalars_download synchronises. ------------------------------- */
+int32_t jp_scalars_create(int32_t n, jp_handle* out);                       /* n doubles, zeroed */
+int32_t jp_scalars_destroy(jp_handle s);
+int32_t jp_scalars_upload(jp_handle s, const double* host);
+int32_t jp_scalars_download(jp_handle s, double* host);
+int32_t jp_scalars_copy(jp_handle s, int32_t dst, int32_t src);            /* s[dst] = s[src] */
+int32_t jp_mv_dot_dev(jp_handle comm, jp_handle x, jp_handle y, jp_handle s, int32_t slot);   /* s[slot] = dot(x, y) */
+/* y = a*x + b*y with a = a_scale * s[a_num] / s[a_den], b likewise (the arithmetic of jp_mv_axpby) */
+int32_t jp_mv_axpby_dev(jp_handle y, jp_handle x, jp_handle s, double a_scale, int32_t a_num, int32_t a_den, double b_scale,
+                        int32_t b_num, int32_t b_den);
+/* the same update and s[out_slot] = sum of squares of the result (norm(y, 2)^2, all-reduced) in one pass */
+int32_t jp_mv_axpby_norm2sq_dev(jp_handle comm, jp_handle y, jp_handle x, jp_handle s, double a_scale, int32_t a_num, int32_t a_den,
+                                double b_scale, int32_t b_num, int32_t b_den, int32_t out_slot);
+/* apply!(Y, A, X, NO_TRANS, alpha, beta) and s[slot] = dot(W, Y) (jp_apply_dot without the host round trip) */
+int32_t jp_apply_dot_dev(jp_handle comm, jp_handle Y, jp_handle A, jp_handle X, jp_handle plan, double alpha, double beta,
+                         jp_handle W, jp_handle s, int32_t slot);
+
 /* ---- Import / Export plan + its Distributor plan on the device
  *      (src/ImportExportData.jl:1-16; src/MPIDistributor.jl:12-65).  export_lids must be
  *      in send order (grouped by procs_to; compose with indices_to on the host when the

@@ -11,7 +11,7 @@ The directory name contains a dot, so it is imported through the `jpetra_b200` s
 """
 from . import _lib
 from .blockmap import BasicDirectory, BlockMap
-from .cg import cg
+from .cg import Scalars, cg, cg_device
 from .comm import Comm, NCCLComm, SerialComm, TorchDistComm
 from .csrmatrix import (CONJ_TRANS, NO_TRANS, STATIC_PROFILE, TRANS, CSRMatrix, TransposeMode, apply_, isTransposed)
 from .distributor import Distributor, SerialDistributor
@@ -24,5 +24,5 @@ __all__ = [
     "Comm", "SerialComm", "NCCLComm", "TorchDistComm", "BlockMap", "BasicDirectory", "Distributor", "SerialDistributor",
     "Import", "Export", "ImportExportData", "DenseMultiVector", "CSRMatrix", "TransposeMode", "CombineMode", "NO_TRANS", "TRANS",
     "CONJ_TRANS", "ADD", "INSERT", "REPLACE", "ABSMAX", "ZERO", "STATIC_PROFILE", "apply_", "dot", "norm", "doImport", "doExport",
-    "computeOffsets", "isTransposed", "cg", "InvalidArgumentError", "InvalidStateError", "BackendError",
+    "computeOffsets", "isTransposed", "cg", "cg_device", "Scalars", "InvalidArgumentError", "InvalidStateError", "BackendError",
 ]

@@ -73,6 +73,15 @@ PROTOTYPES = {
     "jp_mv_norm2": [c_i64, c_i64, c_vp],
     "jp_mv_normp": [c_i64, c_i64, c_f64, c_vp],
     "jp_mv_comm_reduce": [c_i64, c_i64],
+    "jp_scalars_create": [c_i32, P(c_i64)],
+    "jp_scalars_destroy": [c_i64],
+    "jp_scalars_upload": [c_i64, c_vp],
+    "jp_scalars_download": [c_i64, c_vp],
+    "jp_scalars_copy": [c_i64, c_i32, c_i32],
+    "jp_mv_dot_dev": [c_i64, c_i64, c_i64, c_i64, c_i32],
+    "jp_mv_axpby_dev": [c_i64, c_i64, c_i64, c_f64, c_i32, c_i32, c_f64, c_i32, c_i32],
+    "jp_mv_axpby_norm2sq_dev": [c_i64, c_i64, c_i64, c_i64, c_f64, c_i32, c_i32, c_f64, c_i32, c_i32, c_i32],
+    "jp_apply_dot_dev": [c_i64, c_i64, c_i64, c_i64, c_i64, c_f64, c_f64, c_i64, c_i64, c_i32],
     "jp_plan_create": [c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp,
                        c_i32, c_i32, P(c_i64)],
     "jp_plan_destroy": [c_i64],

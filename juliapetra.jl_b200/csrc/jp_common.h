@@ -99,7 +99,7 @@ inline void count_launch(int n = 1) { ctx().launches.fetch_add(n, std::memory_or
   } while (0)
 
 // ---- handle registry ------------------------------------------------------------------------
-enum class Kind : int { Comm = 1, Csr, MultiVector, Plan, Event };
+enum class Kind : int { Comm = 1, Csr, MultiVector, Plan, Event, Scalars };
 
 struct Object {
   Kind kind;

@@ -7,6 +7,7 @@
 #include "../../juliapetra.jl_b200/csrc/jp_fill_pipeline.h"
 #include "../../juliapetra.jl_b200/csrc/jp_mv_kernels.cuh"
 #include "../../juliapetra.jl_b200/csrc/jp_plan_kernels.cuh"
+#include "../../juliapetra.jl_b200/csrc/jp_solver_kernels.cuh"
 
 namespace {
 std::string g_error;
@@ -425,6 +426,38 @@ int emul_spmv_trans(int32_t n_rows, int32_t n_cols, const int32_t* rowptr, const
     JP_KLAUNCH(spmv_trans_kernel, (unsigned)blocks, kSpmvThreads, 0, nullptr, d_rp.as<int32_t>(), d_ci.as<int32_t>(), d_va.as<double>(),
                d_x.as<double>(), (int64_t)n_rows, d_y.as<double>(), (int64_t)n_cols, n_rows, k, alpha);
   std::memcpy(y, d_y.p, (size_t)n_cols * k * 8);
+  return 0;
+}
+
+
+// ---- update kernels with device-resident coefficients (csrc/jp_solver_kernels.cuh) ----
+// y = a*x + b*y with a = a_scale * s[a_num] / s[a_den] (b likewise); with_norm: also s[out_slot] = sum of squares of the
+// result.  `repeats` launches on one workspace.  y (n doubles) and s (ns doubles) are updated in place.
+int emul_axpby_dev(double* y, const double* x, int64_t n, double* s, int32_t ns, double a_scale, int32_t a_num, int32_t a_den, double b_scale,
+                   int32_t b_num, int32_t b_den, int32_t with_norm, int32_t out_slot, int32_t blocks, int32_t repeats) {
+  using namespace jp;
+  using namespace jp::solk;
+  DeviceBuffer d_y, d_x, d_s, ws;
+  d_y.alloc((size_t)n * 8 + 64);
+  d_x.alloc((size_t)n * 8 + 64);
+  d_s.alloc((size_t)ns * 8);
+  ws.alloc((size_t)(blocks + 2) * 8);
+  std::memcpy(d_y.p, y, (size_t)n * 8);
+  std::memcpy(d_x.p, x, (size_t)n * 8);
+  std::memcpy(d_s.p, s, (size_t)ns * 8);
+  std::memset(ws.p, 0, ws.bytes);
+  Coeff ca{a_scale, a_num, a_den}, cb{b_scale, b_num, b_den};
+  double* partials = ws.as<double>();
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(partials + blocks);
+  for (int rep = 0; rep < repeats; ++rep) {
+    if (with_norm)
+      JP_KLAUNCH(axpby_norm2_dev_kernel, (unsigned)blocks, kThreads, 0, nullptr, d_y.as<double>(), d_x.as<double>(), n, ca, cb, d_s.as<double>(),
+                 partials, ticket, d_s.as<double>() + out_slot);
+    else
+      JP_KLAUNCH(axpby_dev_kernel, (unsigned)blocks, kThreads, 0, nullptr, d_y.as<double>(), d_x.as<double>(), n, ca, cb, d_s.as<double>());
+  }
+  std::memcpy(y, d_y.p, (size_t)n * 8);
+  std::memcpy(s, d_s.p, (size_t)ns * 8);
   return 0;
 }
 

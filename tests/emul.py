@@ -188,3 +188,16 @@ def selftest_neighbour(nthreads: int, with_barrier: bool):
     out = np.full(nthreads, -1, dtype=np.int32)
     lib().emul_selftest_neighbour(_p(out), C.c_int(nthreads), C.c_int(int(with_barrier)))
     return out
+
+
+def axpby_dev(y, x, s, a, b, with_norm=False, out_slot=0, blocks=3, repeats=1):
+    """axpby_dev_kernel / axpby_norm2_dev_kernel: a, b = (scale, num_slot, den_slot) with -1 for "no slot".
+    Returns (y_new, s_new)."""
+    yy = np.ascontiguousarray(np.array(y, dtype=np.float64).ravel()).copy()
+    xx = np.ascontiguousarray(np.asarray(x, dtype=np.float64).ravel())
+    ss = np.ascontiguousarray(np.array(s, dtype=np.float64).ravel()).copy()
+    rc = lib().emul_axpby_dev(_p(yy), _p(xx), C.c_int64(len(yy)), _p(ss), C.c_int32(len(ss)), C.c_double(a[0]), C.c_int32(a[1]), C.c_int32(a[2]),
+                              C.c_double(b[0]), C.c_int32(b[1]), C.c_int32(b[2]), C.c_int32(int(with_norm)), C.c_int32(out_slot),
+                              C.c_int32(blocks), C.c_int32(repeats))
+    assert rc == 0
+    return yy, ss

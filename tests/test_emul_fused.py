@@ -54,3 +54,25 @@ def test_axpby_norm2(n, k, blocks):
     for rep, yr in enumerate((y1, y2)):
         ref = O.norm_raw(yr, 2.0)
         assert (np.abs(sums[rep] - ref) <= 1e-12 * ref).all()
+
+
+@pytest.mark.parametrize("n,blocks", [(1, 1), (1000, 2), (4099, 5)])
+def test_update_kernels_with_device_resident_coefficients(n, blocks):
+    """jp_solver_kernels.cuh: the coefficient scale * s[num] / s[den] is formed on the device; the update is the
+    unfused (a*x) + (b*y) of the host-scalar kernel, bit for bit"""
+    x = synthetic.vector_block(1, n, 1, seed=1).ravel()
+    y0 = synthetic.vector_block(1, n, 1, seed=2).ravel()
+    s = np.array([3.7, -0.9, 123.0, 0.25])
+    # CG's  x += (rr / pAp) p :  a = s[0] / s[1], b = 1
+    y, s1 = emul.axpby_dev(y0, x, s, (1.0, 0, 1), (1.0, -1, -1), blocks=blocks)
+    assert np.array_equal(y, (s[0] / s[1]) * x + 1.0 * y0) and np.array_equal(s1, s)
+    # CG's  r -= (rr / pAp) Ap  with ||r||^2 into slot 2
+    y, s2 = emul.axpby_dev(y0, x, s, (-1.0, 0, 1), (1.0, -1, -1), with_norm=True, out_slot=2, blocks=blocks, repeats=1)
+    r = (-1.0 * s[0] / s[1]) * x + 1.0 * y0
+    assert np.array_equal(y, r)
+    ref = O.norm_raw(r.reshape(-1, 1), 2.0)[0]
+    assert abs(s2[2] - ref) <= 1e-12 * ref and np.array_equal(s2[[0, 1, 3]], s[[0, 1, 3]])
+    # CG's  p = r + (rr_new / rr) p :  a = 1, b = s[2] / s[0]; twice on the same workspace
+    y, s3 = emul.axpby_dev(y0, x, s, (1.0, -1, -1), (1.0, 2, 0), blocks=blocks, repeats=2)
+    b = s[2] / s[0]
+    assert np.array_equal(y, 1.0 * x + b * (1.0 * x + b * y0))

@@ -80,3 +80,33 @@ def test_cg_fused_and_unfused_solve_the_laplacian():
         assert err <= 1e-9, err
         results.append((its, X.data))
     assert abs(results[0][0] - results[1][0]) <= 1
+
+
+@pytest.mark.skipif(__import__("os").environ.get("JP_TEST_UNVALIDATED") != "1",
+                    reason="the device-resident-scalar solver calls have not been run on a GPU yet (set JP_TEST_UNVALIDATED=1)")
+def test_cg_with_device_resident_scalars():
+    """jp_*_dev: CG without host round trips inside the iteration against the host-scalar CG and the known solution"""
+    m, n, A = _serial_problem("7pt", 16)
+    xs = synthetic.vector_block(1, n, 1, seed=7)
+    B = A.apply(jp.DenseMultiVector(m, xs))
+    X1, X2 = jp.DenseMultiVector(m, 1), jp.DenseMultiVector(m, 1)
+    its1, rel1 = jp.cg(A, B, X1, tol=1e-12, maxiter=500, fused=True)
+    its2, rel2 = jp.cg_device(A, B, X2, tol=1e-12, maxiter=500, check_every=5)
+    assert rel2 <= 1e-12 and its1 <= its2 <= its1 + 6
+    assert np.abs(X2.data - xs).max() <= 1e-9 and np.abs(X2.data - X1.data).max() <= 1e-9
+    # the building blocks one by one
+    s = jp.Scalars(4)
+    s.upload([3.0, -2.0, 0.0, 0.5])
+    x = synthetic.vector_block(1, n, 1, seed=1)
+    y0 = synthetic.vector_block(1, n, 1, seed=2)
+    Xv, Yv = jp.DenseMultiVector(m, x), jp.DenseMultiVector(m, y0)
+    lib = jp._lib.lib()
+    jp._lib.check(lib.jp_mv_axpby_norm2sq_dev(jp.SerialComm().handle, Yv.h, Xv.h, s.h, -1.0, 0, 1, 1.0, -1, -1, 2))
+    r = (-1.0 * 3.0 / -2.0) * x + 1.0 * y0
+    assert np.array_equal(Yv.data, r)
+    v = s.download()
+    ref = O.norm_raw(r, 2.0)[0]
+    assert abs(v[2] - ref) <= 1e-12 * ref and v[0] == 3.0 and v[3] == 0.5
+    jp._lib.check(lib.jp_mv_dot_dev(jp.SerialComm().handle, Xv.h, Yv.h, s.h, 3))
+    d = s.download()[3]
+    assert abs(d - O.dot_raw(x, r)[0]) <= 1e-12 * O.dot_raw(np.abs(x), np.abs(r))[0]

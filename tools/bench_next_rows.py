@@ -71,6 +71,20 @@ def main():
         bytes_it = nnz * 12 + (n + 1) * 4 + n * 8 * (11 if fused else 14)
         cg["fused" if fused else "separate"] = {"iterations": its, "ms_per_iteration": per_it, "rel_residual": rel,
                                                 "algorithmic_gbs": bytes_it / per_it / 1e6}
+    try:  # device-resident scalars: no host round trip inside the iteration (jp_*_dev; round-2 candidate)
+        X = jp.DenseMultiVector(m, 1)
+        jp.cg_device(Ah, B, X, tol=0.0, maxiter=5, check_every=5)
+        X = jp.DenseMultiVector(m, 1)
+        lib.jp_synchronize()
+        _lib.check(lib.jp_event_record(e0.value))
+        its, rel = jp.cg_device(Ah, B, X, tol=0.0, maxiter=args.iters, check_every=args.iters)
+        _lib.check(lib.jp_event_record(e1.value))
+        ms = C.c_double()
+        _lib.check(lib.jp_event_elapsed_ms(e0.value, e1.value, C.byref(ms)))
+        cg["device_scalars"] = {"iterations": its, "ms_per_iteration": ms.value / its, "rel_residual": rel,
+                                "algorithmic_gbs": (nnz * 12 + (n + 1) * 4 + n * 8 * 11) / (ms.value / its) / 1e6}
+    except Exception as e:  # noqa: BLE001 -- keep the other measurements
+        cg["device_scalars"] = {"error": str(e)}
     out["cg"] = cg
 
     # ---- the building blocks one by one (ms per call, device events; dot/norm include their host synchronisation) ----

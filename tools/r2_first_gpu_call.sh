@@ -8,7 +8,7 @@
 # Everything lands in gpurun_out/r2_first_*; budget ~6 GPU-minutes.
 set -u
 mkdir -p gpurun_out
-JP_TEST_UNVALIDATED=1 timeout 120 python -m pytest tests/test_gpu_exporter.py tests/test_gpu_parity.py tests/test_c_abi_from_c.py -k 'exporter or double_buffered or c_program' -q > gpurun_out/r2_first_pytest_exporter.log 2>&1; echo "rc=$?" >> gpurun_out/r2_first_pytest_exporter.log
+JP_TEST_UNVALIDATED=1 timeout 120 python -m pytest tests/test_gpu_exporter.py tests/test_gpu_parity.py tests/test_c_abi_from_c.py tests/test_gpu_fused.py -k 'exporter or double_buffered or c_program or device_resident' -q > gpurun_out/r2_first_pytest_exporter.log 2>&1; echo "rc=$?" >> gpurun_out/r2_first_pytest_exporter.log
 timeout 200 python -m pytest tests -m gpu -q > gpurun_out/r2_first_pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/r2_first_pytest_gpu.log
 timeout 120 python tools/bench_spmm.py --N 192 --ks 8,32 --reps 10 --variants gather,default,runs_kt4_t256,runs_db,runs_db_rows64_t256 > gpurun_out/r2_first_spmm192.json 2> gpurun_out/r2_first_spmm192.err
 timeout 90 python tools/bench_next_rows.py --N 256 --iters 50 > gpurun_out/r2_first_next_rows_256.json 2> gpurun_out/r2_first_next_rows_256.err
