@@ -1,8 +1,11 @@
 // emul_runtime.h -- the slice of csrc/jp_common.h and of the CUDA runtime API that the host pipelines
-// (csrc/*_pipeline.h) use, backed by malloc/memcpy, for the CPU execution model of cuda_emul.h.
-// TEST INFRASTRUCTURE ONLY.  "Device" buffers carry guard zones that are checked on release, and fresh allocations
-// are filled with garbage like cudaMalloc'ed memory.
+// (csrc/*_pipeline.h) use, backed by mmap/memcpy, for the CPU execution model of cuda_emul.h.
+// TEST INFRASTRUCTURE ONLY.  "Device" buffers end at an inaccessible page and carry a canary in front; fresh
+// allocations are filled with garbage like cudaMalloc'ed memory.
 #pragma once
+#include <sys/mman.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -65,6 +68,8 @@ inline Context& ctx() {
 constexpr size_t kGuard = 256;
 constexpr unsigned char kGuardByte = 0xA7;
 
+// "Device" memory: every buffer ends (up to 16-byte alignment) at a PROT_NONE page, so an access past the end of an
+// allocation faults on the spot -- reads included -- and a canary in front of it catches stray writes before the start.
 struct DeviceBuffer {
   void* p = nullptr;
   size_t bytes = 0;
@@ -72,42 +77,61 @@ struct DeviceBuffer {
   DeviceBuffer(const DeviceBuffer&) = delete;
   DeviceBuffer& operator=(const DeviceBuffer&) = delete;
   ~DeviceBuffer() { release(); }
+  static size_t page() { return (size_t)sysconf(_SC_PAGESIZE); }
   void alloc(size_t n) {
     release();
     if (n == 0) n = 16;
-    unsigned char* raw = (unsigned char*)std::malloc(n + 2 * kGuard);
-    std::memset(raw, kGuardByte, kGuard);
-    std::memset(raw + kGuard, 0xCD, n);
-    std::memset(raw + kGuard + n, kGuardByte, kGuard);
-    p = raw + kGuard;
+    const size_t pg = page();
+    const size_t padded = (n + 15) & ~(size_t)15;                       // keeps the start 16-byte aligned
+    const size_t body = (kGuard + padded + pg - 1) / pg * pg;           // pages holding [canary | buffer]
+    unsigned char* raw = (unsigned char*)mmap(nullptr, body + pg, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (raw == (unsigned char*)MAP_FAILED) {
+      std::fprintf(stderr, "cuda_emul: mmap of %zu bytes failed\n", body + pg);
+      std::abort();
+    }
+    mprotect(raw + body, pg, PROT_NONE);                                 // the page right behind the buffer
+    unsigned char* start = raw + body - padded;
+    std::memset(start - kGuard, kGuardByte, kGuard);
+    std::memset(start, 0xCD, padded);                                    // cudaMalloc'ed memory is not zero
+    p = start;
     bytes = n;
+    map_base = raw;
+    map_bytes = body + pg;
   }
   void ensure(size_t n) {
     if (n > bytes) alloc(n);
   }
   void check_guards() const {
     if (!p) return;
-    const unsigned char* raw = (const unsigned char*)p - kGuard;
+    const unsigned char* g = (const unsigned char*)p - kGuard;
     for (size_t i = 0; i < kGuard; ++i)
-      if (raw[i] != kGuardByte || raw[kGuard + bytes + i] != kGuardByte) {
-        std::fprintf(stderr, "cuda_emul: out-of-bounds write next to a %zu-byte device buffer\n", bytes);
+      if (g[i] != kGuardByte) {
+        std::fprintf(stderr, "cuda_emul: out-of-bounds write in front of a %zu-byte device buffer\n", bytes);
         std::abort();
       }
   }
   void release() {
     if (p) {
       check_guards();
-      std::free((unsigned char*)p - kGuard);
+      munmap(map_base, map_bytes);
     }
     p = nullptr;
     bytes = 0;
+    map_base = nullptr;
+    map_bytes = 0;
   }
   void swap(DeviceBuffer& o) {
     std::swap(p, o.p);
     std::swap(bytes, o.bytes);
+    std::swap(map_base, o.map_base);
+    std::swap(map_bytes, o.map_bytes);
   }
   template <class T>
   T* as() const { return static_cast<T*>(p); }
+
+ private:
+  void* map_base = nullptr;
+  size_t map_bytes = 0;
 };
 
 }  // namespace jp
