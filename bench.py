@@ -10,10 +10,19 @@ partitioned by BlockMap(N^3, comm) (strong scaling), halo exchange included.  Ra
   e2e    : same metric through the host-buffer entry point jp_apply_host (pinned host X -> H2D -> kernels -> D2H Y)
   roofline: algorithmic bytes of one apply / measured duration vs the measured HBM copy peak (MEASURED_PEAKS.json)
   cpu_baseline: the oracle's literal restatement of localApply on ONE host core, same matrix (rank 0, N=1 only)
+  parity : after the timed loop every rank hashes ITS slab of Y and compares it with the committed digest of the CPU
+           oracle's simulation of the reference on the same rank count (tests/golden/bench_parity.json), checks dot / norm
+           (NCCL allreduce), the transposed apply, commReduce and the Comm collectives; any mismatch exits non-zero
+Timed window: W warm-up steps, barrier, a few untimed ALIGNING steps (the ranks enter the window paced by the halo
+handshake itself and the host's launch queue is ahead of the device), event, EXACTLY K steps, event; nothing else -- no
+fork, no host synchronisation -- happens between the barrier and the second event.  A second pass of K steps with one
+event pair per step gives the median / max step (diagnostics, not the reported value).
 Other workloads (parity/profiling cases, not the bench line): --workload 5pt-1000 | 27pt-192 --k 8|32 | powerlaw --rows R
 """
 import argparse
 import ctypes as C
+import datetime
+import hashlib
 import json
 import os
 import statistics
@@ -46,6 +55,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--fused", action="store_true", help="cg workloads: apply! + dot through the fused jp_apply_dot call")
+    ap.add_argument("--device-scalars", action="store_true", help="cg workloads: dot / norm results stay on the device (jp_*_dev): no host sync per iteration")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--ref-ranks", type=int, default=0, help="--impl reference: simulated MPI ranks (default: host cores, max 32)")
     return ap.parse_args()
 
@@ -87,7 +98,10 @@ def ncu_traffic(workload):
 
 
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """nvidia-smi sampling every 50 ms in a child process.  Started BEFORE the first barrier (a fork of a process with GBs
+    of device mappings takes milliseconds: it must never sit between a barrier and the timed window); samples are
+    time-stamped so that only those taken while the kernels ran are reported."""
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
@@ -97,7 +111,8 @@ class ClockSampler:
         except Exception:
             self.p = None
 
-    def stop(self):
+    def stop(self, windows):
+        """windows: [(t0, t1)] wall-clock intervals (time.time()) during which the measured kernels were running"""
         if self.p is None:
             return None
         self.p.terminate()
@@ -111,11 +126,14 @@ class ClockSampler:
         sm, mx, reasons = [], [], set()
         for r in rows:
             try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
+                t = datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if not any(t0 - 0.05 <= t <= t1 + 0.05 for t0, t1 in windows):
+                    continue
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
             except Exception:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                 if v.strip().lower().startswith("active"):
                     reasons.add(name)
         if not sm:
@@ -123,23 +141,34 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bench_config(spec, nnz, k, n_gpus):
+    """the `config` object of the JSON line: identical in the product arm and the reference arm"""
+    per_gpu = algorithmic_bytes(spec["n"], nnz, k) / n_gpus
+    flush = per_gpu < 1.5 * 126e6
+    return {"workload": spec["name"], "n": spec["n"], "nnz": nnz, "k": k, "alpha": 1.0, "beta": 0.0,
+            "parallelism": f"rows/{n_gpus} (BlockMap)",
+            "l2": (f"L2 flushed (256 MB memset) between timed iterations, each iteration on its own event pair; {per_gpu / 1e6:.0f} MB per GPU per apply"
+                   if flush else f"inputs larger than L2: {per_gpu / 1e6:.0f} MB streamed per GPU per apply vs 126 MB L2; no flush needed")}
+
+
 def run_reference(args, spec):
     """--impl reference: the reference's CPU algorithm (oracle port: the Julia sources cannot run here) as P simulated MPI
-    ranks on P host threads, one rank per core like `mpiexec -n P`, halo through the restated Import plan."""
+    ranks on P host threads, one rank per core like `mpiexec -n P`, halo through the restated Import plan.  Honours
+    --steps / --warmup; P = all host cores (at most 32) whatever --gpus says, which is generous to the CPU arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle as O
     from oracle.problems import oracle_problem
+    from jpetra_b200 import synthetic
     cores = os.cpu_count() or 1
     P = args.ref_ranks or min(cores, 32)
     t0 = time.time()
     c, m, A = oracle_problem(spec["kind"], spec["N"], P)
-    nnz = sum(len(A.csr(p)[2]) for p in range(1, P + 1)) if spec["n"] <= 1 << 22 else None
-    if nnz is None:
-        from jpetra_b200 import synthetic
-        nnz = synthetic.stencil_nnz(spec["kind"], spec["N"]) if spec["kind"] != "powerlaw" else sum(len(A.csr(p)[2]) for p in range(1, P + 1))
-    from jpetra_b200 import synthetic
+    if spec["kind"] != "powerlaw":
+        nnz = synthetic.stencil_nnz(spec["kind"], spec["N"])
+    else:
+        nnz = sum(len(A.csr(p)[2]) for p in range(1, P + 1))
     xs = []
     for pid in range(1, P + 1):
         info = m.info(pid)
@@ -147,20 +176,77 @@ def run_reference(args, spec):
     X = O.OMV.from_arrays(m, xs)
     Y = O.OMV(m, args.k)
     setup_s = time.time() - t0
-    iters = max(1, min(args.steps, 5))
-    secs = A.time_apply(Y, X, 1.0, 0.0, iters=iters, warmup=min(args.warmup, 1))
+    iters, warm = max(1, args.steps), max(0, args.warmup)
+    secs = A.time_apply(Y, X, 1.0, 0.0, iters=iters, warmup=warm)
     val = 2.0 * nnz * args.k / secs / 1e9
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": iters, "warmup": min(args.warmup, 1),
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": iters, "warmup": warm,
         "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": spec["name"], "n": spec["n"], "nnz": nnz, "k": args.k, "alpha": 1.0, "beta": 0.0},
+        "config": bench_config(spec, nnz, args.k, args.gpus),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": P, "kind": "port",
-                         "sample": f"{iters} full apply! on the whole matrix, {P} simulated MPI ranks on {P} threads of {cores} host cores; "
-                                   f"oracle setup {setup_s:.0f}s not timed"},
+                         "sample": f"{iters} full apply! on the whole matrix ({warm} warm-up), {P} simulated MPI ranks on {P} threads of {cores} host cores "
+                                   f"(all host cores, at most 32, at every --gpus); oracle setup {setup_s:.0f}s not timed"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "hbm_gbs": algorithmic_bytes(spec["n"], nnz, args.k) / secs / 1e9,
     }
     print(json.dumps(line), flush=True)
+
+
+def sha256_of(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def parity_checks(jp, comm, A, X, Y, x_host, spec, k, world, rank, e2e_y):
+    """Run on every rank after the timed loop; returns (ok, report).  Everything here goes through the same C-ABI entry
+    points as the timed loop: Y is what the LAST timed apply left on the device."""
+    rep = {}
+    ok = True
+    fx = None
+    try:
+        fx = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_parity.json")))["cases"].get(f"{spec['kind']}-{spec['N']}/P{world}")
+    except Exception:
+        fx = None
+    y = Y.data
+    pid, P = comm.myPid(), comm.numProc()
+    if fx is not None and k == 1 and not spec.get("cg"):
+        mine = sha256_of(y) == fx["y_sha256"][rank]
+        rep["y_bit_exact_ranks"] = int(comm.sumAll([1 if mine else 0])[0])
+        ok &= rep["y_bit_exact_ranks"] == P
+        if e2e_y is not None:
+            rep["e2e_y_bit_exact_ranks"] = int(comm.sumAll([1 if sha256_of(e2e_y) == fx["y_sha256"][rank] else 0])[0])
+            ok &= rep["e2e_y_bit_exact_ranks"] == P
+        d = float(X.dot(Y)[0, 0])
+        nr = float(Y.norm(2)[0, 0])
+        rep["dot_rel_err"] = abs(d - fx["dot_x_y"]) / abs(fx["dot_x_y"])
+        rep["norm2_rel_err"] = abs(nr - fx["norm2_y"]) / fx["norm2_y"]
+        rep["tolerance"] = 1e-12
+        ok &= rep["dot_rel_err"] <= 1e-12 and rep["norm2_rel_err"] <= 1e-12
+    if spec["kind"] in ("5pt", "7pt", "27pt") and not spec.get("cg"):
+        # A is symmetric: the transposed apply (scatter + reverse-mode halo exchange with ADD) must reproduce A*X within the
+        # reduction-order tolerance, component-wise: |Yt - Y|_i <= 1e-12 * max(|Y_i|, diag*|x_i|) <= 1e-12 * (|A||x|)_i
+        Yt = jp.DenseMultiVector(Y.getMap(), k)
+        A.apply_(Yt, X, jp.TRANS, 1.0, 0.0)
+        diag = float(jp.synthetic.STENCILS[spec["kind"]][1])
+        bound = 1e-12 * np.maximum(np.abs(y), diag * np.abs(x_host))
+        bad = int(comm.sumAll([int((np.abs(Yt.data - y) > bound).sum())])[0])
+        rep["trans_symmetric_violations"] = bad
+        ok &= bad == 0
+    # commReduce on a replicated map (test/DenseMultiVectorTests.jl:96-99) and the Comm collectives (test/MPICommTests.jl:13-36)
+    rep_map = jp.BlockMap(6, 6, comm)
+    v = jp.DenseMultiVector(rep_map, (2.0 ** pid) * np.ones((6, 2)))
+    v.commReduce()
+    coll = np.array_equal(v.data, float(sum(2 ** i for i in range(1, P + 1))) * np.ones((6, 2)))
+    everyone = list(range(1, P + 1))
+    coll &= comm.gatherAll([pid, 2 * pid]).tolist() == [x for q in everyone for x in (q, 2 * q)]
+    coll &= comm.sumAll([pid, 3]).tolist() == [P * (P + 1) // 2, 3 * P] and comm.maxAll([pid]).tolist() == [P] and comm.minAll([pid]).tolist() == [1]
+    coll &= comm.scanSum([pid]).tolist() == [pid * (pid + 1) // 2] and comm.broadcastAll([pid, 7], P).tolist() == [P, 7]
+    rep["collectives_ok_ranks"] = int(comm.sumAll([1 if coll else 0])[0])
+    ok &= rep["collectives_ok_ranks"] == P
+    rep["checked"] = True
+    rep["bit_exact"] = bool(rep.get("y_bit_exact_ranks") == P) if "y_bit_exact_ranks" in rep else None
+    rep["ok"] = bool(ok)
+    rep["oracle"] = "tests/golden/bench_parity.json (CPU oracle's P-rank simulation of the reference)" if fx is not None else None
+    return bool(ok), rep
 
 
 def main():
@@ -185,6 +271,9 @@ def main():
         comm = jp.NCCLComm.fromTorchDistributed()
     else:
         comm = jp.SerialComm()
+    # the only fork of this process: long before any timed window
+    sampler = ClockSampler(local) if rank == 0 else None
+    windows = []
 
     def barrier():
         lib.jp_synchronize()
@@ -228,8 +317,16 @@ def main():
         R = jp.DenseMultiVector(row_map, synthetic.vector_block(row_map.minMyGID(), n_my, k, seed=2))
         XS = jp.DenseMultiVector(row_map, k)
         args.no_e2e = True
+        if args.device_scalars:
+            S = jp.Scalars(2)  # [0] p'Ap, [1] |r|^2 -- never downloaded inside the loop
 
     def step():
+        if cg and args.device_scalars:
+            # the same operations with every scalar left on the device: no host synchronisation inside the iteration
+            _lib.check(lib.jp_apply_dot_dev(comm.handle, Y.h, A.h, X.h, plan, 1.0, 0.0, X.h, S.h, 0))  # Ap = A p; s[0] = p'Ap (allreduce on the stream)
+            _lib.check(lib.jp_mv_dot_dev(comm.handle, R.h, R.h, S.h, 1))                                # s[1] = |r|^2
+            _lib.check(lib.jp_mv_axpby_dev(XS.h, X.h, S.h, 1e-3, 1, 0, 1.0, -1, -1))                    # x += (1e-3 * s[1] / s[0]) p
+            return
         if cg and args.fused:
             pAp = A.apply_dot_(Y, X)  # jp_apply_dot: no host round trip between apply! and dot
         else:
@@ -240,69 +337,93 @@ def main():
             R.norm(2)
             XS.axpby_(1e-3 / (abs(pAp[0, 0]) + 1.0), X, 1.0)
 
-    ev0, ev1 = C.c_int64(), C.c_int64()
-    _lib.check(lib.jp_event_create(C.byref(ev0)))
-    _lib.check(lib.jp_event_create(C.byref(ev1)))
+    def new_event():
+        e = C.c_int64()
+        _lib.check(lib.jp_event_create(C.byref(e)))
+        return e.value
+
+    def elapsed(e0, e1):
+        ms = C.c_double()
+        _lib.check(lib.jp_event_elapsed_ms(e0, e1, C.byref(ms)))  # synchronises on e1
+        return ms.value
+
+    ev0, ev1 = new_event(), new_event()
+    step_events = [new_event() for _ in range(args.steps + 1)]
     cnt0, cnt1 = C.c_int64(), C.c_int64()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    lib.jp_launch_count(C.byref(cnt0))
     # L2 rule: either the per-GPU working set of one apply is well above the 126 MB L2 (no flush), or a 256 MB
     # scratch buffer is written between timed iterations and every iteration is timed on its own event pair
     bytes_rank_est = algorithmic_bytes(n_my, nnz_my, k)
-    flush = bytes_rank_est < 1.5 * 126e6
-    ms = C.c_double()
+    flush = algorithmic_bytes(n, nnz, k) / world < 1.5 * 126e6
+    warmup = max(args.warmup, 3)
+    _lib.check(lib.jp_event_record(ev0))
+    for _ in range(warmup):
+        step()
+    _lib.check(lib.jp_event_record(ev1))
+    est_ms = max(elapsed(ev0, ev1) / warmup, 1e-3)
+    # aligning steps: ~20 ms of the same step (at least 10, at most 512 = well inside the launch queue), so the clocks are
+    # up, every rank is paced by its neighbours' halo flags, and the host runs ahead of the device when the window opens
+    align = 0 if flush else int(min(512, max(10, 20.0 / est_ms)))
+    barrier()
+    t_load0 = time.time()
+    lib.jp_launch_count(C.byref(cnt0))
     host_enqueue_ms = None
     if not flush:
-        _lib.check(lib.jp_event_record(ev0.value))
+        for _ in range(align):
+            step()
+        lib.jp_launch_count(C.byref(cnt0))
+        _lib.check(lib.jp_event_record(ev0))
         t_h = time.perf_counter()
         for _ in range(args.steps):
             step()
         host_enqueue_ms = (time.perf_counter() - t_h) * 1e3 / args.steps  # CPU time to enqueue one step (no sync inside)
-        _lib.check(lib.jp_event_record(ev1.value))
-        _lib.check(lib.jp_event_elapsed_ms(ev0.value, ev1.value, C.byref(ms)))
-        total_ms = ms.value
+        _lib.check(lib.jp_event_record(ev1))
+        total_ms = elapsed(ev0, ev1)
     else:
         total_ms = 0.0
         for _ in range(args.steps):
             _lib.check(lib.jp_flush_l2(256 << 20))
-            _lib.check(lib.jp_event_record(ev0.value))
+            _lib.check(lib.jp_event_record(ev0))
             step()
-            _lib.check(lib.jp_event_record(ev1.value))
-            _lib.check(lib.jp_event_elapsed_ms(ev0.value, ev1.value, C.byref(ms)))
-            total_ms += ms.value
-    ms.value = total_ms
+            _lib.check(lib.jp_event_record(ev1))
+            total_ms += elapsed(ev0, ev1)
     lib.jp_launch_count(C.byref(cnt1))
     barrier()
-    clocks = sampler.stop() if sampler else None
-    elapsed_ms = max_over_ranks(ms.value)
+    windows.append((t_load0, time.time()))
+    elapsed_ms = max_over_ranks(total_ms)
     ms_per_step = elapsed_ms / args.steps
-    clocks_window = "timed region"
-    if rank == 0 and (clocks is None or clocks.get("samples", 0) < 5):
-        # the timed region was too short for nvidia-smi's sampling period: sample the same kernel loop for ~1.5 s
-        sampler = ClockSampler(local)
-        t_end = time.time() + 1.5
-    else:
-        t_end = 0
-    if world > 1:
-        import torch
-        flag = torch.tensor([1.0 if t_end else 0.0], device="cuda")
-        dist.broadcast(flag, 0)
-        loop = bool(flag.item())
-    else:
-        loop = bool(t_end)
-    if loop:
-        reps = max(1, int(1.5e3 / max(ms_per_step, 1e-3)))
-        for _ in range(reps):
-            step()
-        barrier()
-        if rank == 0:
-            clocks = sampler.stop()
-            clocks_window = "same apply! loop repeated for ~1.5 s right after the timed region (timed region shorter than the sampling period)"
     launches = int(sum_over_ranks(float(cnt1.value - cnt0.value)))
+
+    # ---- diagnostics: the same K steps again, one event per step (not the reported value) ----
+    per_step = None
+    if not flush:
+        for _ in range(min(align, 32)):
+            step()
+        _lib.check(lib.jp_event_record(step_events[0]))
+        for i in range(args.steps):
+            step()
+            _lib.check(lib.jp_event_record(step_events[i + 1]))
+        ts = [elapsed(step_events[i], step_events[i + 1]) for i in range(args.steps)]
+        slow = int(np.argmax(ts))
+        per_step = {"median_ms": max_over_ranks(statistics.median(ts)), "max_ms": max_over_ranks(max(ts)), "slowest_step_rank0": slow,
+                    "total_ms": max_over_ranks(sum(ts)), "note": "second pass, one event pair per step (the events add launch gaps); diagnostics only"}
+        barrier()
+
+    # ---- clocks: the timed region is usually shorter than nvidia-smi's sampling period, so the same loop is repeated for
+    #      ~1 s right behind it and the samples of both windows are reported ----
+    clocks_window = "timed region"
+    if elapsed_ms < 500.0:
+        reps = max(1, int(1.0e3 / max(ms_per_step, 1e-3)))
+        t_w = time.time()
+        for i in range(reps):
+            step()
+            if i % 256 == 255:
+                lib.jp_synchronize()
+        barrier()
+        windows.append((t_w, time.time()))
+        clocks_window = "timed region + the same apply! loop repeated for ~1 s right after it (timed region shorter than the sampling period)"
+    clocks = sampler.stop(windows) if sampler else None
+
     # pure CPU cost of enqueueing one step: a short burst into idle streams (well below the launch-queue depth)
     barrier()
     t_h = time.perf_counter()
@@ -316,11 +437,12 @@ def main():
     bytes_apply = algorithmic_bytes(n, nnz, k) + (48 * n * k if cg else 0)  # dot 16, norm2 8, axpy 24 bytes per element
     peak, peak_src = measured_peak()
     # per-GPU roofline of the SpMV kernel: this rank's algorithmic bytes over the step duration
-    bytes_rank = algorithmic_bytes(n_my, nnz_my, k) + (48 * n_my * k if cg else 0)
+    bytes_rank = bytes_rank_est + (48 * n_my * k if cg else 0)
     achieved = bytes_rank / (ms_per_step * 1e-3) / 1e9
 
     # ---- e2e: host buffers through the C ABI (H2D + kernels + D2H inside the timed region) ----
     e2e = None
+    y_e2e = None
     if not args.no_e2e:
         px, py = C.c_void_p(), C.c_void_p()
         _lib.check(lib.jp_host_alloc(n_my * k * 8 + 64, C.byref(px)))
@@ -334,12 +456,19 @@ def main():
             _lib.check(lib.jp_apply_host(comm.handle, A.h, plan, px, py, k, jp.NO_TRANS, 1.0, 0.0))  # synchronises: Y is on the host on return
         barrier()
         e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.e2e_steps
-        y_e2e = np.ctypeslib.as_array(C.cast(py, C.POINTER(C.c_double)), shape=(n_my * k,)).copy()
-        assert np.array_equal(y_e2e.reshape((n_my, k), order="F"), Y.data), "host-buffer path disagrees with the device path"
+        y_e2e = np.ctypeslib.as_array(C.cast(py, C.POINTER(C.c_double)), shape=(n_my * k,)).copy().reshape((n_my, k), order="F")
         e2e = {"value": 2.0 * nnz * k / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": n * k * 8,
-               "d2h_bytes_per_step": n * k * 8, "host_memory": "pinned (jp_host_alloc)"}
+               "d2h_bytes_per_step": n * k * 8, "host_memory": "pinned (jp_host_alloc)", "steps": args.e2e_steps}
         lib.jp_host_free(px)
         lib.jp_host_free(py)
+
+    # ---- parity of what the timed loop computed, at this rank count (every rank takes part) ----
+    parity = {"checked": False}
+    parity_ok = True
+    if not args.no_parity:
+        if not cg:
+            _lib.check(lib.jp_apply(comm.handle, Y.h, A.h, X.h, plan, jp.NO_TRANS, 1.0, 0.0))  # Y of the very path that was timed
+        parity_ok, parity = parity_checks(jp, comm, A, X, Y, x_host, spec, k, world, rank, y_e2e)
 
     # ---- CPU baseline: the oracle's localApply on one core, same matrix (rank 0 at N=1 only) ----
     cpu = None
@@ -352,22 +481,23 @@ def main():
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": spec["name"], "n": n, "nnz": nnz, "k": k, "alpha": 1.0, "beta": 0.0, "parallelism": f"rows/{world} (BlockMap)",
-                       "l2": (f"L2 flushed (256 MB memset) between timed iterations, each iteration on its own event pair; {bytes_rank / 1e6:.0f} MB per GPU per apply"
-                              if flush else f"inputs larger than L2: {bytes_rank / 1e6:.0f} MB streamed per GPU per apply vs 126 MB L2; no flush needed"),
-                       "setup_s": round(setup_s, 1)},
+            "config": bench_config(spec, nnz, k, world),
+            "setup_s": round(setup_s, 1), "aligning_steps": align, "per_step": per_step,
             "hbm_gbs": bytes_apply / (ms_per_step * 1e-3) / 1e9, "host_enqueue_ms_per_step": host_enqueue_ms, "host_enqueue_burst_ms_per_step": host_burst_ms,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
                          "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0, "bytes_per_launch": bytes_rank,
                          "kernel": "spmv_kernel (one launch per apply at N=1; at N>1 the same row-block code inside spmv_fused_halo_kernel, one launch per apply)"},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": dict(clocks or {}, window=clocks_window) if clocks else None,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "parity": parity,
+            "clocks": dict(clocks, window=clocks_window) if clocks else None,
         }
         print(json.dumps(line), flush=True)
     barrier()
     if dist is not None:
         dist.destroy_process_group()
+    if not parity_ok:
+        sys.exit(3)
 
 
 if __name__ == "__main__":

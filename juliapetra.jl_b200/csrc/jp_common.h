@@ -73,6 +73,7 @@ struct Context {
   // host-mapped word the peer-to-peer halo kernels increment when a flag wait times out
   unsigned long long* p2p_timeout_host = nullptr;
   unsigned long long* p2p_timeout_dev = nullptr;
+  std::vector<void*> retired_arenas;  // IPC-exported halo arenas of destroyed / regrown plans (a peer may still map them)
 };
 Context& ctx();
 void require_init();
@@ -215,12 +216,6 @@ struct Csr : Object {
   // [chunk_block[c], chunk_block[c+1]) = rows [chunk_row[c], chunk_row[c+1]) and reads columns <= chunk_maxcol[c]
   // (prefix maximum), so its kernel can start as soon as that much of X has been uploaded
   std::vector<int32_t> chunk_block, chunk_row, chunk_maxcol;
-  // CUDA graphs of the fused apply sequence, keyed by the device addresses and scalars it was captured with
-  std::unordered_map<std::string, cudaGraphExec_t> graphs;
-  ~Csr() override {
-    for (auto& kv : graphs)
-      if (kv.second) cudaGraphExecDestroy(kv.second);
-  }
 };
 
 struct Plan : Object {
@@ -239,19 +234,16 @@ struct Plan : Object {
   jp_handle posted_tgt = 0;
   int32_t posted_k = 0;
   cudaEvent_t ev_done = nullptr;
-  // ---- peer-to-peer halo (fused apply): every rank exposes an ARENA through CUDA IPC:
-  //      [ready flags: uint64 per source rank | ack flags: uint64 per destination rank | recv buffer 0 | recv buffer 1]
-  //      senders store packed rows straight into the receiver's buffer over NVLink and publish `ready = epoch`;
-  //      receivers publish `ack = epoch` into the sender's arena when the boundary rows have consumed the halo.
+  // ---- peer-to-peer halo (protocol and arena layout: jp_p2p.cuh) ----
   int p2p_state = 0;            // 0 = not tried, 1 = active, -1 = unavailable (NCCL send/recv is used)
-  int32_t p2p_k = 0;
+  int32_t p2p_kcap = 0;         // vectors one halo buffer has room for
   DeviceBuffer arena;
-  size_t arena_buf_bytes = 0;   // bytes of ONE of my recv buffers
+  size_t arena_buf_bytes = 0;   // bytes of ONE of my two halo buffers
   std::vector<void*> peer_arena;   // per rank: mapped base of its arena (own rank: arena.p; non-neighbours: nullptr)
   DeviceBuffer send_table;      // P2PSend per send block
   DeviceBuffer wait_table;      // per source: {const uint64* ready flag (mine)}, {uint64* ack flag (in the source's arena)}
   int32_t n_send_blocks = 0, n_sources = 0;
-  DeviceBuffer p2p_tickets;     // uint32 counters
+  DeviceBuffer p2p_tickets;     // uint32 counters: [0] pack items done, [1] boundary blocks done, [2] pack-item claims
   uint64_t epoch = 0;           // applies done through the peer-memory halo (identical on every rank)
   ~Plan() override;
 };
@@ -287,7 +279,9 @@ double* launch_spmv_fused_dot(Csr& A, const FusedHalo& h, const double* x, const
                               const double* w, cudaStream_t stream);
 const double* plan_post_p2p(Plan& p, const MultiVector& src);
 void plan_p2p_ack(Plan& p);
-bool p2p_setup_public(Plan& p, int32_t k);
+bool plan_p2p_ensure(Plan& p, int32_t k);
+void retire_arena(DeviceBuffer& arena);  // an IPC-exported arena is parked until jp_finalize instead of freed
+double* apply_dot_local(Csr* a, Plan* p, MultiVector* y, MultiVector* x, MultiVector* w, int32_t mode, double alpha, double beta);
 void apply_trans_distributed(Csr* a, Plan* p, MultiVector* y, MultiVector* x, double alpha, double beta);
 void comm_allreduce_device(Comm& c, double* buf, int64_t n, cudaStream_t stream);
 void release_host_path_cache();

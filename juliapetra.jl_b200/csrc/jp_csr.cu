@@ -40,31 +40,83 @@ using namespace csrk;
 
 // ---------------------------------------------------------------------------------------------------------------
 // apply! with the halo exchange INSIDE the SpMV kernel (k = 1, peer-memory halo): one launch per apply, no stream
-// events, no NCCL call.  The grid is [pack CTAs | interior row blocks | boundary row blocks]:
-//   pack CTAs      gather the exported rows of x and store them straight into the neighbours' halo buffers over
-//                  NVLink (IPC-mapped peer pointers), then publish ready = epoch with a system-scope release;
-//   interior CTAs  the ordinary row-block SpMV on local columns (they are the bulk of the grid and hide the exchange);
-//   boundary CTAs  come last in the grid: they acquire the neighbours' ready flags (set ~30 us earlier by the peers'
-//                  pack CTAs, which never wait on this GPU's current kernel), run the row-block SpMV on x + halo, and
-//                  the last one publishes ack = epoch so the senders may overwrite the halo buffer next time.
-// CTAs are dispatched in index order, so pack CTAs run first and a waiting boundary CTA never holds a slot that a
-// pack or interior CTA still needs.
+// events, no NCCL call.  The grid is [pack CTAs | interior row blocks | boundary row blocks]; the protocol (two halo
+// buffers selected by epoch parity, ready / ack flags) is described in jp_p2p.cuh.
+//   pack ITEMS     gather the exported rows of x and store them straight into the neighbours' halo buffers over
+//                  NVLink (IPC-mapped peer pointers); whoever completes the last item publishes ready = epoch with a
+//                  system-scope release.  Items are CLAIMED from a ticket counter -- by the dedicated pack CTAs at the
+//                  head of the grid and by every boundary CTA before it starts to wait;
+//   interior CTAs  the ordinary row-block SpMV on local columns (the bulk of the grid; they hide the exchange);
+//   boundary CTAs  come last in the grid: claim pack items until none is left, acquire the neighbours' ready flags (set
+//                  ~30 us earlier by the peers' pack items), run the row-block SpMV on x + halo, and the last one
+//                  publishes ack = epoch so the senders may reuse this halo buffer two applies later.
+// Forward progress does not depend on the order in which the hardware dispatches CTAs: a CTA only ever spins on a
+// remote flag AFTER every pack item of its own kernel has been claimed by a running CTA, pack items wait only for
+// acks of apply e - 2 (published by kernels that precede the neighbours' current one in stream order), and interior
+// CTAs never wait.  So on every rank the pack items of apply e complete, hence every boundary wait of apply e ends.
 // ---------------------------------------------------------------------------------------------------------------
 struct FusedSpmvArgs {
   const BlockDesc* interior;
   const BlockDesc* boundary;
   int32_t n_pack, n_interior, n_boundary;
+  int32_t n_items;  // pack items (>= 1; item t packs export entries t*T + tid, strided by n_items*T)
   const int32_t* rowptr;
   const int32_t* colind;
   const double* vals;
   const double* x;
-  const double* halo;
+  const double* halo;  // this apply's halo buffer (parity already applied)
   int32_t nloc;
   double* y;
   int32_t cap;
   double alpha, beta;
   FusedHalo h;
 };
+
+// one pack item; called by every thread of the CTA
+__device__ __forceinline__ void fused_pack_item(const FusedSpmvArgs& a, unsigned item, bool* s_last) {
+  const int tid = threadIdx.x;
+  const uint64_t epoch = a.h.epoch;
+  if (tid < a.h.n_sends && epoch > 2)  // back-pressure: the receiver has consumed what this buffer held two applies ago
+    wait_flag_ge(a.h.sends[tid].ack_flag, epoch - 2, a.h.timeout_flag);
+  __syncthreads();
+  const int64_t stride = (int64_t)a.n_items * kSpmvThreads;
+  for (int64_t i = (int64_t)item * kSpmvThreads + tid; i < a.h.n_export; i += stride) {
+    int sb = 0;
+    while (sb + 1 < a.h.n_sends && i >= a.h.sends[sb].start + a.h.sends[sb].count) ++sb;
+    const P2PSend& s = a.h.sends[sb];
+    s.dst_base[(epoch & 1) * s.dst_buf_elems + s.dst_off + (i - s.start)] = __ldg(a.x + __ldg(a.h.lids + i));
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) *s_last = (atomicAdd(a.h.tickets + 0, 1u) == (unsigned)a.n_items - 1);
+  __syncthreads();
+  if (*s_last) {
+    __threadfence_system();
+    if (tid < a.h.n_sends) st_release_sys(a.h.sends[tid].ready_flag, epoch);
+    // a rank whose matrix has no boundary rows still owes its sources the ack
+    if (a.n_boundary == 0 && tid < a.h.n_sources) st_release_sys(a.h.sources[tid].ack_flag, epoch);
+    if (tid == 0) a.h.tickets[0] = 0;  // re-arm for the next apply (stream-ordered after this kernel)
+  }
+  __syncthreads();  // s_last is reused by the next item
+}
+
+// claim and run pack items until none is left.  n_pack + n_boundary CTAs call this once per kernel and each makes
+// exactly one unsuccessful claim, so the CTA that draws the last ticket of the kernel re-arms the counter.
+__device__ __forceinline__ void fused_pack_claims(const FusedSpmvArgs& a, unsigned* s_claim, bool* s_last) {
+  const unsigned last_ticket = (unsigned)a.n_items + (unsigned)a.n_pack + (unsigned)a.n_boundary - 1u;
+  for (;;) {
+    if (threadIdx.x == 0) {
+      const unsigned t = atomicAdd(a.h.tickets + 2, 1u);
+      if (t == last_ticket) a.h.tickets[2] = 0;
+      *s_claim = t;
+    }
+    __syncthreads();
+    const unsigned t = *s_claim;
+    __syncthreads();
+    if (t >= (unsigned)a.n_items) return;
+    fused_pack_item(a, t, s_last);
+  }
+}
 
 // DOT: every CTA also leaves sum_r w[r] * y_new[r] over its rows in partials[blockIdx.x] (0 for the pack CTAs), the
 // multi-GPU form of spmv_dot_kernel (jp_apply_dot with a peer-memory halo)
@@ -74,38 +126,21 @@ __device__ __forceinline__ void fused_halo_body(const FusedSpmvArgs& a, const do
   __shared__ double s_red[kSpmvThreads / 32];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ bool s_last;
+  __shared__ unsigned s_claim;
   const int tid = threadIdx.x;
   const int bid = blockIdx.x;
-  const uint64_t epoch = a.h.epoch;
   double dacc = 0.0;
   if (bid < a.n_pack) {
-    // ---- pack + send ----
-    if (tid < a.h.n_sends && epoch > 1)  // back-pressure: the receiver consumed the previous halo
-      wait_flag_ge(a.h.sends[tid].ack_flag, epoch - 1, a.h.timeout_flag);
-    __syncthreads();
-    const int64_t stride = (int64_t)a.n_pack * kSpmvThreads;
-    for (int64_t i = (int64_t)bid * kSpmvThreads + tid; i < a.h.n_export; i += stride) {
-      int sb = 0;
-      while (sb + 1 < a.h.n_sends && i >= a.h.sends[sb].start + a.h.sends[sb].count) ++sb;
-      a.h.sends[sb].dst[i - a.h.sends[sb].start] = __ldg(a.x + __ldg(a.h.lids + i));
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(a.h.tickets + 0, 1u) == (unsigned)a.n_pack - 1);
-    __syncthreads();
-    if (s_last) {
-      __threadfence_system();
-      if (tid < a.h.n_sends) st_release_sys(a.h.sends[tid].ready_flag, epoch);
-      if (tid == 0) a.h.tickets[0] = 0;  // re-arm for the next apply (stream-ordered after this kernel)
-    }
+    fused_pack_claims(a, &s_claim, &s_last);
   } else if (bid < a.n_pack + a.n_interior) {
     const StageView sv = stage_view(smem_raw, a.cap);
     const BlockRange b = decode_block(a.interior, bid - a.n_pack);
     if (DOT) dacc = spmv_block<false, 1, true>(b, sv, &s_bar, s_red, a.rowptr, a.colind, a.vals, a.x, nullptr, a.nloc, a.y, a.alpha, a.beta, w);
     else spmv_block<false, 1>(b, sv, &s_bar, s_red, a.rowptr, a.colind, a.vals, a.x, nullptr, a.nloc, a.y, a.alpha, a.beta);
   } else {
-    // ---- boundary rows: wait for the neighbours' halos first ----
-    if (tid < a.h.n_sources) wait_flag_ge(a.h.sources[tid].ready_flag, epoch, a.h.timeout_flag);
+    // ---- boundary rows: no pack item may be left unclaimed before this CTA starts to wait for the neighbours ----
+    fused_pack_claims(a, &s_claim, &s_last);
+    if (tid < a.h.n_sources) wait_flag_ge(a.h.sources[tid].ready_flag, a.h.epoch, a.h.timeout_flag);
     __syncthreads();
     const StageView sv = stage_view(smem_raw, a.cap);
     const BlockRange b = decode_block(a.boundary, bid - a.n_pack - a.n_interior);
@@ -115,7 +150,7 @@ __device__ __forceinline__ void fused_halo_body(const FusedSpmvArgs& a, const do
     if (tid == 0) s_last = (atomicAdd(a.h.tickets + 1, 1u) == (unsigned)a.n_boundary - 1);
     __syncthreads();
     if (s_last) {
-      if (tid < a.h.n_sources) st_release_sys(a.h.sources[tid].ack_flag, epoch);
+      if (tid < a.h.n_sources) st_release_sys(a.h.sources[tid].ack_flag, a.h.epoch);
       if (tid == 0) a.h.tickets[1] = 0;
     }
   }
@@ -309,15 +344,16 @@ void launch_spmm_tile(const Csr& A, const BlockDesc* b, int32_t n_blocks, const 
 
 }  // namespace
 
-void launch_spmv_fused(const Csr& A, const FusedHalo& h, const double* x, const double* halo, double* y, double alpha, double beta,
-                       cudaStream_t stream) {
+// the argument block shared by the two fused launches; `halo` is this apply's halo buffer (epoch parity applied)
+static FusedSpmvArgs fused_args(const Csr& A, const FusedHalo& h, const double* x, const double* halo, double* y, double alpha, double beta) {
   FusedSpmvArgs a;
   a.interior = A.blocks_interior.as<BlockDesc>();
   a.boundary = A.blocks_boundary.as<BlockDesc>();
   a.n_interior = A.n_blocks_interior;
   a.n_boundary = A.n_blocks_boundary;
-  static const int pack_rows = std::max(64, env_int("JP_FUSED_PACK_ROWS", 1024));  // exported rows per pack CTA
-  a.n_pack = std::max(1, std::min(64, (h.n_export + pack_rows - 1) / pack_rows));
+  static const int pack_rows = std::max(64, env_int("JP_FUSED_PACK_ROWS", 1024));  // exported rows per pack item
+  a.n_items = std::max(1, std::min(64, (h.n_export + pack_rows - 1) / pack_rows));
+  a.n_pack = a.n_items;  // one dedicated CTA per item at the head of the grid (boundary CTAs claim whatever is left)
   a.rowptr = A.rowptr.as<int32_t>();
   a.colind = A.colind.as<int32_t>();
   a.vals = A.vals.as<double>();
@@ -329,6 +365,12 @@ void launch_spmv_fused(const Csr& A, const FusedHalo& h, const double* x, const 
   a.alpha = alpha;
   a.beta = beta;
   a.h = h;
+  return a;
+}
+
+void launch_spmv_fused(const Csr& A, const FusedHalo& h, const double* x, const double* halo, double* y, double alpha, double beta,
+                       cudaStream_t stream) {
+  const FusedSpmvArgs a = fused_args(A, h, x, halo, y, alpha, beta);
   const size_t smem = stage_smem_bytes(A.nnz_cap);
   set_smem_attr(spmv_fused_halo_kernel, smem);
   const int grid = a.n_pack + a.n_interior + a.n_boundary;
@@ -373,24 +415,7 @@ double* launch_spmv_dot(Csr& A, const double* x, double* y, double alpha, double
 // the fused halo + SpMV launch of launch_spmv_fused with the dot product of jp_apply_dot accumulated on the way
 double* launch_spmv_fused_dot(Csr& A, const FusedHalo& h, const double* x, const double* halo, double* y, double alpha, double beta,
                               const double* w, cudaStream_t stream) {
-  FusedSpmvArgs a;
-  a.interior = A.blocks_interior.as<BlockDesc>();
-  a.boundary = A.blocks_boundary.as<BlockDesc>();
-  a.n_interior = A.n_blocks_interior;
-  a.n_boundary = A.n_blocks_boundary;
-  static const int pack_rows = std::max(64, env_int("JP_FUSED_PACK_ROWS", 1024));  // exported rows per pack CTA
-  a.n_pack = std::max(1, std::min(64, (h.n_export + pack_rows - 1) / pack_rows));
-  a.rowptr = A.rowptr.as<int32_t>();
-  a.colind = A.colind.as<int32_t>();
-  a.vals = A.vals.as<double>();
-  a.x = x;
-  a.halo = halo;
-  a.nloc = A.n_local_cols;
-  a.y = y;
-  a.cap = A.nnz_cap;
-  a.alpha = alpha;
-  a.beta = beta;
-  a.h = h;
+  const FusedSpmvArgs a = fused_args(A, h, x, halo, y, alpha, beta);
   const int grid = a.n_pack + a.n_interior + a.n_boundary;
   const size_t ws_bytes = ((size_t)grid + 4) * 8;  // [CTA partials | result]
   if (A.dot_ws.bytes < ws_bytes) A.dot_ws.alloc(ws_bytes);
@@ -420,10 +445,8 @@ void launch_spmv_blocks(const Csr& A, const void* blocks_int4, int32_t n_blocks,
   // the run-staged kernel serves launches over the WHOLE all-blocks or interior list (it has its own block lists with a
   // different geometry; a chunk of a list, as jp_apply_host launches, stays with the gather kernel)
   const bool whole_all = blocks_int4 == A.blocks_all.p && n_blocks == A.n_blocks_all;
-  // (interior-only launches are the multi-GPU two-stream path: the run-staged kernel has not been run there yet, so it
-  // is opt-in with JP_SPMM_RUNS_INTERIOR=1 and the validated gather kernel stays the default)
-  static const bool runs_interior = env_int("JP_SPMM_RUNS_INTERIOR", 0) != 0;
-  const bool whole_interior = runs_interior && blocks_int4 == A.blocks_interior.p && n_blocks == A.n_blocks_interior;
+  // (the interior-only launch is the compute-stream half of the multi-GPU two-stream path)
+  const bool whole_interior = blocks_int4 == A.blocks_interior.p && n_blocks == A.n_blocks_interior;
   if (k > 1 && A.runs_state == 1 && !use_halo && (ldx & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
       (whole_all || whole_interior)) {
     // banded matrix, no halo columns in this launch

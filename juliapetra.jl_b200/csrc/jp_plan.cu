@@ -91,17 +91,18 @@ void exchange(Plan& p, int32_t k, bool reverse, cudaStream_t st) {
 // order as the whole interior SpMV at 8 GPUs.  Here the pack kernel IS the send: it gathers the exported rows of X
 // and stores them straight into the receiver's halo buffer through an IPC-mapped peer pointer (NVLink stores), then
 // publishes an epoch flag; the receiver's comm stream waits on the flag in a one-warp kernel right before the
-// boundary-row kernel.  Buffers are double-buffered by epoch parity and guarded by an ack flag, so a sender can
-// never overwrite a halo that is still being read.
+// boundary-row kernel.  Every rank has TWO halo buffers, selected by the parity of the epoch, and an ack flag per
+// source, so a sender can never overwrite a halo that is still being read and neighbours are not lock-stepped
+// (protocol: jp_p2p.cuh).
 // ---------------------------------------------------------------------------------------------------------------
-// fused pack + send: dst[(i - start)*k + j] = src[lid[i] + j*ld] for every export entry i, into the receivers' buffers.
+// fused pack + send: dst[(off + i - start)*k + j] = src[lid[i] + j*ld] for every export entry i, into the receivers' buffers.
 __global__ void __launch_bounds__(kThreads) pack_p2p_kernel(const double* __restrict__ src, int64_t ld, const int32_t* __restrict__ lids,
                                                               int32_t n, int32_t k, const P2PSend* __restrict__ table, int32_t n_blocks,
                                                               uint64_t epoch, unsigned int* __restrict__ ticket,
                                                               unsigned long long* timeout_flag) {
   __shared__ bool is_last;
-  // back-pressure: the receiver must have consumed the previous halo before its buffer is overwritten
-  if (threadIdx.x < n_blocks && epoch > 1) wait_flag_ge(table[threadIdx.x].ack_flag, epoch - 1, timeout_flag);
+  // back-pressure: the receiver must have consumed what this buffer held two applies ago
+  if (threadIdx.x < n_blocks && epoch > 2) wait_flag_ge(table[threadIdx.x].ack_flag, epoch - 2, timeout_flag);
   __syncthreads();
   const int64_t total = (int64_t)n * k;
   const int64_t stride = (int64_t)gridDim.x * kThreads;
@@ -109,7 +110,8 @@ __global__ void __launch_bounds__(kThreads) pack_p2p_kernel(const double* __rest
     const int32_t j = (int32_t)(t / n), i = (int32_t)(t - (int64_t)j * n);
     int b = 0;
     while (b + 1 < n_blocks && i >= table[b].start + table[b].count) ++b;
-    table[b].dst[(size_t)(i - table[b].start) * k + j] = __ldg(src + __ldg(lids + i) + (size_t)j * ld);
+    const P2PSend& s = table[b];
+    s.dst_base[(epoch & 1) * s.dst_buf_elems + (size_t)(s.dst_off + i - s.start) * k + j] = __ldg(src + __ldg(lids + i) + (size_t)j * ld);
   }
   __threadfence_system();
   __syncthreads();
@@ -143,9 +145,31 @@ void allgather_host_bytes(Comm& c, const void* in, size_t bytes, void* out) {
   JP_CUDA(cudaStreamSynchronize(x.comm));
 }
 
-// Collective over the plan's comm: build the arenas, exchange IPC handles and recv offsets, map the neighbours.
-// Returns false (on every rank) when peer mapping is unavailable; the caller then uses NCCL send/recv.
-bool p2p_setup(Plan& p, int32_t k) {
+// min over the ranks of a host integer (setup only): "everybody or nobody" decisions
+int64_t allreduce_min_host(Comm& c, int64_t v) {
+  Context& x = ctx();
+  int64_t out = 0;
+  int64_t* buf = (int64_t*)scratch(16);
+  JP_CUDA(cudaMemcpyAsync(buf, &v, 8, cudaMemcpyHostToDevice, x.comm));
+  JP_NCCL(ncclAllReduce(buf, buf, 1, ncclInt64, ncclMin, c.nccl, x.comm));
+  JP_CUDA(cudaMemcpyAsync(&out, buf, 8, cudaMemcpyDeviceToHost, x.comm));
+  JP_CUDA(cudaStreamSynchronize(x.comm));
+  return out;
+}
+
+void close_peer_mappings(Plan& p) {
+  const int me = p.comm ? p.comm->rank0 : -1;
+  for (int q = 0; q < (int)p.peer_arena.size(); ++q)
+    if (p.peer_arena[q] && q != me) cudaIpcCloseMemHandle(p.peer_arena[q]);
+  p.peer_arena.clear();
+}
+
+// Collective over the plan's comm: build an arena with room for k_cap vectors per halo buffer, exchange IPC handles
+// and receive offsets, map the neighbours.  Returns false ON EVERY RANK when the peer-memory halo cannot be used
+// (a rank cannot export or map memory, more ranks / sources / destinations than the flag block and the kernels'
+// one-thread-per-flag loops hold); the caller then uses NCCL send/recv.  Every feasibility condition is evaluated
+// BEFORE the agreement all-reduce, so the ranks never disagree.
+bool p2p_setup(Plan& p, int32_t k_cap) {
   Comm& c = *p.comm;
   Context& x = ctx();
   if (c.serial) return false;
@@ -154,37 +178,46 @@ bool p2p_setup(Plan& p, int32_t k) {
     return v && std::string(v) == "nccl";
   }();
   if (disabled) return false;
-  JP_REQUIRE(c.nproc <= 256, "peer-to-peer halo supports up to 256 ranks");
   JP_CUDA(cudaStreamSynchronize(x.comm));
   JP_CUDA(cudaStreamSynchronize(x.compute));
   const int P = c.nproc, me = c.rank0;
-  // close a previous mapping (k changed)
-  for (int q = 0; q < (int)p.peer_arena.size(); ++q)
-    if (p.peer_arena[q] && q != me) cudaIpcCloseMemHandle(p.peer_arena[q]);
+  // a previous, smaller arena: every rank closes its mappings, and only after all of them have done so is the memory
+  // retired (an exported allocation must not be freed while an importer still has it open)
+  if (!p.peer_arena.empty()) {
+    close_peer_mappings(p);
+    allreduce_min_host(c, 1);
+    retire_arena(p.arena);
+  }
+  int ok = 1;
+  size_t n_sends = 0, n_sources = 0;
+  for (size_t i = 0; i < p.procs_to.size(); ++i) n_sends += p.lengths_to[i] > 0;
+  for (size_t i = 0; i < p.procs_from.size(); ++i) n_sources += p.lengths_from[i] > 0;
+  if (P > kP2PMaxRanks || n_sends > (size_t)kP2PMaxSends || n_sources > (size_t)kP2PMaxSources) ok = 0;
   p.peer_arena.assign(P, nullptr);
-  p.arena_buf_bytes = (((size_t)std::max(p.n_remote, 1) * k * 8) + 255) & ~(size_t)255;
-  p.arena.alloc(kArenaFlagBytes + p.arena_buf_bytes);
-  JP_CUDA(cudaMemset(p.arena.p, 0, kArenaFlagBytes + p.arena_buf_bytes));
-  p.p2p_tickets.alloc(64);  // uint32 tickets: [0] pack blocks, [1] boundary blocks
+  p.arena_buf_bytes = (((size_t)std::max(p.n_remote, 1) * k_cap * 8) + 255) & ~(size_t)255;
+  const size_t arena_bytes = kArenaFlagBytes + 2 * p.arena_buf_bytes;
+  p.arena.alloc(arena_bytes);
+  JP_CUDA(cudaMemset(p.arena.p, 0, arena_bytes));
+  p.p2p_tickets.alloc(64);  // uint32 tickets: [0] pack items, [1] boundary blocks, [2] pack-item claims
   JP_CUDA(cudaMemset(p.p2p_tickets.p, 0, 64));
   p.epoch = 0;
-  // what every rank publishes: IPC handle, buffer size, and for each source rank the element offset of its data
+  // what every rank publishes: IPC handle, buffer size, and for each source rank the row offset of its data
   struct Info {
     cudaIpcMemHandle_t handle;
     uint64_t buf_bytes;
-    int64_t recv_off[256];
+    int64_t recv_off[kP2PMaxRanks];
   };
   std::vector<Info> all(P);
   Info mine;
   std::memset(&mine, 0, sizeof mine);
-  int ok = 1;
   if (cudaIpcGetMemHandle(&mine.handle, p.arena.p) != cudaSuccess) {
     cudaGetLastError();
     ok = 0;
   }
   mine.buf_bytes = p.arena_buf_bytes;
-  for (int q = 0; q < 256; ++q) mine.recv_off[q] = -1;
-  for (size_t i = 0; i < p.procs_from.size(); ++i) mine.recv_off[p.procs_from[i] - 1] = p.starts_from[i];
+  for (int q = 0; q < kP2PMaxRanks; ++q) mine.recv_off[q] = -1;
+  for (size_t i = 0; i < p.procs_from.size(); ++i)
+    if (p.procs_from[i] - 1 < kP2PMaxRanks) mine.recv_off[p.procs_from[i] - 1] = p.starts_from[i];
   allgather_host_bytes(c, &mine, sizeof(Info), all.data());
   // map every neighbour (ranks I send to or receive from)
   std::vector<char> need(P, 0);
@@ -201,19 +234,13 @@ bool p2p_setup(Plan& p, int32_t k) {
     }
     p.peer_arena[q] = ptr;
   }
+  // every receiver must expect what I send
+  for (size_t i = 0; i < p.procs_to.size() && ok; ++i)
+    if (p.lengths_to[i] > 0 && (p.procs_to[i] - 1 >= kP2PMaxRanks || all[p.procs_to[i] - 1].recv_off[me] < 0)) ok = 0;
   // everybody or nobody
-  int64_t okv = ok, okmin = 0;
-  {
-    int64_t* buf = (int64_t*)scratch(16);
-    JP_CUDA(cudaMemcpyAsync(buf, &okv, 8, cudaMemcpyHostToDevice, x.comm));
-    JP_NCCL(ncclAllReduce(buf, buf, 1, ncclInt64, ncclMin, c.nccl, x.comm));
-    JP_CUDA(cudaMemcpyAsync(&okmin, buf, 8, cudaMemcpyDeviceToHost, x.comm));
-    JP_CUDA(cudaStreamSynchronize(x.comm));
-  }
-  if (!okmin) {
-    for (int q = 0; q < P; ++q)
-      if (p.peer_arena[q] && q != me) cudaIpcCloseMemHandle(p.peer_arena[q]);
-    p.peer_arena.assign(P, nullptr);
+  if (!allreduce_min_host(c, ok)) {
+    close_peer_mappings(p);
+    allreduce_min_host(c, 1);  // all mappings are closed before any arena is released
     p.arena.release();
     return false;
   }
@@ -222,18 +249,17 @@ bool p2p_setup(Plan& p, int32_t k) {
   for (size_t i = 0; i < p.procs_to.size(); ++i) {
     if (p.lengths_to[i] == 0) continue;
     const int q = p.procs_to[i] - 1;
-    const int64_t off = all[q].recv_off[me];
-    JP_REQUIRE_STATE(off >= 0, "peer-to-peer halo: the receiver does not expect data from this rank");
     char* base = (char*)p.peer_arena[q];
     P2PSend s;
     s.start = (int32_t)p.starts_to[i];
     s.count = (int32_t)p.lengths_to[i];
-    s.dst = (double*)(base + kArenaFlagBytes) + (size_t)off * k;
+    s.dst_base = (double*)(base + kArenaFlagBytes);
+    s.dst_buf_elems = (int64_t)(all[q].buf_bytes / 8);
+    s.dst_off = all[q].recv_off[me];
     s.ready_flag = (uint64_t*)base + me;
     s.ack_flag = (const uint64_t*)((char*)p.arena.p + 2048) + q;
     sends.push_back(s);
   }
-  JP_REQUIRE(sends.size() <= (size_t)kThreads, "peer-to-peer halo: too many destinations");
   std::vector<P2PSource> sources;
   for (size_t i = 0; i < p.procs_from.size(); ++i) {
     if (p.lengths_from[i] == 0) continue;
@@ -243,7 +269,6 @@ bool p2p_setup(Plan& p, int32_t k) {
     s.ack_flag = (uint64_t*)((char*)p.peer_arena[q] + 2048) + me;
     sources.push_back(s);
   }
-  JP_REQUIRE(sources.size() <= 32, "peer-to-peer halo: more than 32 sources per rank");
   p.n_send_blocks = (int32_t)sends.size();
   p.n_sources = (int32_t)sources.size();
   p.send_table.alloc(sends.size() * sizeof(P2PSend) + 16);
@@ -251,13 +276,8 @@ bool p2p_setup(Plan& p, int32_t k) {
   if (!sends.empty()) JP_CUDA(cudaMemcpy(p.send_table.p, sends.data(), sends.size() * sizeof(P2PSend), cudaMemcpyHostToDevice));
   if (!sources.empty()) JP_CUDA(cudaMemcpy(p.wait_table.p, sources.data(), sources.size() * sizeof(P2PSource), cudaMemcpyHostToDevice));
   // nobody may publish into an arena that is not mapped everywhere yet
-  {
-    double* buf = (double*)scratch(8);
-    JP_CUDA(cudaMemsetAsync(buf, 0, 8, x.comm));
-    JP_NCCL(ncclAllReduce(buf, buf, 1, ncclDouble, ncclSum, c.nccl, x.comm));
-    JP_CUDA(cudaStreamSynchronize(x.comm));
-  }
-  p.p2p_k = k;
+  allreduce_min_host(c, 1);
+  p.p2p_kcap = k_cap;
   return true;
 }
 
@@ -366,23 +386,49 @@ void plan_unpack(Plan& p, MultiVector& tgt, cudaStream_t stream) {
   JP_LAUNCH_CHECK();
 }
 
-bool p2p_setup_public(Plan& p, int32_t k) { return p2p_setup(p, k); }
+// Collective: make the peer-memory halo of `p` usable for k vectors (first use, or k exceeds the arena's capacity).
+// Every rank reaches the same decision because applies are collective and carry the same k everywhere.
+bool plan_p2p_ensure(Plan& p, int32_t k) {
+  if (p.p2p_state == 0 || (p.p2p_state == 1 && k > p.p2p_kcap)) {
+    int32_t cap = std::max(k, 4);  // room for small multivectors without a second collective setup
+    if (p.p2p_state == 1) cap = std::max(cap, 2 * p.p2p_kcap);
+    p.p2p_state = p2p_setup(p, cap) ? 1 : -1;
+  }
+  return p.p2p_state == 1;
+}
+
+// this apply's halo arguments for the fused kernel; advances the epoch
+FusedHalo plan_p2p_next_epoch(Plan& p, const double** halo) {
+  FusedHalo h;
+  h.lids = p.export_lids.as<int32_t>();
+  h.n_export = p.n_export;
+  h.sends = p.send_table.as<P2PSend>();
+  h.n_sends = p.n_send_blocks;
+  h.sources = p.wait_table.as<P2PSource>();
+  h.n_sources = p.n_sources;
+  h.epoch = ++p.epoch;
+  h.tickets = p.p2p_tickets.as<unsigned int>();
+  h.timeout_flag = p2p_timeout_flag_device();
+  *halo = reinterpret_cast<const double*>(static_cast<const char*>(p.arena.p) + kArenaFlagBytes + (p.epoch & 1) * p.arena_buf_bytes);
+  return h;
+}
 
 Plan::~Plan() {
   if (ev_done) cudaEventDestroy(ev_done);
-  const int me = comm ? comm->rank0 : -1;
+  // a peer may still have this rank's arena mapped (plans are destroyed in no particular order across ranks), so the
+  // arena is retired -- kept until jp_finalize -- instead of freed
   for (int q = 0; q < (int)peer_arena.size(); ++q)
-    if (peer_arena[q] && q != me) cudaIpcCloseMemHandle(peer_arena[q]);
+    if (peer_arena[q] && comm && q != comm->rank0) cudaIpcCloseMemHandle(peer_arena[q]);
+  retire_arena(arena);
 }
 
-// Fused-apply halo over peer memory: returns the halo buffer of this epoch, or nullptr when the plan has to use
+// Two-stream halo over peer memory (k > 1): returns the halo buffer of this epoch, or nullptr when the plan has to use
 // the NCCL path.  Enqueues pack+send and the wait on the comm stream; the caller launches the boundary rows on
 // the comm stream and then calls plan_p2p_ack().
 const double* plan_post_p2p(Plan& p, const MultiVector& src) {
   Context& x = ctx();
   const int32_t k = src.k;
-  if (p.p2p_state == 0 || (p.p2p_state == 1 && p.p2p_k != k)) p.p2p_state = p2p_setup(p, k) ? 1 : -1;
-  if (p.p2p_state != 1) return nullptr;
+  if (!plan_p2p_ensure(p, k)) return nullptr;
   p.epoch += 1;
   JP_CUDA(cudaEventRecord(x.ev_x_ready, x.compute));
   JP_CUDA(cudaStreamWaitEvent(x.comm, x.ev_x_ready, 0));
@@ -395,7 +441,7 @@ const double* plan_post_p2p(Plan& p, const MultiVector& src) {
     halo_wait_kernel<<<1, 32, 0, x.comm>>>(p.wait_table.as<P2PSource>(), p.n_sources, p.epoch, p2p_timeout_flag_device());
     JP_LAUNCH_CHECK();
   }
-  return reinterpret_cast<const double*>((const char*)p.arena.p + kArenaFlagBytes);
+  return reinterpret_cast<const double*>((const char*)p.arena.p + kArenaFlagBytes + (p.epoch & 1) * p.arena_buf_bytes);
 }
 
 void plan_p2p_ack(Plan& p) {
@@ -428,6 +474,21 @@ void check_transfer_args(Plan* p, MultiVector* s, MultiVector* t, int32_t combin
   }
 }
 
+// the column map is [domain prefix | remote tail] (what __makeColMap produces): the local part of X is read in place and
+// the received rows are addressed as column - n_local_cols, so no column-map copy of X is needed
+bool halo_in_place(const Csr* a, const Plan* p, const MultiVector* x) {
+  return p->remote_is_tail && p->n_permute == 0 && p->num_same == a->n_local_cols && p->num_same == x->n &&
+         p->num_same + p->n_remote == a->n_cols;
+}
+
+bool fused_kernel_enabled() {
+  static const bool on = []() {
+    const char* v = std::getenv("JP_FUSED");  // JP_FUSED=0: two-stream sequence instead of the one-kernel apply (A/B measurements)
+    return !(v && *v == '0');
+  }();
+  return on;
+}
+
 // apply!'s NO_TRANS body on device objects; X is a domain-map multivector
 void apply_no_trans(Csr* a, Plan* p, MultiVector* y, MultiVector* x, double alpha, double beta) {
   Context& c = ctx();
@@ -440,8 +501,7 @@ void apply_no_trans(Csr* a, Plan* p, MultiVector* y, MultiVector* x, double alph
   }
   JP_REQUIRE(x->n == p->n_src, "apply!: X does not match the importer's source map");
   JP_REQUIRE(p->n_tgt == a->n_cols, "apply!: the importer's target map is not the matrix's column map");
-  const bool fused = p->remote_is_tail && p->n_permute == 0 && p->num_same == a->n_local_cols && p->num_same == x->n &&
-                     p->num_same + p->n_remote == a->n_cols;
+  const bool fused = halo_in_place(a, p, x);
   if (!fused) {
     // general column map (unused local columns => permutes): import into the cached column-map multivector
     // exactly as the reference does (src/RowMatrix.jl:294-295), then one launch over all row blocks
@@ -464,103 +524,29 @@ void apply_no_trans(Csr* a, Plan* p, MultiVector* y, MultiVector* x, double alph
     return;
   }
   // k == 1 with a peer-memory halo: ONE kernel does pack + send + interior rows + wait + boundary rows + ack
-  // (spmv_fused_halo_kernel, csrc/jp_csr.cu).  JP_FUSED=0 falls back to the two-stream sequence below.
-  static const bool fused_kernel_enabled = []() {
-    const char* v = std::getenv("JP_FUSED");
-    return !(v && *v == '0');
-  }();
-  if (fused_kernel_enabled && x->k == 1) {
-    if (p->p2p_state == 0 || (p->p2p_state == 1 && p->p2p_k != 1)) {  // collective, once
-      JP_CUDA(cudaStreamSynchronize(c.compute));
-      p->p2p_state = p2p_setup_public(*p, 1) ? 1 : -1;
-    }
-    if (p->p2p_state == 1 && p->p2p_k == 1) {
-      FusedHalo h;
-      h.lids = p->export_lids.as<int32_t>();
-      h.n_export = p->n_export;
-      h.sends = p->send_table.as<P2PSend>();
-      h.n_sends = p->n_send_blocks;
-      h.sources = p->wait_table.as<P2PSource>();
-      h.n_sources = p->n_sources;
-      h.epoch = ++p->epoch;
-      h.tickets = p->p2p_tickets.as<unsigned int>();
-      h.timeout_flag = p2p_timeout_flag_device();
-      const double* halo = reinterpret_cast<const double*>(static_cast<const char*>(p->arena.p) + kArenaFlagBytes);
-      launch_spmv_fused(*a, h, x->d(), halo, y->d(), alpha, beta, c.compute);
-      return;
-    }
+  // (spmv_fused_halo_kernel, csrc/jp_csr.cu)
+  if (fused_kernel_enabled() && x->k == 1 && plan_p2p_ensure(*p, 1)) {
+    const double* halo = nullptr;
+    const FusedHalo h = plan_p2p_next_epoch(*p, &halo);
+    launch_spmv_fused(*a, h, x->d(), halo, y->d(), alpha, beta, c.compute);
+    return;
   }
-  // Two-stream path.  The sequence is 2 streams, 3-4 kernels and one NCCL group; at 8 GPUs the device time of one apply
-  // (~35 us for 256^3) is of the order of the host time to enqueue it, so the sequence is captured ONCE per
-  // (X, Y, plan buffers, alpha, beta) into a CUDA graph and replayed with a single cudaGraphLaunch afterwards.
+  // Two-stream path.  comm stream (high priority): pack -> exchange -> BOUNDARY rows; compute stream: INTERIOR rows,
+  // concurrently.  The two launches write disjoint rows of Y; the compute stream joins on the comm stream at the end, so
+  // there is no serial boundary-kernel latency after the interior kernel's tail.  (Replaying this sequence as a CUDA
+  // graph was measured slower than eager enqueue at 2 and 8 GPUs in round 1 -- profiles/r1_scale_*graph* -- and is gone.)
   plan_ensure_buffers(*p, x->k);
-  auto body = [&](bool capturing) {
-    // comm stream (high priority): pack -> exchange -> BOUNDARY rows; compute stream: INTERIOR rows, concurrently.
-    // The two launches write disjoint rows of Y; the compute stream joins on the comm stream at the end, so there
-    // is no serial boundary-kernel latency after the interior kernel's tail.
-    // peer-memory halo (epochs are host-counted, so a captured graph falls back to NCCL send/recv); nullptr -> NCCL
-    const double* halo = capturing ? nullptr : plan_post_p2p(*p, *x);
-    const bool p2p = halo != nullptr;
-    if (!p2p) {
-      plan_post(*p, *x, nullptr, /*halo_only=*/true, JP_INSERT, false);
-      halo = p->recvbuf.as<double>();
-    }
-    launch_spmv(*a, a->blocks_boundary, a->n_blocks_boundary, true, x->d(), x->n, halo, y->k, y->d(), y->n, y->k, alpha, beta, c.comm);
-    if (p2p) plan_p2p_ack(*p);
-    JP_CUDA(cudaEventRecord(p->ev_done, c.comm));
-    launch_spmv(*a, a->blocks_interior, a->n_blocks_interior, false, x->d(), x->n, nullptr, 1, y->d(), y->n, y->k, alpha, beta, c.compute);
-    JP_CUDA(cudaStreamWaitEvent(c.compute, p->ev_done, 0));
-    (void)capturing;
-  };
-  // Graph replay pays off when the sequence is kernels only (peer-memory halo); with NCCL send/recv inside, replay
-  // measured slower than eager enqueue.  JP_APPLY_GRAPH=0/1 forces it off/on.
-  static const int graph_env = []() {
-    const char* v = std::getenv("JP_APPLY_GRAPH");
-    return (v && *v) ? (*v == '1' ? 1 : 0) : -1;
-  }();
-  const bool use_graph = graph_env == 1;  // measured slower than eager enqueue at 2 and 8 GPUs (profiles/): opt-in only
-  if (!use_graph) {
-    body(false);
-    return;
+  const double* halo = plan_post_p2p(*p, *x);  // peer-memory halo; nullptr -> NCCL send/recv
+  const bool p2p = halo != nullptr;
+  if (!p2p) {
+    plan_post(*p, *x, nullptr, /*halo_only=*/true, JP_INSERT, false);
+    halo = p->recvbuf.as<double>();
   }
-  char key[256];
-  std::snprintf(key, sizeof key, "%p|%p|%p|%p|%p|%p|%d|%a|%a", (void*)x->d(), (void*)y->d(), (void*)p, p->sendbuf.p, p->recvbuf.p,
-                p->arena.p, (int)x->k, alpha, beta);
-  auto it = a->graphs.find(key);
-  if (it != a->graphs.end()) {
-    if (it->second != nullptr) {
-      JP_CUDA(cudaGraphLaunch(it->second, c.compute));
-      count_launch(p->p2p_state == 1 ? 3 + (p->n_sources > 0 ? 2 : 0) : 3 + (p->n_export > 0 ? 1 : 0));
-      return;
-    }
-    // second call with this key: everything lazy (shared-memory attributes, NCCL connections) was set up by the
-    // first, eager call -> capture now
-    JP_CUDA(cudaStreamSynchronize(c.comm));
-    cudaGraph_t graph = nullptr;
-    JP_CUDA(cudaStreamBeginCapture(c.compute, cudaStreamCaptureModeThreadLocal));
-    try {
-      body(true);
-    } catch (...) {
-      cudaStreamEndCapture(c.compute, &graph);
-      if (graph) cudaGraphDestroy(graph);
-      throw;
-    }
-    JP_CUDA(cudaStreamEndCapture(c.compute, &graph));
-    cudaGraphExec_t exec = nullptr;
-    JP_CUDA(cudaGraphInstantiate(&exec, graph, 0));
-    JP_CUDA(cudaGraphDestroy(graph));
-    it->second = exec;
-    JP_CUDA(cudaGraphLaunch(exec, c.compute));
-    return;
-  }
-  if (a->graphs.size() > 64) {  // bound the cache: drop everything (handles change rarely in a solver loop)
-    JP_CUDA(cudaStreamSynchronize(c.compute));
-    for (auto& kv : a->graphs)
-      if (kv.second) cudaGraphExecDestroy(kv.second);
-    a->graphs.clear();
-  }
-  a->graphs.emplace(key, nullptr);
-  body(false);
+  launch_spmv(*a, a->blocks_boundary, a->n_blocks_boundary, true, x->d(), x->n, halo, y->k, y->d(), y->n, y->k, alpha, beta, c.comm);
+  if (p2p) plan_p2p_ack(*p);
+  JP_CUDA(cudaEventRecord(p->ev_done, c.comm));
+  launch_spmv(*a, a->blocks_interior, a->n_blocks_interior, false, x->d(), x->n, nullptr, 1, y->d(), y->n, y->k, alpha, beta, c.compute);
+  JP_CUDA(cudaStreamWaitEvent(c.compute, p->ev_done, 0));
 }
 
 // apply! when rangeMap != rowMap (src/RowMatrix.jl:298-308 and 324-330).  The reference's lines
@@ -706,6 +692,27 @@ MultiVector* cached_mv(std::unique_ptr<MultiVector>& slot, int32_t n, int32_t k)
 }  // namespace
 
 namespace jp {
+// y = beta*y + alpha*op(A)*x, and the LOCAL part of sum_r w[r, v] * y[r, v] for every vector v left in a device array of
+// k doubles (compute stream; the caller adds the ranks' parts).  One kernel when the apply itself is one launch:
+//   no importer, k = 1, NO_TRANS       spmv_dot_kernel
+//   peer-memory halo, k = 1, NO_TRANS  spmv_fused_halo_dot_kernel (halo exchange + SpMV + dot)
+// otherwise the apply followed, on the same stream, by the dot kernel (no host round trip in between).
+double* apply_dot_local(Csr* a, Plan* p, MultiVector* y, MultiVector* x, MultiVector* w, int32_t mode, double alpha, double beta) {
+  JP_REQUIRE(w->n == y->n && w->k == y->k, "jp_apply_dot: W must have the shape of Y");
+  JP_REQUIRE(x != y, "apply!: X and Y must be different multivectors");
+  JP_REQUIRE(x->k == y->k, "apply!: X and Y must have the same number of vectors");
+  const bool one_launch = mode == JP_NO_TRANS && alpha != 0.0 && y->k == 1 && w != y && y->n == a->n_rows;
+  if (one_launch && p == nullptr && x->n == a->n_cols) return launch_spmv_dot(*a, x->d(), y->d(), alpha, beta, w->d(), ctx().compute);
+  if (one_launch && p != nullptr && fused_kernel_enabled() && x->n == p->n_src && p->n_tgt == a->n_cols && halo_in_place(a, p, x) &&
+      plan_p2p_ensure(*p, 1)) {
+    const double* halo = nullptr;
+    const FusedHalo h = plan_p2p_next_epoch(*p, &halo);
+    return launch_spmv_fused_dot(*a, h, x->d(), halo, y->d(), alpha, beta, w->d(), ctx().compute);
+  }
+  apply_impl(a, p, y, x, mode, alpha, beta);
+  return mv_dot_local(*w, *y);
+}
+
 void release_host_path_cache() {
   g_host_cache.x.reset();
   g_host_cache.y.reset();
@@ -847,45 +854,9 @@ int32_t jp_apply_dot(jp_handle comm, jp_handle Y, jp_handle A, jp_handle X, jp_h
     MultiVector* x = get<MultiVector>(X, Kind::MultiVector, "multivector");
     MultiVector* w = get<MultiVector>(W, Kind::MultiVector, "multivector");
     Plan* p = plan ? get<Plan>(plan, Kind::Plan, "plan") : nullptr;
-    JP_REQUIRE(w->n == y->n && w->k == y->k, "jp_apply_dot: W must have the shape of Y");
-    JP_REQUIRE(x != y, "apply!: X and Y must be different multivectors");
-    JP_REQUIRE(x->k == y->k, "apply!: X and Y must have the same number of vectors");
     if (y->k == 0) return;
     JP_REQUIRE(out_k != nullptr, "jp_apply_dot: null output");
-    // one kernel when the whole apply is one launch over all row blocks: k = 1, NO_TRANS, no importer
-    const bool fused = mode == JP_NO_TRANS && alpha != 0.0 && y->k == 1 && p == nullptr && w != y && x->n == a->n_cols && y->n == a->n_rows;
-    if (fused) {
-      double* dev = launch_spmv_dot(*a, x->d(), y->d(), alpha, beta, w->d(), ctx().compute);
-      mv_finish_reduction(*c, dev, 1, out_k);
-      return;
-    }
-    // multi-GPU, k = 1, peer-memory halo: the fused halo + SpMV kernel carries the dot product as well.  Opt-in
-    // (JP_FUSED_DOT=1) until it has been run on several GPUs; the conditions are those of apply_no_trans' fused path,
-    // and the peer-memory plan must already be active (the plain jp_apply sets it up collectively).
-    static const bool fused_dot_enabled = []() {
-      const char* v = std::getenv("JP_FUSED_DOT");
-      return v && *v == '1';
-    }();
-    if (fused_dot_enabled && mode == JP_NO_TRANS && alpha != 0.0 && y->k == 1 && p != nullptr && w != y && y->n == a->n_rows &&
-        x->n == p->n_src && p->n_tgt == a->n_cols && p->remote_is_tail && p->n_permute == 0 && p->num_same == a->n_local_cols &&
-        p->num_same == x->n && p->num_same + p->n_remote == a->n_cols && p->p2p_state == 1 && p->p2p_k == 1) {
-      FusedHalo h;
-      h.lids = p->export_lids.as<int32_t>();
-      h.n_export = p->n_export;
-      h.sends = p->send_table.as<P2PSend>();
-      h.n_sends = p->n_send_blocks;
-      h.sources = p->wait_table.as<P2PSource>();
-      h.n_sources = p->n_sources;
-      h.epoch = ++p->epoch;
-      h.tickets = p->p2p_tickets.as<unsigned int>();
-      h.timeout_flag = p2p_timeout_flag_device();
-      const double* halo = reinterpret_cast<const double*>(static_cast<const char*>(p->arena.p) + kArenaFlagBytes);
-      double* dev = launch_spmv_fused_dot(*a, h, x->d(), halo, y->d(), alpha, beta, w->d(), ctx().compute);
-      mv_finish_reduction(*c, dev, 1, out_k);
-      return;
-    }
-    apply_impl(a, p, y, x, mode, alpha, beta);
-    double* dev = mv_dot_local(*w, *y);  // stream-ordered after the apply: no host round trip in between
+    double* dev = apply_dot_local(a, p, y, x, w, mode, alpha, beta);
     mv_finish_reduction(*c, dev, y->k, out_k);
   });
 }

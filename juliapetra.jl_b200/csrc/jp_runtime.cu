@@ -56,6 +56,13 @@ unsigned long long* p2p_timeout_flag_device() {
   return c.p2p_timeout_dev;
 }
 
+void retire_arena(DeviceBuffer& arena) {
+  if (!arena.p) return;
+  ctx().retired_arenas.push_back(arena.p);
+  arena.p = nullptr;
+  arena.bytes = 0;
+}
+
 void check_p2p_health() {
   Context& c = ctx();
   if (c.p2p_timeout_host && *reinterpret_cast<volatile unsigned long long*>(c.p2p_timeout_host) != 0) {
@@ -188,6 +195,8 @@ int32_t jp_finalize(void) {
     if (c.flush_buf) cudaFree(c.flush_buf);
     if (c.p2p_timeout_host) cudaFreeHost(c.p2p_timeout_host);
     c.p2p_timeout_host = c.p2p_timeout_dev = nullptr;
+    for (void* a : c.retired_arenas) cudaFree(a);  // every plan is gone: nobody publishes into a peer's arena any more
+    c.retired_arenas.clear();
     c.scratch = c.host_scratch = c.flush_buf = nullptr;
     c.scratch_bytes = c.host_scratch_bytes = c.flush_bytes = 0;
     cudaEventDestroy(c.ev_x_ready);
@@ -286,8 +295,6 @@ int32_t jp_flush_l2(int64_t bytes) {
     size_t want = bytes > 0 ? (size_t)bytes : (size_t)256 << 20;
     if (want > c.flush_bytes) {
       if (c.flush_buf) cudaFree(c.flush_buf);
-    if (c.p2p_timeout_host) cudaFreeHost(c.p2p_timeout_host);
-    c.p2p_timeout_host = c.p2p_timeout_dev = nullptr;
       JP_CUDA(cudaMalloc(&c.flush_buf, want));
       c.flush_bytes = want;
     }

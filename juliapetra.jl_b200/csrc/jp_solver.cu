@@ -1,4 +1,4 @@
-// jp_solver.cu -- device-resident scalars for solver loops (round-2 candidate; SURVEY.md 8f item 3, BASELINE configs[4]).
+// jp_solver.cu -- device-resident scalars for solver loops (BASELINE configs[4]).
 //
 // The reference's API returns every dot / norm to the host (src/MultiVector.jl:84-146), so a CG iteration written
 // against it synchronises the host with the GPU twice, ~26 us each on one GPU plus an allreduce latency on several --
@@ -8,8 +8,6 @@
 // then pure stream work (and CUDA-graph capturable); the host looks at the residual every few iterations
 // (jp_scalars_download).  The arithmetic is the one of the host-scalar calls: same kernels for the reductions, the
 // same unfused update, the quotient formed once per thread instead of once on the host.
-//
-// Written after round 1's GPU budget was spent: verified on the CPU model of the kernels, not yet run on a GPU.
 #include "jp_common.h"
 #include "jp_solver_kernels.cuh"
 
@@ -135,19 +133,8 @@ int32_t jp_apply_dot_dev(jp_handle comm, jp_handle Y, jp_handle A, jp_handle X, 
     Scalars* sc = scalars(s);
     check_slot(*sc, slot, "jp_apply_dot_dev");
     JP_REQUIRE(x != y && x->k == 1 && y->k == 1 && w->k == 1 && w->n == y->n, "jp_apply_dot_dev: single vectors, X != Y, W shaped like Y");
-    double* dev = nullptr;
-    const bool fused = alpha != 0.0 && plan == 0 && w != y && x->n == a->n_cols && y->n == a->n_rows;
-    if (fused) {
-      dev = launch_spmv_dot(*a, x->d(), y->d(), alpha, beta, w->d(), ctx().compute);
-    } else {
-      const int32_t rc = jp_apply(comm, Y, A, X, plan, JP_NO_TRANS, alpha, beta);  // any halo implementation
-      if (rc != JP_OK) {
-        char buf[512];
-        jp_last_error(buf, sizeof buf);
-        fail(rc, buf);
-      }
-      dev = mv_dot_local(*w, *y);
-    }
+    Plan* p = plan ? get<Plan>(plan, Kind::Plan, "plan") : nullptr;
+    double* dev = apply_dot_local(a, p, y, x, w, JP_NO_TRANS, alpha, beta);  // one kernel with or without a peer-memory halo
     JP_CUDA(cudaMemcpyAsync(sc->d() + slot, dev, 8, cudaMemcpyDeviceToDevice, ctx().compute));
     comm_allreduce_device(*c, sc->d() + slot, 1, ctx().compute);
   });

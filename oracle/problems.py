@@ -23,8 +23,9 @@ def global_rows(kind, N):
     return N if kind == "powerlaw" else N ** _synthetic().STENCILS[kind][0]
 
 
-def oracle_problem(kind, N, P, chunk_rows=1 << 21, **kw):
-    """(comm, rowMap, filled OMatrix) for P simulated ranks, rows split by BlockMap(n, comm)"""
+def oracle_problem(kind, N, P, chunk_rows=1 << 21, abs_vals=False, **kw):
+    """(comm, rowMap, filled OMatrix) for P simulated ranks, rows split by BlockMap(n, comm); abs_vals=True builds |A|
+    (same structure, absolute values: the operator of the component-wise error bounds)"""
     s = _synthetic()
     c = OComm(P)
     n = global_rows(kind, N)
@@ -43,7 +44,7 @@ def oracle_problem(kind, N, P, chunk_rows=1 << 21, **kw):
         while lo <= last and info["numMyElements"] > 0:
             hi = min(last, lo + chunk_rows - 1)
             rows, rp, cols, vals = problem_rows(kind, N, lo, hi, **kw)
-            A.insert_rows(pid, rows, rp, cols, vals)
+            A.insert_rows(pid, rows, rp, cols, np.abs(vals) if abs_vals else vals)
             lo = hi + 1
     A.fill_complete(m, m)
     return c, m, A

@@ -19,6 +19,12 @@ def test_reference_arm_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 2 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["nnz"] == 7 * 24 ** 3 - 6 * 24 ** 2
+    assert d["steps"] == 2 and d["warmup"] == 1  # the arm honours --steps / --warmup
+    # the config object is the product arm's, key for key
+    sys.path.insert(0, ROOT)
+    import bench
+    spec = bench.workload_spec(type("A", (), {"workload": "7pt-24", "rows": 0})())
+    assert d["config"] == bench.bench_config(spec, d["config"]["nnz"], 1, 1)
 
 
 def test_reference_arm_non_root_ranks_exit_quietly():

@@ -32,7 +32,6 @@ def test_header_is_c_and_library_fails_loudly_without_a_gpu(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("JP_TEST_UNVALIDATED") != "1", reason="not yet run on a GPU (set JP_TEST_UNVALIDATED=1)")
 def test_c_program_runs_the_reference_2x2_apply(tmp_path):
     exe, lib = _build(tmp_path)
     r = subprocess.run([exe, lib], capture_output=True, text=True, timeout=300)

@@ -1,18 +1,14 @@
 """apply! when rangeMap != rowMap (jp_apply_export) on the GPU against the CPU oracle's exporter
 branch (itself checked against a dense operator in tests/test_oracle_golden.py).
 
-NOT YET RUN ON A GPU: the device path is host orchestration of kernels the importer / transposed paths already use,
-written after this round's GPU budget was spent.  The tests are therefore opt-in (JP_TEST_UNVALIDATED=1) until the first
-GPU call of the next round has run them; the multi-rank case lives in tests/multi_gpu_cases.py behind the same switch."""
-import os
-
+The device path is host orchestration of kernels the importer / transposed paths already use; the multi-rank case lives in
+tests/multi_gpu_cases.py."""
 import numpy as np
 import pytest
 
 from helpers import O, jp
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("JP_TEST_UNVALIDATED") != "1", reason="device path not yet validated on a GPU (set JP_TEST_UNVALIDATED=1)")]
+pytestmark = pytest.mark.gpu
 
 
 def _serial_permuted_problem(n, seed):

@@ -82,8 +82,6 @@ def test_cg_fused_and_unfused_solve_the_laplacian():
     assert abs(results[0][0] - results[1][0]) <= 1
 
 
-@pytest.mark.skipif(__import__("os").environ.get("JP_TEST_UNVALIDATED") != "1",
-                    reason="the device-resident-scalar solver calls have not been run on a GPU yet (set JP_TEST_UNVALIDATED=1)")
 def test_cg_with_device_resident_scalars():
     """jp_*_dev: CG without host round trips inside the iteration against the host-scalar CG and the known solution"""
     m, n, A = _serial_problem("7pt", 16)

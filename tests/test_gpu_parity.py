@@ -475,8 +475,6 @@ def test_spmm_run_staged_path(monkeypatch, kind, N, k, kt, rows_threads):
     assert info["runs_state"] == 1 and info["runs_blocks"] > 0, info  # the run-staged kernel really ran
 
 
-@pytest.mark.skipif(__import__("os").environ.get("JP_TEST_UNVALIDATED") != "1",
-                    reason="spmm_runs_db_kernel has not been run on a GPU yet (set JP_TEST_UNVALIDATED=1)")
 @pytest.mark.parametrize("rows_threads", [("128", "128"), ("64", "256")])
 @pytest.mark.parametrize("kind,N,k", [("27pt", 20, 8), ("27pt", 20, 11), ("27pt", 12, 32)])
 def test_spmm_double_buffered_tiles(monkeypatch, kind, N, k, rows_threads):
