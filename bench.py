@@ -360,7 +360,7 @@ def main():
     for _ in range(warmup):
         step()
     _lib.check(lib.jp_event_record(ev1))
-    est_ms = max(elapsed(ev0, ev1) / warmup, 1e-3)
+    est_ms = max(max_over_ranks(elapsed(ev0, ev1)) / warmup, 1e-3)  # the SAME number on every rank: applies are collective
     # aligning steps: ~20 ms of the same step (at least 10, at most 512 = well inside the launch queue), so the clocks are
     # up, every rank is paced by its neighbours' halo flags, and the host runs ahead of the device when the window opens
     align = 0 if flush else int(min(512, max(10, 20.0 / est_ms)))

@@ -206,6 +206,8 @@ struct Csr : Object {
   // cache of the column-map multivector (A.importMV, src/CSRMatrix.jl:10,772-781); only used when the column
   // map is not [domain prefix | remote tail] and the fused apply path does not apply
   std::unique_ptr<MultiVector> import_mv;
+  // A^T as a device CSR of its own, built at the first transposed apply (jp_transpose.cu)
+  std::unique_ptr<Csr> transposed;
   // cache of the row-map multivector (A.exportMV, src/CSRMatrix.jl:11): the exporter branch of apply! (rangeMap != rowMap)
   std::unique_ptr<MultiVector> export_mv;
   // GIDs of the column map in LID order, kept when the matrix was fill-completed on the device (jp_csr_fill_complete)
@@ -264,7 +266,8 @@ void launch_spmv_blocks(const Csr& A, const void* blocks_int4, int32_t n_blocks,
 void launch_spmv(const Csr& A, const DeviceBuffer& blocks, int32_t n_blocks, bool use_halo, const double* x, int64_t ldx,
                  const double* halo, int32_t halo_k, double* y, int64_t ldy, int32_t k, double alpha, double beta,
                  cudaStream_t stream);
-void launch_spmv_trans(const Csr& A, const double* x, int64_t ldx, double* y, int64_t ldy, int32_t ny, int32_t k, double alpha,
+Csr& csr_transposed(Csr& A);  // builds A.transposed on first use
+void launch_spmv_trans(Csr& A, const double* x, int64_t ldx, double* y, int64_t ldy, int32_t ny, int32_t k, double alpha,
                        double beta, cudaStream_t stream);
 void csr_prepare_spmm(Csr& A);  // builds the SpMM tile / run tables if that has not been decided yet
 void csr_finalize_structure(Csr& A, const std::vector<int32_t>& rp, const std::vector<int32_t>& rowmax);

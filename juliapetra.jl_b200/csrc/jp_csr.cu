@@ -497,23 +497,15 @@ void launch_spmv_blocks(const Csr& A, const void* blocks_int4, int32_t n_blocks,
   JP_LAUNCH_CHECK();
 }
 
-void launch_spmv_trans(const Csr& A, const double* x, int64_t ldx, double* y, int64_t ldy, int32_t ny, int32_t k, double alpha,
-                       double beta, cudaStream_t stream) {
-  if (k == 0) return;
-  // rawY[:, :] *= beta  (src/CSRMatrix.jl:1148), beta==0 overwrites
-  if (ldy == ny) {
-    launch_scale_fill(y, (int64_t)ny * k, beta, stream);
-  } else {
-    for (int v = 0; v < k; ++v) launch_scale_fill(y + (size_t)v * ldy, ny, beta, stream);
-  }
-  if (A.n_rows == 0 || A.nnz == 0) return;
-  int64_t warps = A.n_rows;
-  int64_t blocks = (warps * 32 + kSpmvThreads - 1) / kSpmvThreads;
-  int64_t cap = (int64_t)ctx().sm_count * 16;
-  if (blocks > cap) blocks = cap;
-  spmv_trans_kernel<<<(int)blocks, kSpmvThreads, 0, stream>>>(A.rowptr.as<int32_t>(), A.colind.as<int32_t>(), A.vals.as<double>(), x, ldx,
-                                                               y, ldy, A.n_rows, k, alpha);
-  JP_LAUNCH_CHECK();
+// y (A's column map, ny rows) = beta*y + alpha * A^T * x (x on A's row map): the ordinary row-block kernels on the
+// transposed matrix (jp_transpose.cu) -- no atomics, deterministic, the entries of a column added in ascending row order
+// like the reference's row sweep (src/CSRMatrix.jl:1147-1160)
+void launch_spmv_trans(Csr& A, const double* x, int64_t ldx, double* y, int64_t ldy, int32_t ny, int32_t k, double alpha, double beta,
+                       cudaStream_t stream) {
+  if (k == 0 || ny == 0) return;
+  Csr& T = csr_transposed(A);
+  JP_REQUIRE(ny == T.n_rows, "transposed apply: Y must have one row per column-map entry");
+  launch_spmv(T, T.blocks_all, T.n_blocks_all, false, x, ldx, nullptr, 1, y, ldy, k, alpha, beta, stream);
 }
 
 

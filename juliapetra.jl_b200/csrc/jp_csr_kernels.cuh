@@ -152,6 +152,10 @@ __device__ __forceinline__ double spmv_block(const BlockRange& b, const StageVie
     if (DOT && tid == 0) dacc = __ldg(w + b.row0) * y[b.row0];  // thread 0 wrote y[row0] itself
     return dacc;
   }
+  // DOT: this thread's first weight is requested before the stage is waited for, so its latency is not serialised behind
+  // the row sum (profiles/r2_ncu_spmv_dot_summary.txt: the fused kernel was 33 % slower than the plain SpMV without this)
+  double w_first = 0.0;
+  if (DOT && tid < b.nrows) w_first = __ldg(w + b.row0 + tid);
   stage_block<TMA>(sv, s_bar_p, rowptr, colind, vals, b);
   const int32_t* rp = sv.s_rp + b.rpo;  // rp[r] is a global nonzero index; shared index = rp[r] - a0
   if (b.kind == KIND_DIRECT) {
@@ -166,8 +170,9 @@ __device__ __forceinline__ double spmv_block(const BlockRange& b, const StageVie
         sum = __dadd_rn(sum, __dmul_rn(sv.s_val[i], xv));
       }
       double* yp = y + b.row0 + r;
-      *yp = combine(beta == 0.0 ? 0.0 : *yp, sum, alpha, beta);
-      if (DOT) dacc += __ldg(w + b.row0 + r) * *yp;
+      const double ynew = combine(beta == 0.0 ? 0.0 : *yp, sum, alpha, beta);
+      *yp = ynew;
+      if (DOT) dacc += (r == tid ? w_first : __ldg(w + b.row0 + r)) * ynew;
     }
     return dacc;
   }
@@ -197,8 +202,9 @@ __device__ __forceinline__ double spmv_block(const BlockRange& b, const StageVie
     for (int r = tid; r < b.nrows; r += kSpmvThreads) {
       const int s = rp[r] - b.a0, e = rp[r + 1] - b.a0;
       double* yp = y + b.row0 + r;
-      *yp = combine(beta == 0.0 ? 0.0 : *yp, row_sum_sequential(sv.s_val, s, e), alpha, beta);
-      if (DOT) dacc += __ldg(w + b.row0 + r) * *yp;
+      const double ynew = combine(beta == 0.0 ? 0.0 : *yp, row_sum_sequential(sv.s_val, s, e), alpha, beta);
+      *yp = ynew;
+      if (DOT) dacc += (r == tid ? w_first : __ldg(w + b.row0 + r)) * ynew;
     }
   } else {
     // WARPROW: the block holds at least one long row.  Short rows still go thread-per-row (sequential sum, the
@@ -952,24 +958,6 @@ spmm_runs_db_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restr
       }
     }
     __syncthreads();  // tile buffer t & 1 is free for vector tile t + 2
-  }
-}
-
-// TRANS / CONJ_TRANS (src/CSRMatrix.jl:1147-1160): Y[ind, v] += (alpha * X[row, v]) * val, after Y *= beta.
-// Scatter with fp64 atomics (RED.ADD.F64): the summation order differs from the reference's row sweep, within
-// the 1e-12 contract.  Warp per row, lanes over the row's entries.
-__global__ void __launch_bounds__(kSpmvThreads)
-spmv_trans_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind, const double* __restrict__ vals,
-                  const double* __restrict__ x, int64_t ldx, double* __restrict__ y, int64_t ldy, int32_t n_rows, int32_t k, double alpha) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * kSpmvThreads + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * kSpmvThreads) >> 5;
-  for (int64_t r = warp; r < n_rows; r += nwarps) {
-    const int s = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);
-    for (int v = 0; v < k; ++v) {
-      const double ax = __dmul_rn(alpha, __ldg(x + r + (size_t)v * ldx));
-      for (int i = s + lane; i < e; i += 32) atomicAdd(y + __ldg(colind + i) + (size_t)v * ldy, __dmul_rn(ax, __ldg(vals + i)));
-    }
   }
 }
 

@@ -64,15 +64,64 @@ double* reduce_local(const MultiVector& x, const MultiVector* y, double p) {
   return w.out;
 }
 
-// sumAll of the k local sums + copy to the host (the only synchronising step)
+// sumAll of the k local sums + hand-over to the host (the only synchronising step).  The results travel through
+// host-mapped pinned memory: publish_results_kernel stores them and then a sequence number, the host spins on the
+// sequence number (checking the stream every few thousand polls so that a failed kernel surfaces as an error).
+constexpr int kMappedResults = 1024;  // doubles in the mapped result block; wider multivectors take memcpy + synchronise
+
+struct MappedResults {
+  double* host = nullptr;
+  double* dev = nullptr;
+  unsigned long long* flag_host = nullptr;
+  unsigned long long* flag_dev = nullptr;
+  unsigned long long seq = 0;
+};
+MappedResults g_mapped;
+
+MappedResults& mapped_results() {
+  if (!g_mapped.host) {
+    void* h = nullptr;
+    JP_CUDA(cudaHostAlloc(&h, (size_t)kMappedResults * 8 + 64, cudaHostAllocMapped));
+    std::memset(h, 0, (size_t)kMappedResults * 8 + 64);
+    g_mapped.host = static_cast<double*>(h);
+    g_mapped.flag_host = reinterpret_cast<unsigned long long*>(g_mapped.host + kMappedResults);
+    void* d = nullptr;
+    JP_CUDA(cudaHostGetDevicePointer(&d, h, 0));
+    g_mapped.dev = static_cast<double*>(d);
+    g_mapped.flag_dev = reinterpret_cast<unsigned long long*>(g_mapped.dev + kMappedResults);
+  }
+  return g_mapped;
+}
+
 void finish_reduction(Comm& c, double* dev_out, int32_t k, double* host_out) {
   Context& x = ctx();
   comm_allreduce_device(c, dev_out, k, x.compute);
-  double* pinned = (double*)host_scratch((size_t)k * 8);
-  JP_CUDA(cudaMemcpyAsync(pinned, dev_out, (size_t)k * 8, cudaMemcpyDeviceToHost, x.compute));
-  JP_CUDA(cudaStreamSynchronize(x.compute));
+  if (k > kMappedResults) {
+    double* pinned = (double*)host_scratch((size_t)k * 8);
+    JP_CUDA(cudaMemcpyAsync(pinned, dev_out, (size_t)k * 8, cudaMemcpyDeviceToHost, x.compute));
+    JP_CUDA(cudaStreamSynchronize(x.compute));
+    check_p2p_health();
+    std::memcpy(host_out, pinned, (size_t)k * 8);
+    return;
+  }
+  MappedResults& m = mapped_results();
+  const unsigned long long seq = ++m.seq;
+  publish_results_kernel<<<1, 32, 0, x.compute>>>(dev_out, k, m.dev, m.flag_dev, seq);
+  JP_LAUNCH_CHECK();
+  volatile unsigned long long* flag = m.flag_host;
+  for (unsigned spins = 1; *flag != seq; ++spins) {
+    if ((spins & 0xfff) == 0) {
+      const cudaError_t e = cudaStreamQuery(x.compute);
+      if (e != cudaSuccess && e != cudaErrorNotReady) JP_CUDA(e);
+      if (e == cudaSuccess && *flag != seq) {  // the stream has drained: the store is at most a fence away
+        JP_CUDA(cudaStreamSynchronize(x.compute));
+        if (*flag != seq) fail(JP_CUDA_ERROR, "reduction results did not reach the host");
+      }
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
   check_p2p_health();
-  std::memcpy(host_out, pinned, (size_t)k * 8);
+  for (int32_t v = 0; v < k; ++v) host_out[v] = reinterpret_cast<volatile double*>(m.host)[v];
 }
 
 }  // namespace
@@ -83,6 +132,8 @@ void mv_finish_reduction(Comm& c, double* dev_out, int32_t k, double* host_out) 
 void release_reduce_workspace() {
   g_reduce_buf.release();
   g_reduce_k = 0;
+  if (g_mapped.host) cudaFreeHost(g_mapped.host);
+  g_mapped = MappedResults();
 }
 
 void launch_scale_fill(double* y, int64_t n, double beta, cudaStream_t stream) {

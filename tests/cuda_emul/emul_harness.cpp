@@ -405,31 +405,6 @@ int emul_plan_op(int32_t op, double* mv, int64_t n_mv, double* other, int64_t n_
   return 0;
 }
 
-// ---- localApply TRANS (spmv_trans_kernel): y (n_cols x k) += (alpha * x[row]) * val, y pre-scaled by the caller ----
-int emul_spmv_trans(int32_t n_rows, int32_t n_cols, const int32_t* rowptr, const int32_t* colind, const double* vals, const double* x, double* y,
-                    int32_t k, double alpha, int32_t blocks) {
-  using namespace jp;
-  using namespace jp::csrk;
-  const int64_t nnz = rowptr[n_rows];
-  DeviceBuffer d_rp, d_ci, d_va, d_x, d_y;
-  d_rp.alloc(((size_t)n_rows + 1) * 4);
-  d_ci.alloc((size_t)nnz * 4 + 16);
-  d_va.alloc((size_t)nnz * 8 + 16);
-  d_x.alloc((size_t)n_rows * k * 8 + 64);
-  d_y.alloc((size_t)n_cols * k * 8 + 64);
-  std::memcpy(d_rp.p, rowptr, ((size_t)n_rows + 1) * 4);
-  std::memcpy(d_ci.p, colind, (size_t)nnz * 4);
-  std::memcpy(d_va.p, vals, (size_t)nnz * 8);
-  std::memcpy(d_x.p, x, (size_t)n_rows * k * 8);
-  std::memcpy(d_y.p, y, (size_t)n_cols * k * 8);
-  if (n_rows > 0 && nnz > 0)
-    JP_KLAUNCH(spmv_trans_kernel, (unsigned)blocks, kSpmvThreads, 0, nullptr, d_rp.as<int32_t>(), d_ci.as<int32_t>(), d_va.as<double>(),
-               d_x.as<double>(), (int64_t)n_rows, d_y.as<double>(), (int64_t)n_cols, n_rows, k, alpha);
-  std::memcpy(y, d_y.p, (size_t)n_cols * k * 8);
-  return 0;
-}
-
-
 // ---- update kernels with device-resident coefficients (csrc/jp_solver_kernels.cuh) ----
 // y = a*x + b*y with a = a_scale * s[a_num] / s[a_den] (b likewise); with_norm: also s[out_slot] = sum of squares of the
 // result.  `repeats` launches on one workspace.  y (n doubles) and s (ns doubles) are updated in place.

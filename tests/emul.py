@@ -167,16 +167,16 @@ def plan_op(op, mv, other, lids_a=None, lids_b=None, n_ids=None, blocks=2):
     return m, o
 
 
-def spmv_trans(rowptr0, colind0, vals, x, y, alpha=1.0, blocks=2):
-    """spmv_trans_kernel: y (n_cols, k) += (alpha * x[row]) * val"""
-    rp = np.ascontiguousarray(rowptr0, dtype=np.int32)
-    ci = np.ascontiguousarray(colind0, dtype=np.int32)
-    va = np.ascontiguousarray(vals, dtype=np.float64)
-    xx, yy = _f(x), _f(y)
-    rc = lib().emul_spmv_trans(C.c_int32(len(rp) - 1), C.c_int32(yy.shape[0]), _p(rp), _p(ci), _p(va), _p(xx), _p(yy), C.c_int32(xx.shape[1]),
-                               C.c_double(alpha), C.c_int32(blocks))
-    assert rc == 0
-    return yy
+def transpose_csr(rowptr0, colind0, vals, n_cols):
+    """A^T as CSR the way csrc/jp_transpose.cu builds it: a STABLE sort of the nonzero positions by column index, so the
+    entries of a row of A^T are in ascending row order of A (0-based arrays in, 0-based arrays out)"""
+    rp = np.asarray(rowptr0, dtype=np.int64)
+    ci = np.asarray(colind0, dtype=np.int64)
+    row_of = np.repeat(np.arange(len(rp) - 1, dtype=np.int64), np.diff(rp))
+    order = np.argsort(ci, kind="stable")
+    rpt = np.zeros(n_cols + 1, dtype=np.int64)
+    np.cumsum(np.bincount(ci, minlength=n_cols), out=rpt[1:])
+    return rpt.astype(np.int32), row_of[order].astype(np.int32), np.asarray(vals, dtype=np.float64)[order]
 
 
 def set_schedule(mode: str = "forward", seed: int = 0):

@@ -88,7 +88,9 @@ def test_transposed_local_apply(kind, N, k):
     y0 = synthetic.vector_block(1, n, k, seed=2)
     alpha, beta = 3.0, 0.5
     ref = O.local_apply_raw(y0.copy(order="F"), rp, ci, va, x, O.TRANS, alpha, beta)
-    got = emul.spmv_trans(rp - 1, ci - 1, va, x, y0 * beta, alpha)  # the launcher scales Y first (src/CSRMatrix.jl:1148)
+    # the transposed apply is the row-block kernel on A^T (csrc/jp_transpose.cu builds it by a stable sort by column)
+    rpt, cit, vat = emul.transpose_csr(rp - 1, ci - 1, va, n)
+    got, _ = emul.local_apply(rpt, cit, vat, x, y0, alpha, beta)
     bound = 1e-12 * (alpha * O.local_apply_raw(np.zeros_like(y0), rp, ci, np.abs(va), np.abs(x), O.TRANS, 1.0, 0.0) + beta * np.abs(y0))
     assert (np.abs(got - ref) <= bound + 1e-300).all()
 
@@ -96,5 +98,6 @@ def test_transposed_local_apply(kind, N, k):
 def test_reference_golden_transposed_apply():
     """test/CSRMatrixTests.jl:152-158: A = [[2,3],[5,7]], apply!(Y, A, X, TRANS, 3, 0.5), Y = diag(1,2), X = 2s"""
     rp, ci, va = np.array([0, 2, 4]), np.array([0, 1, 0, 1]), np.array([2.0, 3.0, 5.0, 7.0])
-    y = emul.spmv_trans(rp, ci, va, np.full((2, 2), 2.0), np.array([[1.0, 0.0], [0.0, 2.0]]) * 0.5, 3.0)
+    rpt, cit, vat = emul.transpose_csr(rp, ci, va, 2)
+    y, _ = emul.local_apply(rpt, cit, vat, np.full((2, 2), 2.0), np.array([[1.0, 0.0], [0.0, 2.0]]), 3.0, 0.5)
     assert np.array_equal(y, np.array([[42.5, 42.0], [60.0, 61.0]]))
