@@ -4,10 +4,14 @@
 // The host-array collectives here serve the one-time setup (maps, directories, plan construction); the hot
 // reductions (dot/norm) run on device buffers through comm_allreduce_device().
 #include "jp_common.h"
+#include "jp_p2p.cuh"
 
 namespace jp {
 
 Comm::~Comm() {
+  for (int q = 0; q < (int)ar_peer_host.size(); ++q)
+    if (ar_peer_host[q] && q != rank0) cudaIpcCloseMemHandle(ar_peer_host[q]);
+  retire_arena(ar_arena);  // a peer may still have it mapped
   if (nccl) ncclCommDestroy(nccl);
 }
 
@@ -21,10 +25,135 @@ static ncclRedOp_t nccl_op(int32_t op) {
   return op == JP_SUM ? ncclSum : op == JP_MAX ? ncclMax : ncclMin;
 }
 
+// all-gather of `bytes` host bytes per rank (setup only)
+void allgather_host_bytes(Comm& c, const void* in, size_t bytes, void* out) {
+  Context& x = ctx();
+  char* buf = (char*)scratch(bytes * (c.nproc + 1));
+  JP_CUDA(cudaMemcpyAsync(buf, in, bytes, cudaMemcpyHostToDevice, x.comm));
+  JP_NCCL(ncclAllGather(buf, buf + bytes, bytes, ncclChar, c.nccl, x.comm));
+  JP_CUDA(cudaMemcpyAsync(out, buf + bytes, bytes * c.nproc, cudaMemcpyDeviceToHost, x.comm));
+  JP_CUDA(cudaStreamSynchronize(x.comm));
+}
+
+// min over the ranks of a host integer (setup only): "everybody or nobody" decisions
+int64_t allreduce_min_host(Comm& c, int64_t v) {
+  Context& x = ctx();
+  int64_t out = 0;
+  int64_t* buf = (int64_t*)scratch(16);
+  JP_CUDA(cudaMemcpyAsync(buf, &v, 8, cudaMemcpyHostToDevice, x.comm));
+  JP_NCCL(ncclAllReduce(buf, buf, 1, ncclInt64, ncclMin, c.nccl, x.comm));
+  JP_CUDA(cudaMemcpyAsync(&out, buf, 8, cudaMemcpyDeviceToHost, x.comm));
+  JP_CUDA(cudaStreamSynchronize(x.comm));
+  return out;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Small allreduce over peer memory (the dot / norm scalars of src/MultiVector.jl:107,132: k doubles per call).
+// Arena of rank r:  flags[q] (uint64, q < nproc) = last epoch rank q has stored into r's slots
+//                   slots[parity][q][kSmallAllreduceMax] doubles
+// Call number e (identical on every rank: collectives are ordered) uses parity e & 1.  A rank that is in call e + 2 has
+// seen every peer's flag of call e + 1, and a peer stores its values of call e + 1 only after it has finished reading
+// call e -- so the slots of parity e & 1 are free again: two parities suffice, no ack is needed.
+// The sum is taken in rank order on every rank: all ranks get bit-identical results (like MPI_Allreduce on one node).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kSmallAllreduceMax = 64;
+constexpr int kSmallAllreduceRanks = 64;
+constexpr size_t kArSlotsOffset = 4096;
+
+__global__ void __launch_bounds__(256) allreduce_p2p_kernel(double* __restrict__ inout, int k, int P, int me, char* const* __restrict__ peers,
+                                                            uint64_t epoch, HostSink sink, unsigned long long* timeout_flag) {
+  const int tid = threadIdx.x;
+  const size_t par_off = kArSlotsOffset + (size_t)(epoch & 1) * P * kSmallAllreduceMax * 8;
+  for (int idx = tid; idx < P * k; idx += blockDim.x) {
+    const int q = idx / k, j = idx - q * k;
+    reinterpret_cast<double*>(peers[q] + par_off)[(size_t)me * kSmallAllreduceMax + j] = inout[j];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < P) {
+    st_release_sys(reinterpret_cast<uint64_t*>(peers[tid]) + me, epoch);
+    wait_flag_ge(reinterpret_cast<const uint64_t*>(peers[me]) + tid, epoch, timeout_flag);
+  }
+  __syncthreads();
+  if (tid < k) {
+    const volatile double* slots = reinterpret_cast<const volatile double*>(peers[me] + par_off);
+    double s = 0.0;
+    for (int q = 0; q < P; ++q) s += slots[(size_t)q * kSmallAllreduceMax + tid];
+    inout[tid] = s;
+    if (sink.out) *reinterpret_cast<volatile double*>(sink.out + tid) = s;
+  }
+  if (sink.out) {
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) *reinterpret_cast<volatile unsigned long long*>(sink.flag) = sink.seq;
+  }
+}
+
+// collective, once per comm: arenas, IPC handles, mappings.  False on every rank when any rank cannot take part.
+static bool small_allreduce_setup(Comm& c) {
+  Context& x = ctx();
+  static const bool disabled = []() {
+    const char* v = std::getenv("JP_ALLREDUCE");
+    return v && std::string(v) == "nccl";
+  }();
+  if (disabled) return false;
+  const int P = c.nproc, me = c.rank0;
+  JP_CUDA(cudaStreamSynchronize(x.comm));
+  JP_CUDA(cudaStreamSynchronize(x.compute));
+  int ok = P <= kSmallAllreduceRanks ? 1 : 0;
+  const size_t bytes = kArSlotsOffset + 2 * (size_t)std::min(P, kSmallAllreduceRanks) * kSmallAllreduceMax * 8;
+  c.ar_arena.alloc(bytes);
+  JP_CUDA(cudaMemset(c.ar_arena.p, 0, bytes));
+  cudaIpcMemHandle_t mine;
+  std::memset(&mine, 0, sizeof mine);
+  if (cudaIpcGetMemHandle(&mine, c.ar_arena.p) != cudaSuccess) {
+    cudaGetLastError();
+    ok = 0;
+  }
+  std::vector<cudaIpcMemHandle_t> all(P);
+  allgather_host_bytes(c, &mine, sizeof mine, all.data());
+  c.ar_peer_host.assign(P, nullptr);
+  c.ar_peer_host[me] = c.ar_arena.p;
+  for (int q = 0; q < P && ok; ++q) {
+    if (q == me) continue;
+    void* ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0;
+      break;
+    }
+    c.ar_peer_host[q] = ptr;
+  }
+  if (!allreduce_min_host(c, ok)) {
+    for (int q = 0; q < P; ++q)
+      if (c.ar_peer_host[q] && q != me) cudaIpcCloseMemHandle(c.ar_peer_host[q]);
+    c.ar_peer_host.clear();
+    allreduce_min_host(c, 1);  // every mapping is closed before any arena is released
+    c.ar_arena.release();
+    return false;
+  }
+  c.ar_peers.alloc((size_t)P * sizeof(void*));
+  JP_CUDA(cudaMemcpy(c.ar_peers.p, c.ar_peer_host.data(), (size_t)P * sizeof(void*), cudaMemcpyHostToDevice));
+  c.ar_epoch = 0;
+  allreduce_min_host(c, 1);  // nobody stores into an arena that is not mapped everywhere yet
+  return true;
+}
+
 // sumAll of a device buffer in place (MPI.allreduce(+), src/MPIComm.jl:57-59)
-void comm_allreduce_device(Comm& c, double* buf, int64_t n, cudaStream_t stream) {
-  if (c.serial || n == 0) return;  // src/SerialComm.jl:105-107
+bool comm_allreduce_device(Comm& c, double* buf, int64_t n, cudaStream_t stream, const HostSink* sink) {
+  if (c.serial || n == 0) return false;  // src/SerialComm.jl:105-107
+  if (n <= kSmallAllreduceMax) {
+    if (c.ar_state == 0) c.ar_state = small_allreduce_setup(c) ? 1 : -1;
+    if (c.ar_state == 1) {
+      allreduce_p2p_kernel<<<1, 256, 0, stream>>>(buf, (int)n, c.nproc, c.rank0, c.ar_peers.as<char*>(), ++c.ar_epoch,
+                                                   sink ? *sink : HostSink(), p2p_timeout_flag_device());
+      JP_LAUNCH_CHECK();
+      return sink != nullptr;
+    }
+  }
   JP_NCCL(ncclAllReduce(buf, buf, (size_t)n, ncclDouble, ncclSum, c.nccl, stream));
+  return false;
 }
 
 }  // namespace jp

@@ -538,6 +538,9 @@ void csr_finalize_structure(Csr& A, const std::vector<int32_t>& rp, const std::v
   if (const char* v = std::getenv("JP_SPMV_DIRECT_RATIO"))
     if (*v) rule.ratio = std::atof(v);
   JP_REQUIRE(rule.maxlen >= 1 && rule.ratio >= 1.0, "JP_SPMV_DIRECT_MAXLEN must be >= 1 and JP_SPMV_DIRECT_RATIO >= 1");
+  if (const char* v = std::getenv("JP_SPMV_SUBWARP_DIV"))  // 0: irregular blocks take the two-phase path (A/B measurements)
+    if (*v) rule.subwarp_div = std::atof(v);
+  JP_REQUIRE(rule.subwarp_div >= 0.0, "JP_SPMV_SUBWARP_DIV must be >= 0");
   build_blocks(rp, cls, cap, max_rows, env_int("JP_SPMV_DIRECT", 1) != 0, bi, bb, ba, rule);
   upload_blocks(bi, A.blocks_interior, A.n_blocks_interior);
   upload_blocks(bb, A.blocks_boundary, A.n_blocks_boundary);
@@ -553,6 +556,25 @@ void csr_finalize_structure(Csr& A, const std::vector<int32_t>& rp, const std::v
   for (int c = 0; c < nchunks; ++c) {
     for (int32_t r = A.chunk_row[c]; r < A.chunk_row[c + 1]; ++r) run = std::max(run, rowmax[r]);
     A.chunk_maxcol.push_back(run);
+  }
+  // chunks of the interior list (host-buffer path with an importer)
+  if (!bi.empty() && !bb.empty()) {
+    const int nic = std::max(1, std::min<int>(env_int("JP_HOST_CHUNKS", 16), (int)bi.size()));
+    for (int c = 0; c <= nic; ++c) {
+      const int32_t bidx = (int32_t)((int64_t)bi.size() * c / nic);
+      A.ichunk_block.push_back(bidx);
+      A.ichunk_row.push_back(c == 0 ? 0 : (bidx < (int32_t)bi.size() ? bi[bidx].row0 : n_rows));
+    }
+    int32_t irun = -1;
+    for (int c = 0; c < nic; ++c) {
+      uint8_t hasb = 0;
+      for (int32_t r = A.ichunk_row[c]; r < A.ichunk_row[c + 1]; ++r) {
+        if (cls[r]) hasb = 1;
+        else irun = std::max(irun, rowmax[r]);
+      }
+      A.ichunk_maxcol.push_back(irun);
+      A.ichunk_has_boundary.push_back(hasb);
+    }
   }
 }
 

@@ -21,6 +21,9 @@ inline size_t stage_smem_bytes(int cap) { return (size_t)(cap + 8) * 12 + (size_
 struct DirectRule {
   int32_t maxlen = 32;
   double ratio = 2.0;
+  // irregular blocks: 0 = TWOPHASE / WARPROW (products through shared memory), otherwise KIND_SUBWARP with
+  // T = the largest power of two <= mean row length of the block / subwarp_div lanes per row (2 <= T <= 32)
+  double subwarp_div = 1.5;
 };
 
 inline void build_blocks(const std::vector<int32_t>& rp, const std::vector<uint8_t>& cls, int32_t cap, int32_t max_rows, bool allow_direct,
@@ -43,7 +46,12 @@ inline void build_blocks(const std::vector<int32_t>& rp, const std::vector<uint8
       const int64_t nrows = r - start, nnzb = rp[r] - nnz0;
       // near-uniform short rows: max <= 2 * mean  ->  thread-per-row straight from the stage
       if (allow_direct && maxlen <= rule.maxlen && (double)maxlen * (double)nrows <= rule.ratio * (double)nnzb + 32.0) kind = KIND_DIRECT;
-      else kind = maxlen > kLongRowLen ? KIND_WARPROW : KIND_TWOPHASE;
+      else if (rule.subwarp_div > 0.0) {
+        const double target = (double)nnzb / (double)std::max<int64_t>(nrows, 1) / rule.subwarp_div;
+        int lg = 1;
+        while (lg < 5 && (double)(2 << lg) <= target) ++lg;
+        kind = KIND_SUBWARP | (lg << 4);  // shifted by 16 below: the lane count lands in bits 20..23
+      } else kind = maxlen > kLongRowLen ? KIND_WARPROW : KIND_TWOPHASE;
     }
     BlockDesc b;
     b.row0 = start;
@@ -76,7 +84,7 @@ inline bool build_tile_tables(const std::vector<int32_t>& ci, std::vector<BlockD
     for (size_t bi = tix; bi < nb; bi += nthreads) {
       BlockDesc& b = all[bi];
       b.ucount = 0;
-      if ((b.nrows_kind >> 16) == KIND_LONGROW) {
+      if (((b.nrows_kind >> 16) & 0xf) == KIND_LONGROW) {
         has_longrow = true;  // (benign race: only ever set to true)
         continue;
       }
@@ -136,7 +144,7 @@ inline bool build_run_tables(const std::vector<int32_t>& ci, std::vector<BlockDe
   std::vector<int32_t> width(nb, 0), ncopied(nb, 0);
   const int nthreads = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
   for (const BlockDesc& b : all)
-    if ((b.nrows_kind >> 16) == KIND_LONGROW) return false;
+    if (((b.nrows_kind >> 16) & 0xf) == KIND_LONGROW) return false;
   // cheap early answer for matrices that are not banded (a random 10^9-nonzero matrix must not pay a full sort of
   // every block just to be turned away): distinct aligned column pairs of up to 256 evenly spaced blocks
   {

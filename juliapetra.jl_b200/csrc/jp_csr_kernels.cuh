@@ -14,7 +14,9 @@ constexpr int kSpmvThreads = 256;
 constexpr int kMaxRowsPerBlock = 512;   // rows staged per block (row pointers in shared memory)
 constexpr int kLongRowLen = 64;         // blocks holding a row longer than this reduce warp-per-row
 
-enum BlockKind : int { KIND_DIRECT = 0, KIND_TWOPHASE = 1, KIND_WARPROW = 2, KIND_LONGROW = 3 };
+// KIND_SUBWARP carries log2(lanes per row) in bits 20..23 of BlockDesc::nrows_kind
+enum BlockKind : int { KIND_DIRECT = 0, KIND_TWOPHASE = 1, KIND_WARPROW = 2, KIND_LONGROW = 3, KIND_SUBWARP = 4 };
+constexpr int kSubwarpLongFactor = 16;  // SUBWARP blocks: rows longer than this many passes of their lane group go warp-per-row
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -58,6 +60,7 @@ __device__ __forceinline__ StageView stage_view(unsigned char* smem, int cap) {
 
 struct BlockRange {
   int row0, nrows, kind, p0, p1;
+  int lg;   // KIND_SUBWARP: log2 of the lanes per row
   int a0;   // 4-aligned first staged nonzero: shared index of nonzero i is i - a0
   int rpo;  // shared index of row r's pointer is rpo + r
 };
@@ -67,7 +70,8 @@ __device__ __forceinline__ BlockRange decode_block(const BlockDesc* __restrict__
   BlockRange b;
   b.row0 = blk.x;
   b.nrows = blk.y & 0xffff;
-  b.kind = blk.y >> 16;
+  b.kind = (blk.y >> 16) & 0xf;
+  b.lg = (blk.y >> 20) & 0xf;
   b.p0 = blk.z;
   b.p1 = blk.w;
   b.a0 = b.p0 & ~3;
@@ -173,6 +177,94 @@ __device__ __forceinline__ double spmv_block(const BlockRange& b, const StageVie
       const double ynew = combine(beta == 0.0 ? 0.0 : *yp, sum, alpha, beta);
       *yp = ynew;
       if (DOT) dacc += (r == tid ? w_first : __ldg(w + b.row0 + r)) * ynew;
+    }
+    return dacc;
+  }
+  if (b.kind == KIND_SUBWARP) {
+    // T = 2^lg lanes per row straight out of the stage: no product round trip through shared memory, no second block
+    // barrier.  Lanes of a group read consecutive staged entries (conflict-free), gather x, and the group adds up with
+    // log2(T) shuffles; every group works on TWO rows at a time so that two gathers per thread are in flight.  Rows much
+    // longer than the group (heavy tail) are left to whole warps in a second pass.
+    const int T = 1 << b.lg, lane_t = tid & (T - 1), grp = tid >> b.lg, ngrp = kSpmvThreads >> b.lg;
+    const int longlen = kSubwarpLongFactor * T;
+    const uint64_t pol_x = policy_evict_last();
+    bool any_long = false;
+    for (int rbase = 0; rbase < b.nrows; rbase += 2 * ngrp) {  // warp-uniform trip count (shuffles below)
+      const int ra = rbase + grp, rb = ra + ngrp;
+      int ia = 0, ea = 0, ib = 0, eb = 0;
+      bool wa = ra < b.nrows, wb = rb < b.nrows;  // this group writes y[ra] / y[rb] in this pass
+      if (wa) {
+        ia = rp[ra] - b.a0;
+        ea = rp[ra + 1] - b.a0;
+        if (ea - ia > longlen) { ea = ia; wa = false; any_long = true; }
+      }
+      if (wb) {
+        ib = rp[rb] - b.a0;
+        eb = rp[rb + 1] - b.a0;
+        if (eb - ib > longlen) { eb = ib; wb = false; any_long = true; }
+      }
+      double acca = 0.0, accb = 0.0;
+      ia += lane_t;
+      ib += lane_t;
+      while (ia < ea || ib < eb) {
+        if (ia < ea) {
+          const int c = sv.s_col[ia];
+          const double xv = (HALO && c >= nloc) ? halo[c - nloc] : ldg_gather(x + c, pol_x);
+          acca = fma(sv.s_val[ia], xv, acca);
+          ia += T;
+        }
+        if (ib < eb) {
+          const int c = sv.s_col[ib];
+          const double xv = (HALO && c >= nloc) ? halo[c - nloc] : ldg_gather(x + c, pol_x);
+          accb = fma(sv.s_val[ib], xv, accb);
+          ib += T;
+        }
+      }
+      for (int o = T >> 1; o > 0; o >>= 1) {
+        acca += __shfl_xor_sync(0xffffffffu, acca, o);
+        accb += __shfl_xor_sync(0xffffffffu, accb, o);
+      }
+      if (lane_t == 0) {
+        if (wa) {
+          double* yp = y + b.row0 + ra;
+          const double ynew = combine(beta == 0.0 ? 0.0 : *yp, acca, alpha, beta);
+          *yp = ynew;
+          if (DOT) dacc += __ldg(w + b.row0 + ra) * ynew;
+        }
+        if (wb) {
+          double* yp = y + b.row0 + rb;
+          const double ynew = combine(beta == 0.0 ? 0.0 : *yp, accb, alpha, beta);
+          *yp = ynew;
+          if (DOT) dacc += __ldg(w + b.row0 + rb) * ynew;
+        }
+      }
+    }
+    if (__syncthreads_or(any_long)) {
+      const int lane = tid & 31, warp = tid >> 5;
+      for (int r = warp; r < b.nrows; r += kSpmvThreads / 32) {
+        const int s = rp[r] - b.a0, e = rp[r + 1] - b.a0;
+        if (e - s <= longlen) continue;  // warp-uniform
+        double a0 = 0.0, a1 = 0.0;
+        int i = s + lane;
+        for (; i + 32 < e; i += 64) {
+          const int c0 = sv.s_col[i], c1 = sv.s_col[i + 32];
+          const double x0 = (HALO && c0 >= nloc) ? halo[c0 - nloc] : ldg_gather(x + c0, pol_x);
+          const double x1 = (HALO && c1 >= nloc) ? halo[c1 - nloc] : ldg_gather(x + c1, pol_x);
+          a0 = fma(sv.s_val[i], x0, a0);
+          a1 = fma(sv.s_val[i + 32], x1, a1);
+        }
+        if (i < e) {
+          const int c0 = sv.s_col[i];
+          a0 = fma(sv.s_val[i], (HALO && c0 >= nloc) ? halo[c0 - nloc] : ldg_gather(x + c0, pol_x), a0);
+        }
+        const double sum = warp_sum(a0 + a1);
+        if (lane == 0) {
+          double* yp = y + b.row0 + r;
+          const double ynew = combine(beta == 0.0 ? 0.0 : *yp, sum, alpha, beta);
+          *yp = ynew;
+          if (DOT) dacc += __ldg(w + b.row0 + r) * ynew;
+        }
+      }
     }
     return dacc;
   }
@@ -323,7 +415,7 @@ spmm_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ ro
   stage_block<TMA>(sv, &s_bar, rowptr, colind, vals, b);
   const int32_t* rp = sv.s_rp + b.rpo;
   // blocks holding long rows use a full warp per row; otherwise T lanes per row from the matrix statistics
-  const int Tb = b.kind == KIND_WARPROW ? 32 : T;
+  const int Tb = b.kind == KIND_WARPROW ? 32 : (b.kind == KIND_SUBWARP && (1 << b.lg) > T) ? (1 << b.lg) : T;
   const int lane_t = tid & (Tb - 1), group = tid / Tb, ngroups = kSpmvThreads / Tb;
   for (int v0 = 0; v0 < k; v0 += KT) {
     const int kt = k - v0 < KT ? k - v0 : KT;  // warp-uniform

@@ -95,8 +95,8 @@ MappedResults& mapped_results() {
 
 void finish_reduction(Comm& c, double* dev_out, int32_t k, double* host_out) {
   Context& x = ctx();
-  comm_allreduce_device(c, dev_out, k, x.compute);
   if (k > kMappedResults) {
+    comm_allreduce_device(c, dev_out, k, x.compute);
     double* pinned = (double*)host_scratch((size_t)k * 8);
     JP_CUDA(cudaMemcpyAsync(pinned, dev_out, (size_t)k * 8, cudaMemcpyDeviceToHost, x.compute));
     JP_CUDA(cudaStreamSynchronize(x.compute));
@@ -106,8 +106,14 @@ void finish_reduction(Comm& c, double* dev_out, int32_t k, double* host_out) {
   }
   MappedResults& m = mapped_results();
   const unsigned long long seq = ++m.seq;
-  publish_results_kernel<<<1, 32, 0, x.compute>>>(dev_out, k, m.dev, m.flag_dev, seq);
-  JP_LAUNCH_CHECK();
+  HostSink sink;
+  sink.out = m.dev;
+  sink.flag = m.flag_dev;
+  sink.seq = seq;
+  if (!comm_allreduce_device(c, dev_out, k, x.compute, &sink)) {  // the peer-memory allreduce kernel hands over by itself
+    publish_results_kernel<<<1, 32, 0, x.compute>>>(dev_out, k, m.dev, m.flag_dev, seq);
+    JP_LAUNCH_CHECK();
+  }
   volatile unsigned long long* flag = m.flag_host;
   for (unsigned spins = 1; *flag != seq; ++spins) {
     if ((spins & 0xfff) == 0) {

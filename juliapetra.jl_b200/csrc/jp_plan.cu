@@ -135,28 +135,6 @@ __global__ void halo_ack_kernel(const P2PSource* __restrict__ sources, int32_t n
   if ((int)threadIdx.x < n_sources) st_release_sys(sources[threadIdx.x].ack_flag, epoch);
 }
 
-// all-gather of `bytes` host bytes per rank (setup only)
-void allgather_host_bytes(Comm& c, const void* in, size_t bytes, void* out) {
-  Context& x = ctx();
-  char* buf = (char*)scratch(bytes * (c.nproc + 1));
-  JP_CUDA(cudaMemcpyAsync(buf, in, bytes, cudaMemcpyHostToDevice, x.comm));
-  JP_NCCL(ncclAllGather(buf, buf + bytes, bytes, ncclChar, c.nccl, x.comm));
-  JP_CUDA(cudaMemcpyAsync(out, buf + bytes, bytes * c.nproc, cudaMemcpyDeviceToHost, x.comm));
-  JP_CUDA(cudaStreamSynchronize(x.comm));
-}
-
-// min over the ranks of a host integer (setup only): "everybody or nobody" decisions
-int64_t allreduce_min_host(Comm& c, int64_t v) {
-  Context& x = ctx();
-  int64_t out = 0;
-  int64_t* buf = (int64_t*)scratch(16);
-  JP_CUDA(cudaMemcpyAsync(buf, &v, 8, cudaMemcpyHostToDevice, x.comm));
-  JP_NCCL(ncclAllReduce(buf, buf, 1, ncclInt64, ncclMin, c.nccl, x.comm));
-  JP_CUDA(cudaMemcpyAsync(&out, buf, 8, cudaMemcpyDeviceToHost, x.comm));
-  JP_CUDA(cudaStreamSynchronize(x.comm));
-  return out;
-}
-
 void close_peer_mappings(Plan& p) {
   const int me = p.comm ? p.comm->rank0 : -1;
   for (int q = 0; q < (int)p.peer_arena.size(); ++q)
@@ -881,11 +859,86 @@ int32_t jp_apply_host(jp_handle comm, jp_handle A, jp_handle plan, const double*
       const char* v = std::getenv("JP_HOST_PIPELINE");
       return !(v && *v == '0');
     }();
+    // below this many bytes of X the chunked pipeline is not worth its events (the tests lower it to cover the pipeline)
+    static const size_t pipeline_min_bytes = []() {
+      const char* v = std::getenv("JP_HOST_PIPELINE_MIN_BYTES");
+      return (v && *v) ? (size_t)std::atoll(v) : ((size_t)4 << 20);
+    }();
     // The run-staged SpMM kernel works on its own row blocks, not on chunks of the all-blocks list; when a matrix takes
     // it, a k > 1 host apply is one launch (like jp_apply), so both entry points give bit-identical results.
     if (k > 1 && !trans) csr_prepare_spmm(*a);
-    const bool pipelined = pipeline_enabled && !trans && p == nullptr && beta == 0.0 && alpha != 0.0 && nch > 1 && xb >= ((size_t)4 << 20) &&
+    const bool pipelined = pipeline_enabled && !trans && p == nullptr && beta == 0.0 && alpha != 0.0 && nch > 1 && xb >= pipeline_min_bytes &&
                            nx == a->n_cols && ny == a->n_rows && (k == 1 || a->runs_state != 1);
+    // With an importer whose halo lands in place (the multi-GPU bench path): the same three-stream pipeline.  X goes up
+    // in chunks on the comm stream, which then carries the halo exchange (pack + peer stores / NCCL) and the boundary
+    // rows; the interior rows run chunk by chunk on the compute stream as their columns arrive; every chunk of Y goes
+    // down on the copy stream as soon as the kernels that write it are done, while later pieces of X are still coming up.
+    const int nic = (int)a->ichunk_maxcol.size();
+    const bool plan_pipelined = pipeline_enabled && !trans && p != nullptr && beta == 0.0 && alpha != 0.0 && nic > 1 &&
+                                xb >= pipeline_min_bytes && ny == a->n_rows && nx == p->n_src && p->n_tgt == a->n_cols && halo_in_place(a, p, x) &&
+                                (k == 1 || a->runs_state != 1);
+    if (plan_pipelined) {
+      while ((int)g_host_events.size() < 2 * std::max(nch, nic) + 1) {
+        cudaEvent_t e;
+        JP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        g_host_events.push_back(e);
+      }
+      cudaStream_t h2d = c.comm, comp = c.compute, d2h = c.copy;
+      JP_CUDA(cudaEventRecord(c.ev_tmp, comp));  // order after whatever the compute stream was doing
+      JP_CUDA(cudaStreamWaitEvent(h2d, c.ev_tmp, 0));
+      std::vector<int32_t> xr(nic + 1);
+      for (int i = 0; i <= nic; ++i) xr[i] = (int32_t)((int64_t)nx * i / nic);
+      for (int i = 0; i < nic; ++i) {
+        const size_t w = (size_t)(xr[i + 1] - xr[i]) * 8;
+        if (w)
+          JP_CUDA(cudaMemcpy2DAsync(x->d() + xr[i], (size_t)nx * 8, x_host + xr[i], (size_t)nx * 8, w, (size_t)k, cudaMemcpyHostToDevice, h2d));
+        JP_CUDA(cudaEventRecord(g_host_events[i], h2d));
+      }
+      // comm stream, behind the last piece of X: halo exchange, then the boundary rows
+      plan_ensure_buffers(*p, k);
+      const double* halo = plan_post_p2p(*p, *x);  // nullptr -> NCCL send/recv
+      const bool p2p = halo != nullptr;
+      if (!p2p) {
+        plan_post(*p, *x, nullptr, /*halo_only=*/true, JP_INSERT, false);
+        halo = p->recvbuf.as<double>();
+      }
+      launch_spmv(*a, a->blocks_boundary, a->n_blocks_boundary, true, x->d(), nx, halo, k, y->d(), ny, k, alpha, beta, c.comm);
+      if (p2p) plan_p2p_ack(*p);
+      cudaEvent_t ev_boundary = g_host_events[2 * nic];
+      JP_CUDA(cudaEventRecord(ev_boundary, c.comm));
+      const char* iblocks = static_cast<const char*>(a->blocks_interior.p);
+      int uploaded_chunk = -1;
+      for (int ch = 0; ch < nic; ++ch) {
+        const int32_t need = a->ichunk_maxcol[ch];
+        int want = 0;
+        while (want < nic - 1 && xr[want + 1] <= need) ++want;
+        if (want > uploaded_chunk) {
+          JP_CUDA(cudaStreamWaitEvent(comp, g_host_events[want], 0));
+          uploaded_chunk = want;
+        }
+        const int32_t b0 = a->ichunk_block[ch], b1 = a->ichunk_block[ch + 1];
+        launch_spmv_blocks(*a, iblocks + (size_t)b0 * kBlockDescBytes, b1 - b0, false, x->d(), nx, nullptr, 1, y->d(), ny, k, alpha, beta, comp);
+        JP_CUDA(cudaEventRecord(g_host_events[nic + ch], comp));
+      }
+      // the chunks without boundary rows go down first (the boundary rows finish last: they need the whole of X and the halo)
+      for (int pass = 0; pass < 2; ++pass)
+        for (int ch = 0; ch < nic; ++ch) {
+          if ((a->ichunk_has_boundary[ch] != 0) != (pass == 1)) continue;
+          JP_CUDA(cudaStreamWaitEvent(d2h, g_host_events[nic + ch], 0));
+          if (pass == 1) JP_CUDA(cudaStreamWaitEvent(d2h, ev_boundary, 0));
+          const int32_t r0 = a->ichunk_row[ch], r1 = a->ichunk_row[ch + 1];
+          if (r1 > r0)
+            JP_CUDA(cudaMemcpy2DAsync(y_host + r0, (size_t)ny * 8, y->d() + r0, (size_t)ny * 8, (size_t)(r1 - r0) * 8, (size_t)k,
+                                      cudaMemcpyDeviceToHost, d2h));
+        }
+      JP_CUDA(cudaStreamSynchronize(d2h));
+      JP_CUDA(cudaStreamSynchronize(comp));
+      JP_CUDA(cudaStreamSynchronize(h2d));
+      JP_CUDA(cudaEventRecord(c.ev_tmp, c.comm));  // later compute-stream work is ordered after the halo traffic of this call
+      JP_CUDA(cudaStreamWaitEvent(comp, c.ev_tmp, 0));
+      check_p2p_health();
+      return;
+    }
     if (!pipelined) {
       if (xb) JP_CUDA(cudaMemcpyAsync(x->d(), x_host, xb, cudaMemcpyHostToDevice, c.compute));
       if (beta != 0.0 && yb) JP_CUDA(cudaMemcpyAsync(y->d(), y_host, yb, cudaMemcpyHostToDevice, c.compute));

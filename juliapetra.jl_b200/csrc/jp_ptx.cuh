@@ -55,6 +55,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(pol)
                : "memory");
 }
+// gather of one multivector entry by an irregular row: read-only path, no L1 allocation (no reuse inside the block) and an
+// L2 evict-last hint -- x is what should stay in the L2, the matrix stream passes through with evict-first
+__device__ __forceinline__ double ldg_gather(const double* p, uint64_t pol) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;\n" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_addr(bar)) : "memory");
 }
@@ -109,6 +116,7 @@ inline void mbar_wait(uint64_t* bar, unsigned parity) {  // returns once the pha
 }
 inline uint64_t policy_evict_first() { return 0; }
 inline uint64_t policy_evict_last() { return 0; }
+inline double ldg_gather(const double* p, uint64_t) { return *p; }
 inline void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar, uint64_t) {
   if ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src) | bytes) & 15) {
     std::fprintf(stderr, "cuda_emul: cp.async.bulk needs 16-byte aligned addresses and size (dst %p src %p bytes %u)\n", dst, src, bytes);

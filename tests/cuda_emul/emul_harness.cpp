@@ -106,12 +106,13 @@ int emul_local_apply(int32_t n_rows, int32_t n_cols, int32_t n_local_cols, const
   DirectRule rule;  // same knobs as the library (csr_finalize_structure)
   if (const char* v = std::getenv("JP_SPMV_DIRECT_MAXLEN")) rule.maxlen = std::atoi(v);
   if (const char* v = std::getenv("JP_SPMV_DIRECT_RATIO")) rule.ratio = std::atof(v);
+  if (const char* v = std::getenv("JP_SPMV_SUBWARP_DIV")) rule.subwarp_div = std::atof(v);
   build_blocks(rp, cls, cap, max_rows, allow_direct != 0, bi, bb, ba, rule);
   if (stats) {
     stats[0] = (int64_t)ba.size();
     stats[1] = stats[2] = stats[3] = 0;
     for (const BlockDesc& b : ba) {
-      const int kind = b.nrows_kind >> 16;
+      const int kind = (b.nrows_kind >> 16) & 0xf;
       ++stats[kind == KIND_DIRECT ? 1 : kind == KIND_LONGROW ? 3 : 2];
     }
   }

@@ -26,6 +26,7 @@ def dense_abs_bound(triples, N, xs, ys, trans, lo, hi):
 
 
 def main():
+    os.environ["JP_HOST_PIPELINE_MIN_BYTES"] = "1"  # apply_host takes the chunked three-stream pipeline even at test sizes
     import torch.distributed as dist
     dist.init_process_group("gloo")
     import jpetra_b200 as jp
@@ -132,6 +133,10 @@ def main():
         # host-buffer entry point
         yh = Aj.apply_host(xs[rank], np.array(ys[rank], order="F", copy=True), jp.NO_TRANS, 3.0, 0.5)
         assert np.array_equal(yh, got)
+        # beta == 0: the chunked three-stream pipeline of jp_apply_host (H2D chunks | halo + boundary rows | interior chunks | D2H)
+        for _ in range(2):
+            yh0 = Aj.apply_host(xs[rank], None, jp.NO_TRANS, 3.0, 0.0)
+        assert np.array_equal(yh0, Aj.apply(Xj, jp.NO_TRANS, 3.0).data), (kind, pid, "pipelined host path")
         # dot / norm with the cross-rank allreduce
         dref = OX.dot(OY)
         dgot = Xj.dot(Yj)[0]
