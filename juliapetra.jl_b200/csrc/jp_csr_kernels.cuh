@@ -786,6 +786,35 @@ __host__ __device__ inline size_t runs_smem_bytes(int cap, int wpad, int KT) {
   return (size_t)(cap + 8) * 8 + (size_t)KT * wpad * 8 + (size_t)(kRunsMaxRows + 8) * 4 + (size_t)(cap + 16) * 2;
 }
 
+// acc[j] += sum over the row's entries i = first, first + T, ... < e of val[i] * xs[j][lidx[i]].  The kernel is bound by the
+// latency of its shared-memory loads (profiles/r2_ncu_spmm_runs_summary.txt: 12 warps per SM, short-scoreboard stalls), so
+// four entries are in flight at once: their positions and values are read first, then the 4 * KT tile reads, then the FMAs.
+template <int KT>
+__device__ __forceinline__ void runs_row_accumulate(double (&acc)[KT], const uint16_t* __restrict__ lidx0, const double* __restrict__ val0,
+                                                    const double* __restrict__ xs, int wpad, int first, int e, int T) {
+  int i = first;
+  for (; i + 3 * T < e; i += 4 * T) {
+    const int l0 = lidx0[i], l1 = lidx0[i + T], l2 = lidx0[i + 2 * T], l3 = lidx0[i + 3 * T];
+    const double v0 = val0[i], v1 = val0[i + T], v2 = val0[i + 2 * T], v3 = val0[i + 3 * T];
+    double x0[KT], x1[KT], x2[KT], x3[KT];
+#pragma unroll
+    for (int j = 0; j < KT; ++j) {
+      x0[j] = xs[j * wpad + l0];
+      x1[j] = xs[j * wpad + l1];
+      x2[j] = xs[j * wpad + l2];
+      x3[j] = xs[j * wpad + l3];
+    }
+#pragma unroll
+    for (int j = 0; j < KT; ++j) acc[j] = fma(v3, x3[j], fma(v2, x2[j], fma(v1, x1[j], fma(v0, x0[j], acc[j]))));
+  }
+  for (; i < e; i += T) {
+    const int li = lidx0[i];
+    const double v = val0[i];
+#pragma unroll
+    for (int j = 0; j < KT; ++j) acc[j] = fma(v, xs[j * wpad + li], acc[j]);
+  }
+}
+
 template <int KT, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 spmm_runs_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ rowptr, const double* __restrict__ vals,
@@ -868,13 +897,7 @@ spmm_runs_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict
       double acc[KT];
 #pragma unroll
       for (int j = 0; j < KT; ++j) acc[j] = 0.0;
-#pragma unroll 2
-      for (int i = s + lane_t; i < e; i += T) {
-        const int li = lidx0[i];
-        const double v = val0[i];
-#pragma unroll
-        for (int j = 0; j < KT; ++j) acc[j] = fma(v, xs[j * wpad + li], acc[j]);
-      }
+      runs_row_accumulate<KT>(acc, lidx0, val0, xs, wpad, s + lane_t, e, T);
       for (int o = T >> 1; o > 0; o >>= 1) {
 #pragma unroll
         for (int j = 0; j < KT; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
@@ -1029,13 +1052,7 @@ spmm_runs_db_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restr
       double acc[KT];
 #pragma unroll
       for (int j = 0; j < KT; ++j) acc[j] = 0.0;
-#pragma unroll 2
-      for (int i = s + lane_t; i < e; i += T) {
-        const int li = lidx0[i];
-        const double v = val0[i];
-#pragma unroll
-        for (int j = 0; j < KT; ++j) acc[j] = fma(v, xs[j * wpad + li], acc[j]);
-      }
+      runs_row_accumulate<KT>(acc, lidx0, val0, xs, wpad, s + lane_t, e, T);
       for (int o = T >> 1; o > 0; o >>= 1) {
 #pragma unroll
         for (int j = 0; j < KT; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
