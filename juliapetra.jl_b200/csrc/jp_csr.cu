@@ -384,32 +384,44 @@ void csr_prepare_spmm(Csr& A) {
   if (A.runs_state == 0) build_runs(A);
 }
 
+// jp_apply_dot workspace of `n` CTA partials: [partials n | level-2 partials | result | ticket]; zeroed when (re)allocated
+struct DotWorkspace {
+  double* partials;
+  double* level2;
+  double* out;
+  unsigned int* ticket;
+};
+static DotWorkspace dot_workspace(Csr& A, int32_t n, cudaStream_t stream) {
+  const unsigned g2 = sum_partials_grid((unsigned)n);
+  const size_t bytes = ((size_t)n + g2 + 4) * 8;
+  if (A.dot_ws.bytes < bytes) {
+    A.dot_ws.alloc(bytes);
+    JP_CUDA(cudaMemsetAsync(A.dot_ws.p, 0, bytes, stream));
+  }
+  DotWorkspace w;
+  w.partials = A.dot_ws.as<double>();
+  w.level2 = w.partials + n;
+  w.out = w.level2 + g2;
+  w.ticket = reinterpret_cast<unsigned int*>(w.out + 1);
+  return w;
+}
+
 double* launch_spmv_dot(Csr& A, const double* x, double* y, double alpha, double beta, const double* w, cudaStream_t stream) {
   const int32_t nb = A.n_blocks_all;
-  const size_t ws_bytes = ((size_t)nb + 4) * 8;  // [block partials | result]
-  if (A.dot_ws.bytes < ws_bytes) A.dot_ws.alloc(ws_bytes);
-  double* partials = A.dot_ws.as<double>();
-  double* out = partials + nb;
+  const DotWorkspace ws = dot_workspace(A, nb, stream);
   if (nb == 0) {
-    JP_CUDA(cudaMemsetAsync(out, 0, 8, stream));
-    return out;
+    JP_CUDA(cudaMemsetAsync(ws.out, 0, 8, stream));
+    return ws.out;
   }
   const size_t smem = stage_smem_bytes(A.nnz_cap);
-  static const int tma = env_int("JP_SPMV_TMA", 1);
   const BlockDesc* b = A.blocks_all.as<BlockDesc>();
-  if (tma) {
-    set_smem_attr(spmv_dot_kernel<false, 1>, smem);
-    spmv_dot_kernel<false, 1><<<nb, kSpmvThreads, smem, stream>>>(b, A.rowptr.as<int32_t>(), A.colind.as<int32_t>(), A.vals.as<double>(), x,
-                                                                   nullptr, A.n_cols, y, A.nnz_cap, alpha, beta, w, partials);
-  } else {
-    set_smem_attr(spmv_dot_kernel<false, 0>, smem);
-    spmv_dot_kernel<false, 0><<<nb, kSpmvThreads, smem, stream>>>(b, A.rowptr.as<int32_t>(), A.colind.as<int32_t>(), A.vals.as<double>(), x,
-                                                                   nullptr, A.n_cols, y, A.nnz_cap, alpha, beta, w, partials);
-  }
+  set_smem_attr(spmv_dot_kernel<false, 1>, smem);
+  spmv_dot_kernel<false, 1><<<nb, kSpmvThreads, smem, stream>>>(b, A.rowptr.as<int32_t>(), A.colind.as<int32_t>(), A.vals.as<double>(), x,
+                                                                 nullptr, A.n_cols, y, A.nnz_cap, alpha, beta, w, ws.partials);
   JP_LAUNCH_CHECK();
-  sum_partials_kernel<<<1, kSpmvThreads, 0, stream>>>(partials, (unsigned)nb, out);
+  sum_partials_kernel<<<sum_partials_grid((unsigned)nb), kSpmvThreads, 0, stream>>>(ws.partials, (unsigned)nb, ws.out, ws.level2, ws.ticket);
   JP_LAUNCH_CHECK();
-  return out;
+  return ws.out;
 }
 
 // the fused halo + SpMV launch of launch_spmv_fused with the dot product of jp_apply_dot accumulated on the way
@@ -417,17 +429,14 @@ double* launch_spmv_fused_dot(Csr& A, const FusedHalo& h, const double* x, const
                               const double* w, cudaStream_t stream) {
   const FusedSpmvArgs a = fused_args(A, h, x, halo, y, alpha, beta);
   const int grid = a.n_pack + a.n_interior + a.n_boundary;
-  const size_t ws_bytes = ((size_t)grid + 4) * 8;  // [CTA partials | result]
-  if (A.dot_ws.bytes < ws_bytes) A.dot_ws.alloc(ws_bytes);
-  double* partials = A.dot_ws.as<double>();
-  double* out = partials + grid;
+  const DotWorkspace ws = dot_workspace(A, grid, stream);
   const size_t smem = stage_smem_bytes(A.nnz_cap);
   set_smem_attr(spmv_fused_halo_dot_kernel, smem);
-  spmv_fused_halo_dot_kernel<<<grid, kSpmvThreads, smem, stream>>>(a, w, partials);
+  spmv_fused_halo_dot_kernel<<<grid, kSpmvThreads, smem, stream>>>(a, w, ws.partials);
   JP_LAUNCH_CHECK();
-  sum_partials_kernel<<<1, kSpmvThreads, 0, stream>>>(partials, (unsigned)grid, out);
+  sum_partials_kernel<<<sum_partials_grid((unsigned)grid), kSpmvThreads, 0, stream>>>(ws.partials, (unsigned)grid, ws.out, ws.level2, ws.ticket);
   JP_LAUNCH_CHECK();
-  return out;
+  return ws.out;
 }
 
 void launch_spmv(const Csr& A, const DeviceBuffer& blocks, int32_t n_blocks, bool use_halo, const double* x, int64_t ldx,
@@ -600,7 +609,7 @@ int32_t jp_csr_create(int32_t n_rows, int32_t n_cols, int32_t n_local_cols, int6
     A->n_cols = n_cols;
     A->n_local_cols = n_local_cols;
     A->nnz = nnz;
-    // host pass: validate, classify rows, row-length statistics
+    // host pass over the row pointers only (n_rows + 1 integers)
     std::vector<int32_t> rp((size_t)n_rows + 1);
     JP_REQUIRE(rowptr[0] == index_base, "jp_csr_create: rowptr[first] must equal index_base");
     for (int32_t r = 0; r <= n_rows; ++r) {
@@ -608,34 +617,39 @@ int32_t jp_csr_create(int32_t n_rows, int32_t n_cols, int32_t n_local_cols, int6
       if (r > 0) JP_REQUIRE(rp[r] >= rp[r - 1], "jp_csr_create: rowptr must be non-decreasing");
     }
     JP_REQUIRE(rp[n_rows] == nnz, "jp_csr_create: rowptr[last] does not match nnz");
-    std::vector<int32_t> rowmax((size_t)n_rows, -1);
-    for (int32_t r = 0; r < n_rows; ++r) {
-      int32_t mx = -1;
-      for (int32_t i = rp[r]; i < rp[r + 1]; ++i) {
-        const int32_t c = colind[i] - index_base;
-        JP_REQUIRE(c >= 0 && c < n_cols, "jp_csr_create: column index outside the column map");
-        mx = c > mx ? c : mx;
-      }
-      rowmax[r] = mx;
-    }
-    csr_finalize_structure(*A, rp, rowmax);
     // device arrays; 64 elements of zeroed slack so the 16-byte staging may over-read past nnz
+    cudaStream_t st = ctx().compute;
     A->rowptr.alloc(((size_t)n_rows + 1 + 16) * 4);  // slack: row pointers are staged in aligned groups of 4
-    JP_CUDA(cudaMemset(A->rowptr.p, 0, ((size_t)n_rows + 1 + 16) * 4));
+    JP_CUDA(cudaMemsetAsync(A->rowptr.p, 0, ((size_t)n_rows + 1 + 16) * 4, st));
     A->colind.alloc(((size_t)nnz + 64) * 4);
     A->vals.alloc(((size_t)nnz + 64) * 8);
-    JP_CUDA(cudaMemcpy(A->rowptr.p, rp.data(), rp.size() * 4, cudaMemcpyHostToDevice));
-    JP_CUDA(cudaMemset(A->colind.as<int32_t>() + nnz, 0, 64 * 4));
-    JP_CUDA(cudaMemset(A->vals.as<double>() + nnz, 0, 64 * 8));
+    JP_CUDA(cudaMemcpyAsync(A->rowptr.p, rp.data(), rp.size() * 4, cudaMemcpyHostToDevice, st));
+    JP_CUDA(cudaMemsetAsync(A->colind.as<int32_t>() + nnz, 0, 64 * 4, st));
+    JP_CUDA(cudaMemsetAsync(A->vals.as<double>() + nnz, 0, 64 * 8, st));
     if (nnz > 0) {
-      JP_CUDA(cudaMemcpy(A->colind.p, colind, (size_t)nnz * 4, cudaMemcpyHostToDevice));
-      JP_CUDA(cudaMemcpy(A->vals.p, vals, (size_t)nnz * 8, cudaMemcpyHostToDevice));
-      if (index_base != 0) {
-        shift_index_kernel<<<ctx().sm_count * 8, 256, 0, ctx().compute>>>(A->colind.as<int32_t>(), nnz, index_base);
-        JP_LAUNCH_CHECK();
-        JP_CUDA(cudaStreamSynchronize(ctx().compute));
-      }
+      JP_CUDA(cudaMemcpyAsync(A->colind.p, colind, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+      JP_CUDA(cudaMemcpyAsync(A->vals.p, vals, (size_t)nnz * 8, cudaMemcpyHostToDevice, st));
     }
+    // device pass over the column indices: 0-based, range check, every row's largest column
+    std::vector<int32_t> rowmax((size_t)n_rows, -1);
+    if (n_rows > 0) {
+      DeviceBuffer d_rowmax, d_bad;
+      d_rowmax.alloc((size_t)n_rows * 4);
+      d_bad.alloc(8);
+      JP_CUDA(cudaMemsetAsync(d_bad.p, 0, 8, st));
+      const int64_t want = ((int64_t)n_rows + 255) / 256;
+      csr_validate_kernel<<<(int)std::min<int64_t>(want, (int64_t)ctx().sm_count * 16), 256, 0, st>>>(
+          A->rowptr.as<int32_t>(), A->colind.as<int32_t>(), n_rows, n_cols, index_base, d_rowmax.as<int32_t>(), d_bad.as<unsigned long long>());
+      JP_LAUNCH_CHECK();
+      unsigned long long bad = 0;
+      JP_CUDA(cudaMemcpyAsync(rowmax.data(), d_rowmax.p, (size_t)n_rows * 4, cudaMemcpyDeviceToHost, st));
+      JP_CUDA(cudaMemcpyAsync(&bad, d_bad.p, 8, cudaMemcpyDeviceToHost, st));
+      JP_CUDA(cudaStreamSynchronize(st));
+      JP_REQUIRE(bad == 0, "jp_csr_create: column index outside the column map");
+    } else {
+      JP_CUDA(cudaStreamSynchronize(st));  // the host arrays are not retained
+    }
+    csr_finalize_structure(*A, rp, rowmax);
     *out = register_object(std::move(A));
   });
 }

@@ -343,26 +343,51 @@ __device__ __forceinline__ void block_partial_store(double v, double* s_red, dou
   }
 }
 
-// out[0] = sum of partials[0..n) in a fixed order (ONE CTA of kSpmvThreads threads)
-__global__ void __launch_bounds__(kSpmvThreads) sum_partials_kernel(const double* __restrict__ partials, unsigned n, double* __restrict__ out) {
+// out[0] = sum of partials[0..n) in a fixed order.  Two levels in one launch: CTA c adds partials [c*kSumChunk,
+// (c+1)*kSumChunk) -- 16 independent loads per thread -- into level2[c]; the last CTA to finish (ticket, re-armed) adds
+// the level-2 values in CTA order.  (A single CTA over the 65536 partials of a 256^3 apply took ~100 us: a third of the
+// apply itself, profiles/r2_next_rows_256.json.)
+constexpr unsigned kSumChunk = kSpmvThreads * 16;
+__host__ __device__ inline unsigned sum_partials_grid(unsigned n) { return n == 0 ? 1u : (n + kSumChunk - 1) / kSumChunk; }
+
+__global__ void __launch_bounds__(kSpmvThreads) sum_partials_kernel(const double* __restrict__ partials, unsigned n, double* __restrict__ out,
+                                                                      double* __restrict__ level2, unsigned int* __restrict__ ticket) {
   __shared__ double s_red[kSpmvThreads / 32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-  unsigned b = tid;
-  for (; b + 3 * kSpmvThreads < n; b += 4 * kSpmvThreads) {
-    a0 += partials[b];
-    a1 += partials[b + kSpmvThreads];
-    a2 += partials[b + 2 * kSpmvThreads];
-    a3 += partials[b + 3 * kSpmvThreads];
+  __shared__ bool s_last;
+  const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned base = blockIdx.x * kSumChunk;
+  double v[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const unsigned i = base + q * kSpmvThreads + tid;
+    v[q] = i < n ? partials[i] : 0.0;
   }
-  for (; b < n; b += kSpmvThreads) a0 += partials[b];
-  const double t = warp_sum((a0 + a1) + (a2 + a3));
+  double a = 0.0;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) a += v[q];
+  const double t = warp_sum(a);
   if (lane == 0) s_red[warp] = t;
   __syncthreads();
   if (warp == 0) {
     double u = lane < kSpmvThreads / 32 ? s_red[lane] : 0.0;
     u = warp_sum(u);
-    if (lane == 0) out[0] = u;
+    if (lane == 0) {
+      level2[blockIdx.x] = u;
+      __threadfence();
+      s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+  }
+  __syncthreads();
+  if (s_last && warp == 0) {
+    __threadfence();
+    const volatile double* l2 = level2;
+    double u = 0.0;
+    for (unsigned c = lane; c < gridDim.x; c += 32) u += l2[c];
+    u = warp_sum(u);
+    if (lane == 0) {
+      out[0] = u;
+      *ticket = 0;
+    }
   }
 }
 
@@ -1070,9 +1095,24 @@ spmm_runs_db_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restr
   }
 }
 
-__global__ void shift_index_kernel(int32_t* __restrict__ a, int64_t n, int32_t base) {
+// jp_csr_create, one pass over the uploaded column indices (rows strided over the threads): make them 0-based, find every
+// row's largest column (-1 for an empty row) and count the indices outside [0, n_cols) -- the O(nnz) part of the
+// validation runs here, not on one host core
+__global__ void csr_validate_kernel(const int32_t* __restrict__ rowptr, int32_t* __restrict__ colind, int32_t n_rows, int32_t n_cols, int32_t base,
+                                    int32_t* __restrict__ rowmax, unsigned long long* __restrict__ bad) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a[i] -= base;
+  unsigned long long nbad = 0;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
+    int32_t mx = -1;
+    for (int32_t i = rowptr[r]; i < rowptr[r + 1]; ++i) {
+      const int32_t c = colind[i] - base;
+      if (base != 0) colind[i] = c;
+      if (c < 0 || c >= n_cols) ++nbad;
+      mx = c > mx ? c : mx;
+    }
+    rowmax[r] = mx;
+  }
+  if (nbad) atomicAdd(bad, nbad);
 }
 
 }  // namespace csrk

@@ -15,6 +15,29 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Sum of pv[0..n) by ALL threads of the block in a fixed order (the tail of the reduction kernels, run by the last block to
+// finish): four independent loads per thread at a time, then the usual warp / block tree.  The result is valid in thread 0.
+// (One warp walking the <= 1024 partials one dependent L2 load after the other cost ~15 us per dot / norm call.)
+__device__ __forceinline__ double block_sum_fixed_order(const volatile double* pv, unsigned n, double* warp_part) {
+  const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double a = 0.0;
+  for (unsigned base = 0; base < n; base += 4 * kThreads) {
+    const unsigned i0 = base + tid, i1 = i0 + kThreads, i2 = i1 + kThreads, i3 = i2 + kThreads;
+    const double v0 = i0 < n ? pv[i0] : 0.0, v1 = i1 < n ? pv[i1] : 0.0, v2 = i2 < n ? pv[i2] : 0.0, v3 = i3 < n ? pv[i3] : 0.0;
+    a += (v0 + v1) + (v2 + v3);
+  }
+  const double t = warp_sum(a);
+  __syncthreads();  // warp_part may still be read by warp 0 of the caller
+  if (lane == 0) warp_part[warp] = t;
+  __syncthreads();
+  double u = 0.0;
+  if (warp == 0) {
+    u = lane < kThreads / 32 ? warp_part[lane] : 0.0;
+    u = warp_sum(u);
+  }
+  return u;
+}
+
 // How the k results of a reduction reach the host: one warp stores them straight into host-mapped pinned memory and
 // then a sequence number the host spins on.  This replaces the cudaMemcpyAsync + cudaStreamSynchronize pair (~20 us of
 // fixed cost per dot / norm call); with several ranks it runs behind the NCCL allreduce on the same stream.
@@ -108,14 +131,11 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(const double* __restri
     }
   }
   __syncthreads();
-  if (is_last && warp == 0) {
+  if (is_last) {  // block-uniform
     __threadfence();
     // fixed-order final sum over the blocks of this vector
-    double t = 0.0;
-    const volatile double* pv = partials + (size_t)vec * gridDim.x;
-    for (unsigned int b = lane; b < gridDim.x; b += 32) t += pv[b];
-    t = warp_sum(t);
-    if (lane == 0) {
+    const double t = block_sum_fixed_order(partials + (size_t)vec * gridDim.x, gridDim.x, warp_part);
+    if (threadIdx.x == 0) {
       out[vec] = t;
       tickets[vec] = 0;  // re-arm for the next call
     }
@@ -216,13 +236,10 @@ __global__ void __launch_bounds__(kThreads) axpby_norm2_kernel(double* __restric
     }
   }
   __syncthreads();
-  if (is_last && warp == 0) {
+  if (is_last) {  // block-uniform
     __threadfence();
-    double t = 0.0;
-    const volatile double* pv = partials + (size_t)vec * gridDim.x;
-    for (unsigned int blk = lane; blk < gridDim.x; blk += 32) t += pv[blk];
-    t = warp_sum(t);
-    if (lane == 0) {
+    const double t = block_sum_fixed_order(partials + (size_t)vec * gridDim.x, gridDim.x, warp_part);
+    if (threadIdx.x == 0) {
       out[vec] = t;
       tickets[vec] = 0;
     }

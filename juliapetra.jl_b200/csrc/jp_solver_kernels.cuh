@@ -81,15 +81,27 @@ __global__ void __launch_bounds__(kThreads) axpby_norm2_dev_kernel(double* __res
     }
   }
   __syncthreads();
-  if (is_last && warp == 0) {
+  if (is_last) {  // block-uniform: every thread of the last block takes part in the fixed-order final sum
     __threadfence();
-    double t = 0.0;
     const volatile double* pv = partials;
-    for (unsigned int blk = lane; blk < gridDim.x; blk += 32) t += pv[blk];
-    t = warp_sum(t);
-    if (lane == 0) {
-      out[0] = t;
-      tickets[0] = 0;
+    double acc = 0.0;
+    for (unsigned int base = 0; base < gridDim.x; base += 4 * kThreads) {
+      const unsigned int i0 = base + threadIdx.x, i1 = i0 + kThreads, i2 = i1 + kThreads, i3 = i2 + kThreads;
+      const double v0 = i0 < gridDim.x ? pv[i0] : 0.0, v1 = i1 < gridDim.x ? pv[i1] : 0.0;
+      const double v2 = i2 < gridDim.x ? pv[i2] : 0.0, v3 = i3 < gridDim.x ? pv[i3] : 0.0;
+      acc += (v0 + v1) + (v2 + v3);
+    }
+    const double ws = warp_sum(acc);
+    __syncthreads();
+    if (lane == 0) warp_part[warp] = ws;
+    __syncthreads();
+    if (warp == 0) {
+      double t = lane < kThreads / 32 ? warp_part[lane] : 0.0;
+      t = warp_sum(t);
+      if (lane == 0) {
+        out[0] = t;
+        tickets[0] = 0;
+      }
     }
   }
 }

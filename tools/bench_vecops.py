@@ -39,13 +39,18 @@ def main():
         X = jp.DenseMultiVector(m, synthetic.vector_block(1, n, k, seed=1))
         Y = jp.DenseMultiVector(m, synthetic.vector_block(1, n, k, seed=2))
         reps = 200 if n * k <= 1 << 27 else 50
+        S = jp.Scalars(2)
         ops = {
-            "dot (16 B/elem, incl. D2H + sync per call)": (lambda: X.dot(Y), 16),
-            "norm2 (8 B/elem, incl. D2H + sync per call)": (lambda: X.norm(2), 8),
+            "dot (16 B/elem, host result: hand-over + host round trip per call)": (lambda: X.dot(Y), 16),
+            "norm2 (8 B/elem, host result: hand-over + host round trip per call)": (lambda: X.norm(2), 8),
             "axpby y=a*x+b*y (24 B/elem)": (lambda: Y.axpby_(0.5, X, 0.5), 24),
             "scale! (16 B/elem)": (lambda: Y.scale_(1.0000001), 16),
             "fill! (8 B/elem)": (lambda: Y.fill_(1.5), 8),
         }
+        if k == 1:  # the same reduction kernel with the result left on the device (jp_mv_dot_dev): kernel time, no host round trip
+            ops["dot, device-resident result (16 B/elem, kernel only)"] = (lambda: _lib.check(lib.jp_mv_dot_dev(comm.handle, X.h, Y.h, S.h, 0)), 16)
+            ops["norm2 as dot(x, x), device-resident result (8 B/elem of HBM traffic, kernel only)"] = (
+                lambda: _lib.check(lib.jp_mv_dot_dev(comm.handle, X.h, X.h, S.h, 1)), 8)
         for name, (fn, bpe) in ops.items():
             ms = timed(fn, reps, lib)
             gbs = bpe * n * k / (ms * 1e-3) / 1e9
