@@ -154,7 +154,7 @@ __device__ __forceinline__ void fused_halo_body(const FusedSpmvArgs& a, const do
       if (tid == 0) a.h.tickets[1] = 0;
     }
   }
-  if (DOT) block_partial_store(dacc, s_red, partials, blockIdx.x);
+  if (DOT) warp_partial_store(dacc, partials, blockIdx.x);
 }
 
 __global__ void __launch_bounds__(kSpmvThreads) spmv_fused_halo_kernel(const FusedSpmvArgs a) { fused_halo_body<false>(a, nullptr, nullptr); }
@@ -408,7 +408,8 @@ static DotWorkspace dot_workspace(Csr& A, int32_t n, cudaStream_t stream) {
 
 double* launch_spmv_dot(Csr& A, const double* x, double* y, double alpha, double beta, const double* w, cudaStream_t stream) {
   const int32_t nb = A.n_blocks_all;
-  const DotWorkspace ws = dot_workspace(A, nb, stream);
+  const int32_t np = nb * kDotPartialsPerBlock;  // one partial per warp
+  const DotWorkspace ws = dot_workspace(A, np, stream);
   if (nb == 0) {
     JP_CUDA(cudaMemsetAsync(ws.out, 0, 8, stream));
     return ws.out;
@@ -419,7 +420,7 @@ double* launch_spmv_dot(Csr& A, const double* x, double* y, double alpha, double
   spmv_dot_kernel<false, 1><<<nb, kSpmvThreads, smem, stream>>>(b, A.rowptr.as<int32_t>(), A.colind.as<int32_t>(), A.vals.as<double>(), x,
                                                                  nullptr, A.n_cols, y, A.nnz_cap, alpha, beta, w, ws.partials);
   JP_LAUNCH_CHECK();
-  sum_partials_kernel<<<sum_partials_grid((unsigned)nb), kSpmvThreads, 0, stream>>>(ws.partials, (unsigned)nb, ws.out, ws.level2, ws.ticket);
+  sum_partials_kernel<<<sum_partials_grid((unsigned)np), kSpmvThreads, 0, stream>>>(ws.partials, (unsigned)np, ws.out, ws.level2, ws.ticket);
   JP_LAUNCH_CHECK();
   return ws.out;
 }
@@ -429,12 +430,13 @@ double* launch_spmv_fused_dot(Csr& A, const FusedHalo& h, const double* x, const
                               const double* w, cudaStream_t stream) {
   const FusedSpmvArgs a = fused_args(A, h, x, halo, y, alpha, beta);
   const int grid = a.n_pack + a.n_interior + a.n_boundary;
-  const DotWorkspace ws = dot_workspace(A, grid, stream);
+  const int32_t np = grid * kDotPartialsPerBlock;  // one partial per warp
+  const DotWorkspace ws = dot_workspace(A, np, stream);
   const size_t smem = stage_smem_bytes(A.nnz_cap);
   set_smem_attr(spmv_fused_halo_dot_kernel, smem);
   spmv_fused_halo_dot_kernel<<<grid, kSpmvThreads, smem, stream>>>(a, w, ws.partials);
   JP_LAUNCH_CHECK();
-  sum_partials_kernel<<<sum_partials_grid((unsigned)grid), kSpmvThreads, 0, stream>>>(ws.partials, (unsigned)grid, ws.out, ws.level2, ws.ticket);
+  sum_partials_kernel<<<sum_partials_grid((unsigned)np), kSpmvThreads, 0, stream>>>(ws.partials, (unsigned)np, ws.out, ws.level2, ws.ticket);
   JP_LAUNCH_CHECK();
   return ws.out;
 }

@@ -326,21 +326,17 @@ __device__ __forceinline__ double spmv_block(const BlockRange& b, const StageVie
   return dacc;
 }
 
-// One partial per CTA: partials[bid] = sum of `v` over the CTA's threads.  s_red: kSpmvThreads / 32 doubles.
-// (A first version finished the grid-wide sum inside the same kernel with __threadfence + a ticket counter; measured
-// on 7-pt 128^3 that made the fused kernel 11 us slower than the plain SpMV -- more than the separate dot kernel
-// costs -- so the partials are now added by sum_partials_kernel, a one-CTA launch behind it.)
-__device__ __forceinline__ void block_partial_store(double v, double* s_red, double* __restrict__ partials, unsigned bid) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// One partial per WARP: partials[bid * (kSpmvThreads / 32) + warp] = sum of `v` over the warp's lanes.  No block-level
+// step: a warp stores its sum and is done, so the CTA gives its slot back as soon as its last warp has finished.
+// (History: finishing the grid-wide sum inside the kernel with __threadfence + a ticket made the fused kernel 11 us slower
+// than the plain SpMV on 7-pt 128^3; one partial per CTA still cost two block barriers at the end of every CTA, 15 % of
+// the CTA's lifetime of a kernel that runs at the HBM roofline -- profiles/r2_next_rows_256.json.  sum_partials_kernel
+// adds the partials up in a fixed order behind it.)
+constexpr int kDotPartialsPerBlock = kSpmvThreads / 32;
+__device__ __forceinline__ void warp_partial_store(double v, double* __restrict__ partials, unsigned bid) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double s = warp_sum(v);
-  __syncthreads();  // s_red may still be in use by the row block
-  if (lane == 0) s_red[warp] = s;
-  __syncthreads();
-  if (warp == 0) {
-    double t = lane < kSpmvThreads / 32 ? s_red[lane] : 0.0;
-    t = warp_sum(t);
-    if (lane == 0) partials[bid] = t;
-  }
+  if (lane == 0) partials[(size_t)bid * kDotPartialsPerBlock + warp] = s;
 }
 
 // out[0] = sum of partials[0..n) in a fixed order.  Two levels in one launch: CTA c adds partials [c*kSumChunk,
@@ -405,7 +401,7 @@ spmv_dot_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict_
   const StageView sv = stage_view(smem_raw, cap);
   const BlockRange b = decode_block(blocks, blockIdx.x);
   const double dacc = spmv_block<HALO, TMA, true>(b, sv, &s_bar, s_red, rowptr, colind, vals, x, halo, nloc, y, alpha, beta, w);
-  block_partial_store(dacc, s_red, partials, blockIdx.x);
+  warp_partial_store(dacc, partials, blockIdx.x);
 }
 
 template <bool HALO, int TMA>

@@ -280,11 +280,12 @@ int emul_spmv_dot(int32_t n_rows, int32_t n_cols, const int32_t* rowptr, const i
   d_w.alloc((size_t)n_rows * 8 + 64);
   std::memcpy(d_w.p, w, (size_t)n_rows * 8);
   d_y.alloc((size_t)n_rows * 8 + 64);
-  const unsigned g2 = sum_partials_grid((unsigned)nb);  // workspace layout of the library (jp_csr.cu dot_workspace)
-  ws.alloc(((size_t)nb + g2 + 4) * 8);
+  const unsigned np = (unsigned)nb * kDotPartialsPerBlock;  // one partial per warp
+  const unsigned g2 = sum_partials_grid(np);                // workspace layout of the library (jp_csr.cu dot_workspace)
+  ws.alloc(((size_t)np + g2 + 4) * 8);
   std::memset(ws.p, 0, ws.bytes);
   double* partials = ws.as<double>();
-  double* level2 = partials + nb;
+  double* level2 = partials + np;
   double* d_out = level2 + g2;
   unsigned int* ticket = reinterpret_cast<unsigned int*>(d_out + 1);
   const size_t smem = stage_smem_bytes(cap);
@@ -302,7 +303,7 @@ int emul_spmv_dot(int32_t n_rows, int32_t n_cols, const int32_t* rowptr, const i
                  d_ci.as<int32_t>(), d_va.as<double>(), d_x.as<double>(), (const double*)nullptr, n_cols, d_y.as<double>(), cap, alpha, beta,
                  d_w.as<double>(), partials);
     }
-    if (nb) JP_KLAUNCH(sum_partials_kernel, g2, kSpmvThreads, 0, nullptr, partials, (unsigned)nb, d_out, level2, ticket);
+    if (nb) JP_KLAUNCH(sum_partials_kernel, g2, kSpmvThreads, 0, nullptr, partials, np, d_out, level2, ticket);
     out[rep] = *d_out;
   }
   std::memcpy(y, d_y.p, (size_t)n_rows * 8);
