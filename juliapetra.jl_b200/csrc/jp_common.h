@@ -186,6 +186,11 @@ struct MultiVector : Object {
 };
 
 
+struct DiaData;  // jp_dia.cu
+struct DiaDeleter {
+  void operator()(DiaData* p) const;
+};
+
 struct Csr : Object {
   Csr() : Object(Kind::Csr) {}
   int32_t n_rows = 0, n_cols = 0, n_local_cols = 0;
@@ -198,21 +203,18 @@ struct Csr : Object {
   DeviceBuffer blocks_interior, blocks_boundary, blocks_all;
   int32_t n_blocks_interior = 0, n_blocks_boundary = 0, n_blocks_all = 0;
   std::vector<BlockDesc> h_blocks_interior, h_blocks_boundary, h_blocks_all;  // host copies (the tile builder patches them)
-  // SpMM tile path (built lazily at the first k > 1 apply): per block the sorted unique columns it references and,
-  // per nonzero, the uint16 position of its column in that list, so the block's X tile can be staged in shared memory
-  int tile_state = 0;        // 0 = not built, 1 = active, -1 = not beneficial for this matrix
-  int32_t tile_umax = 0;     // largest unique-column count of a block
-  DeviceBuffer ucols, lidx;
   // SpMM runs path (spmm_runs_kernel; built lazily at the first k > 1 apply): its own row blocks (<= 64 rows), the
   // aligned column runs of every block and the uint16 tile position of every nonzero
   int runs_state = 0;        // 0 = not built, 1 = active, -1 = not usable / disabled
-  int32_t runs_wmax = 0, runs_cap = 0, runs_kt = 4, runs_threads = 128;
-  bool runs_db = false;      // JP_SPMM_RUNS_DB=1: double-buffered tiles (spmm_runs_db_kernel)
+  int32_t runs_wmax = 0, runs_cap = 0;
   DeviceBuffer runs, runs_lidx, runs_blocks_all, runs_blocks_interior;
   int32_t n_runs_blocks_all = 0, n_runs_blocks_interior = 0;
   // cache of the column-map multivector (A.importMV, src/CSRMatrix.jl:10,772-781); only used when the column
   // map is not [domain prefix | remote tail] and the fused apply path does not apply
   std::unique_ptr<MultiVector> import_mv;
+  // SpMM on diagonal-structured matrices (spmm_dia_kernel; built lazily at the first k > 1 apply, jp_dia.cu)
+  int dia_state = 0;  // 0 = not decided, 1 = active, -1 = not a diagonal-structured matrix / disabled
+  std::unique_ptr<DiaData, DiaDeleter> dia;
   // A^T as a device CSR of its own, built at the first transposed apply (jp_transpose.cu)
   std::unique_ptr<Csr> transposed;
   // cache of the row-map multivector (A.exportMV, src/CSRMatrix.jl:11): the exporter branch of apply! (rangeMap != rowMap)
@@ -281,7 +283,14 @@ void launch_spmv(const Csr& A, const DeviceBuffer& blocks, int32_t n_blocks, boo
 Csr& csr_transposed(Csr& A);  // builds A.transposed on first use
 void launch_spmv_trans(Csr& A, const double* x, int64_t ldx, double* y, int64_t ldy, int32_t ny, int32_t k, double alpha,
                        double beta, cudaStream_t stream);
-void csr_prepare_spmm(Csr& A);  // builds the SpMM tile / run tables if that has not been decided yet
+void csr_prepare_spmm(Csr& A);  // decides (once) the SpMM path of the matrix: diagonal copy, run tables, or the gather kernel
+void csr_prepare_dia(Csr& A);   // decides (once) whether the matrix gets a diagonal-major copy for spmm_dia_kernel
+void launch_spmm_dia(const Csr& A, const double* x, int64_t ldx, double* y, int64_t ldy, int32_t k, double alpha, double beta,
+                     cudaStream_t stream);
+// the gather SpMM kernel on a contiguous piece of a block list (k > 1, no halo columns)
+void launch_spmm_gather_blocks(const Csr& A, const void* blocks, int32_t n_blocks, const double* x, int64_t ldx, double* y, int64_t ldy,
+                               int32_t k, double alpha, double beta, cudaStream_t stream);
+int64_t csr_dia_info(const Csr& A, int what);  // 0: diagonals, 1: rows served by the diagonal kernel, 2: tile width
 void csr_finalize_structure(Csr& A, const std::vector<int32_t>& rp, const std::vector<int32_t>& rowmax);
 void launch_scale_fill(double* y, int64_t n, double beta, cudaStream_t stream);  // y = beta==0 ? 0 : beta*y
 void plan_ensure_buffers(Plan& p, int32_t k);

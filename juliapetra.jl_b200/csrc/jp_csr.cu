@@ -47,9 +47,11 @@ using namespace csrk;
 //                  system-scope release.  Items are CLAIMED from a ticket counter -- by the dedicated pack CTAs at the
 //                  head of the grid and by every boundary CTA before it starts to wait;
 //   interior CTAs  the ordinary row-block SpMV on local columns (the bulk of the grid; they hide the exchange);
-//   boundary CTAs  come last in the grid: claim pack items until none is left, acquire the neighbours' ready flags (set
-//                  ~30 us earlier by the peers' pack items), run the row-block SpMV on x + halo, and the last one
-//                  publishes ack = epoch so the senders may reuse this halo buffer two applies later.
+//   boundary CTAs  sit behind the first three quarters of the interior blocks: claim pack items until none is left,
+//                  acquire the neighbours' ready flags (set ~20 us earlier by the peers' pack items), run the row-block
+//                  SpMV on x + halo, and the last one publishes ack = epoch so the senders may reuse this halo buffer two
+//                  applies later.  The last quarter of the interior blocks runs behind them, so the claim / acquire
+//                  latency of the boundary CTAs is not the tail of the kernel (at 8 GPUs they were 43 % of the last wave).
 // Forward progress does not depend on the order in which the hardware dispatches CTAs: a CTA only ever spins on a
 // remote flag AFTER every pack item of its own kernel has been claimed by a running CTA, pack items wait only for
 // acks of apply e - 2 (published by kernels that precede the neighbours' current one in stream order), and interior
@@ -59,6 +61,7 @@ struct FusedSpmvArgs {
   const BlockDesc* interior;
   const BlockDesc* boundary;
   int32_t n_pack, n_interior, n_boundary;
+  int32_t n_first;  // interior blocks in front of the boundary blocks; grid = [pack | first | boundary | rest of the interior]
   int32_t n_items;  // pack items (>= 1; item t packs export entries t*T + tid, strided by n_items*T)
   const int32_t* rowptr;
   const int32_t* colind;
@@ -132,9 +135,9 @@ __device__ __forceinline__ void fused_halo_body(const FusedSpmvArgs& a, const do
   double dacc = 0.0;
   if (bid < a.n_pack) {
     fused_pack_claims(a, &s_claim, &s_last);
-  } else if (bid < a.n_pack + a.n_interior) {
+  } else if (bid < a.n_pack + a.n_first || bid >= a.n_pack + a.n_first + a.n_boundary) {
     const StageView sv = stage_view(smem_raw, a.cap);
-    const BlockRange b = decode_block(a.interior, bid - a.n_pack);
+    const BlockRange b = decode_block(a.interior, bid < a.n_pack + a.n_first ? bid - a.n_pack : bid - a.n_pack - a.n_boundary);
     if (DOT) dacc = spmv_block<false, 1, true>(b, sv, &s_bar, s_red, a.rowptr, a.colind, a.vals, a.x, nullptr, a.nloc, a.y, a.alpha, a.beta, w);
     else spmv_block<false, 1>(b, sv, &s_bar, s_red, a.rowptr, a.colind, a.vals, a.x, nullptr, a.nloc, a.y, a.alpha, a.beta);
   } else {
@@ -143,7 +146,7 @@ __device__ __forceinline__ void fused_halo_body(const FusedSpmvArgs& a, const do
     if (tid < a.h.n_sources) wait_flag_ge(a.h.sources[tid].ready_flag, a.h.epoch, a.h.timeout_flag);
     __syncthreads();
     const StageView sv = stage_view(smem_raw, a.cap);
-    const BlockRange b = decode_block(a.boundary, bid - a.n_pack - a.n_interior);
+    const BlockRange b = decode_block(a.boundary, bid - a.n_pack - a.n_first);
     if (DOT) dacc = spmv_block<true, 1, true>(b, sv, &s_bar, s_red, a.rowptr, a.colind, a.vals, a.x, a.halo, a.nloc, a.y, a.alpha, a.beta, w);
     else spmv_block<true, 1>(b, sv, &s_bar, s_red, a.rowptr, a.colind, a.vals, a.x, a.halo, a.nloc, a.y, a.alpha, a.beta);
     __syncthreads();
@@ -204,59 +207,17 @@ void launch_spmm_impl(const Csr& A, const BlockDesc* b, int32_t n_blocks, size_t
 }
 
 
-// Build the SpMM tile tables (lazily, at the first k > 1 apply): per block the sorted unique columns, per nonzero the
-// position of its column in that list.  Host threads over blocks; one-time cost.
-void build_tiles(Csr& A) {
-  constexpr int KT = 8;
-  if (A.nnz == 0 || A.h_blocks_all.empty() || env_int("JP_SPMM_TILE", 0) == 0) {  // opt-in: measured slower than the gather kernel (profiles/)
-    A.tile_state = -1;
-    return;
-  }
-  std::vector<int32_t> ci((size_t)A.nnz);
-  JP_CUDA(cudaStreamSynchronize(ctx().compute));
-  JP_CUDA(cudaMemcpy(ci.data(), A.colind.p, (size_t)A.nnz * 4, cudaMemcpyDeviceToHost));
-  std::vector<BlockDesc>& all = A.h_blocks_all;
-  TileTables t;
-  if (!build_tile_tables(ci, all, A.nnz_cap, KT, t)) {
-    A.tile_state = -1;
-    return;
-  }
-  // the interior / boundary lists are subsequences of the all-list: copy the patched fields over
-  auto patch = [&](std::vector<BlockDesc>& lst) {
-    size_t j = 0;
-    for (BlockDesc& d : lst) {
-      while (all[j].row0 != d.row0) ++j;
-      d.ucol0 = all[j].ucol0;
-      d.ucount = all[j].ucount;
-    }
-  };
-  patch(A.h_blocks_interior);
-  patch(A.h_blocks_boundary);
-  A.ucols.alloc(t.ucols.size() * 4);
-  A.lidx.alloc(t.lidx.size() * 2);
-  JP_CUDA(cudaMemcpy(A.ucols.p, t.ucols.data(), t.ucols.size() * 4, cudaMemcpyHostToDevice));
-  JP_CUDA(cudaMemcpy(A.lidx.p, t.lidx.data(), t.lidx.size() * 2, cudaMemcpyHostToDevice));
-  upload_blocks(A.h_blocks_interior, A.blocks_interior, A.n_blocks_interior);
-  upload_blocks(A.h_blocks_boundary, A.blocks_boundary, A.n_blocks_boundary);
-  upload_blocks(A.h_blocks_all, A.blocks_all, A.n_blocks_all);
-  A.tile_umax = t.umax;
-  A.tile_state = 1;
-}
-
-// Build the tables of the SpMM runs path (lazily, at the first k > 1 apply); one-time host cost like build_tiles.
+// Build the tables of the SpMM runs path (lazily, at the first k > 1 apply); a one-time host cost.  One configuration:
+// 128 rows per block, one lane per row, 4 vectors per tile -- the best of the twelve measured in round 1
+// (profiles/r1_spmm_ab_runs_tma_27pt128.json) and of the double-buffered variant measured in round 2
+// (profiles/r2_spmm192_variants.json); the others are gone.
+constexpr int kRunsCap = 3456, kRunsKT = 4, kRunsThreads = 128;
 void build_runs(Csr& A) {
   if (A.nnz == 0 || A.n_rows == 0 || env_int("JP_SPMM_RUNS", 1) == 0) {  // on by default; only banded matrices pass build_run_tables
     A.runs_state = -1;
     return;
   }
-  const int cap = env_int("JP_SPMM_RUNS_CAP", 3456);
-  const int kt = env_int("JP_SPMM_RUNS_KT", 4);
-  JP_REQUIRE(cap >= 256 && cap <= 8192 && cap % 4 == 0, "JP_SPMM_RUNS_CAP must be a multiple of 4 in [256,8192]");
-  JP_REQUIRE(kt == 4 || kt == 8, "JP_SPMM_RUNS_KT must be 4 or 8");
-  const int threads = env_int("JP_SPMM_RUNS_THREADS", 128);
-  JP_REQUIRE(threads == 64 || threads == 128 || threads == 256, "JP_SPMM_RUNS_THREADS must be 64, 128 or 256");
-  const int max_rows = env_int("JP_SPMM_RUNS_ROWS", 128);  // one lane per row with 128 threads: measured best (profiles/)
-  JP_REQUIRE(max_rows >= 16 && max_rows <= kRunsMaxRows, "JP_SPMM_RUNS_ROWS must be in [16,128]");
+  const int cap = kRunsCap, kt = kRunsKT, max_rows = kRunsMaxRows;
   if (A.max_row_len > cap) {  // a row longer than the stage would be a LONGROW block: not this kernel's matrix (no download needed)
     A.runs_state = -1;
     return;
@@ -293,9 +254,6 @@ void build_runs(Csr& A) {
   upload_blocks(bi, A.runs_blocks_interior, A.n_runs_blocks_interior);
   A.runs_wmax = t.wmax;
   A.runs_cap = cap;
-  A.runs_kt = kt;
-  A.runs_threads = threads;
-  A.runs_db = env_int("JP_SPMM_RUNS_DB", 0) != 0;
   A.runs_state = 1;
 }
 
@@ -307,39 +265,6 @@ void launch_spmm_runs_impl(const Csr& A, const BlockDesc* b, int32_t n_blocks, c
   set_smem_attr(spmm_runs_kernel<KT, THREADS>, smem);
   spmm_runs_kernel<KT, THREADS><<<n_blocks, THREADS, smem, stream>>>(b, A.rowptr.as<int32_t>(), A.vals.as<double>(), A.runs_lidx.as<uint16_t>(),
                                                                       A.runs.as<int2>(), x, ldx, y, ldy, k, A.runs_cap, wpad, alpha, beta);
-}
-
-template <int KT, int THREADS>
-void launch_spmm_runs_db_impl(const Csr& A, const BlockDesc* b, int32_t n_blocks, const double* x, int64_t ldx, double* y, int64_t ldy,
-                              int32_t k, double alpha, double beta, cudaStream_t stream) {
-  const int wpad = (A.runs_wmax + 1) & ~1;
-  const size_t smem = runs_db_smem_bytes(A.runs_cap, wpad, KT);
-  set_smem_attr(spmm_runs_db_kernel<KT, THREADS>, smem);
-  spmm_runs_db_kernel<KT, THREADS><<<n_blocks, THREADS, smem, stream>>>(b, A.rowptr.as<int32_t>(), A.vals.as<double>(),
-                                                                         A.runs_lidx.as<uint16_t>(), A.runs.as<int2>(), x, ldx, y, ldy, k,
-                                                                         A.runs_cap, wpad, alpha, beta);
-}
-
-template <bool HALO>
-void launch_spmm_tile(const Csr& A, const BlockDesc* b, int32_t n_blocks, const double* x, int64_t ldx, const double* halo, int32_t halo_k,
-                      double* y, int64_t ldy, int32_t k, double alpha, double beta, cudaStream_t stream) {
-  constexpr int KT = 8;
-  const int upad = (A.tile_umax + 3) & ~3;
-  static const int pipe = env_int("JP_SPMM_PIPE", 1);
-  if (pipe) {
-    const size_t smem = 2 * pipe_stage_bytes(A.nnz_cap, upad, KT);
-    set_smem_attr(spmm_pipe_kernel<KT, HALO>, smem);
-    const int grid = std::min<int>(n_blocks, ctx().sm_count);
-    spmm_pipe_kernel<KT, HALO><<<grid, kPipeThreads, smem, stream>>>(b, n_blocks, A.rowptr.as<int32_t>(), A.vals.as<double>(),
-                                                                      A.lidx.as<uint16_t>(), A.ucols.as<int32_t>(), x, ldx, halo, halo_k,
-                                                                      HALO ? A.n_local_cols : A.n_cols, y, ldy, k, A.nnz_cap, upad, alpha, beta);
-    return;
-  }
-  const size_t smem = tile_smem_bytes(A.nnz_cap, upad, KT);
-  set_smem_attr(spmm_tile_kernel<KT, HALO>, smem);
-  spmm_tile_kernel<KT, HALO><<<n_blocks, kTileThreads, smem, stream>>>(b, A.rowptr.as<int32_t>(), A.colind.as<int32_t>(), A.vals.as<double>(),
-                                                                        A.lidx.as<uint16_t>(), A.ucols.as<int32_t>(), x, ldx, halo, halo_k,
-                                                                        HALO ? A.n_local_cols : A.n_cols, y, ldy, k, A.nnz_cap, upad, alpha, beta);
 }
 
 }  // namespace
@@ -354,6 +279,8 @@ static FusedSpmvArgs fused_args(const Csr& A, const FusedHalo& h, const double* 
   static const int pack_rows = std::max(64, env_int("JP_FUSED_PACK_ROWS", 1024));  // exported rows per pack item
   a.n_items = std::max(1, std::min(64, (h.n_export + pack_rows - 1) / pack_rows));
   a.n_pack = a.n_items;  // one dedicated CTA per item at the head of the grid (boundary CTAs claim whatever is left)
+  static const int first_pct = std::min(100, std::max(0, env_int("JP_FUSED_BOUNDARY_AT", 75)));  // % of the interior blocks in front
+  a.n_first = (int32_t)((int64_t)a.n_interior * first_pct / 100);
   a.rowptr = A.rowptr.as<int32_t>();
   a.colind = A.colind.as<int32_t>();
   a.vals = A.vals.as<double>();
@@ -380,8 +307,20 @@ void launch_spmv_fused(const Csr& A, const FusedHalo& h, const double* x, const 
 
 // decide (once per matrix) which SpMM path k > 1 applies take
 void csr_prepare_spmm(Csr& A) {
-  if (A.tile_state == 0) build_tiles(A);
-  if (A.runs_state == 0) build_runs(A);
+  csr_prepare_dia(A);
+  if (A.runs_state == 0) {
+    // a single-rank diagonal-structured matrix is served by the diagonal kernel alone: no run tables needed
+    if (A.dia_state == 1) A.runs_state = -1;
+    else build_runs(A);
+  }
+}
+
+void launch_spmm_gather_blocks(const Csr& A, const void* blocks, int32_t n_blocks, const double* x, int64_t ldx, double* y, int64_t ldy,
+                               int32_t k, double alpha, double beta, cudaStream_t stream) {
+  if (n_blocks == 0) return;
+  launch_spmm_impl<false, 1>(A, static_cast<const BlockDesc*>(blocks), n_blocks, stage_smem_bytes(A.nnz_cap), x, ldx, nullptr, 1, y, ldy, k, alpha,
+                             beta, stream);
+  JP_LAUNCH_CHECK();
 }
 
 // jp_apply_dot workspace of `n` CTA partials: [partials n | level-2 partials | result | ticket]; zeroed when (re)allocated
@@ -451,33 +390,25 @@ void launch_spmv_blocks(const Csr& A, const void* blocks_int4, int32_t n_blocks,
                         const double* halo, int32_t halo_k, double* y, int64_t ldy, int32_t k, double alpha, double beta,
                         cudaStream_t stream) {
   if (n_blocks == 0 || k == 0) return;
-  // lazily build the SpMM tables (tile path: the block lists are re-uploaded in place -- same buffers, same order)
+  // lazily decide the SpMM path of this matrix
   if (k > 1) csr_prepare_spmm(const_cast<Csr&>(A));
   // the run-staged kernel serves launches over the WHOLE all-blocks or interior list (it has its own block lists with a
   // different geometry; a chunk of a list, as jp_apply_host launches, stays with the gather kernel)
   const bool whole_all = blocks_int4 == A.blocks_all.p && n_blocks == A.n_blocks_all;
   // (the interior-only launch is the compute-stream half of the multi-GPU two-stream path)
   const bool whole_interior = blocks_int4 == A.blocks_interior.p && n_blocks == A.n_blocks_interior;
-  if (k > 1 && A.runs_state == 1 && !use_halo && (ldx & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
-      (whole_all || whole_interior)) {
+  const bool tma_ok = (ldx & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;  // bulk copies need 16-byte aligned sources
+  if (k > 1 && A.dia_state == 1 && !use_halo && tma_ok && whole_all) {
+    launch_spmm_dia(A, x, ldx, y, ldy, k, alpha, beta, stream);  // diagonal-structured matrix
+    return;
+  }
+  if (k > 1 && A.runs_state == 1 && !use_halo && tma_ok && (whole_all || whole_interior)) {
     // banded matrix, no halo columns in this launch
     const bool all = whole_all;
     const BlockDesc* rb = (all ? A.runs_blocks_all : A.runs_blocks_interior).as<BlockDesc>();
     const int32_t rn = all ? A.n_runs_blocks_all : A.n_runs_blocks_interior;
-    // double-buffered tiles (round-2 candidate, JP_SPMM_RUNS_DB=1): KT = 4 with 128 or 256 threads, when two tile
-    // buffers fit the shared memory
-    const bool db = A.runs_db && A.runs_kt == 4 && A.runs_threads != 64 && k > 4 &&
-                    runs_db_smem_bytes(A.runs_cap, (A.runs_wmax + 1) & ~1, 4) <= 220 * 1024;
-    if (rn > 0 && db) {
-      if (A.runs_threads == 256) launch_spmm_runs_db_impl<4, 256>(A, rb, rn, x, ldx, y, ldy, k, alpha, beta, stream);
-      else launch_spmm_runs_db_impl<4, 128>(A, rb, rn, x, ldx, y, ldy, k, alpha, beta, stream);
-      JP_LAUNCH_CHECK();
-    } else if (rn > 0) {
-      if (A.runs_kt == 8 && A.runs_threads == 256) launch_spmm_runs_impl<8, 256>(A, rb, rn, x, ldx, y, ldy, k, alpha, beta, stream);
-      else if (A.runs_kt == 8) launch_spmm_runs_impl<8, 128>(A, rb, rn, x, ldx, y, ldy, k, alpha, beta, stream);
-      else if (A.runs_threads == 256) launch_spmm_runs_impl<4, 256>(A, rb, rn, x, ldx, y, ldy, k, alpha, beta, stream);
-      else if (A.runs_threads == 64) launch_spmm_runs_impl<4, 64>(A, rb, rn, x, ldx, y, ldy, k, alpha, beta, stream);
-      else launch_spmm_runs_impl<4, 128>(A, rb, rn, x, ldx, y, ldy, k, alpha, beta, stream);
+    if (rn > 0) {
+      launch_spmm_runs_impl<kRunsKT, kRunsThreads>(A, rb, rn, x, ldx, y, ldy, k, alpha, beta, stream);
       JP_LAUNCH_CHECK();
     }
     return;
@@ -493,9 +424,6 @@ void launch_spmv_blocks(const Csr& A, const void* blocks_int4, int32_t n_blocks,
       if (tma) launch_spmv_impl<false, 1>(A, b, n_blocks, smem, x, nullptr, y, alpha, beta, stream);
       else launch_spmv_impl<false, 0>(A, b, n_blocks, smem, x, nullptr, y, alpha, beta, stream);
     }
-  } else if (A.tile_state == 1) {
-    if (use_halo) launch_spmm_tile<true>(A, b, n_blocks, x, ldx, halo, halo_k, y, ldy, k, alpha, beta, stream);
-    else launch_spmm_tile<false>(A, b, n_blocks, x, ldx, nullptr, 1, y, ldy, k, alpha, beta, stream);
   } else {
     if (use_halo) {
       if (tma) launch_spmm_impl<true, 1>(A, b, n_blocks, smem, x, ldx, halo, halo_k, y, ldy, k, alpha, beta, stream);
@@ -549,9 +477,9 @@ void csr_finalize_structure(Csr& A, const std::vector<int32_t>& rp, const std::v
   if (const char* v = std::getenv("JP_SPMV_DIRECT_RATIO"))
     if (*v) rule.ratio = std::atof(v);
   JP_REQUIRE(rule.maxlen >= 1 && rule.ratio >= 1.0, "JP_SPMV_DIRECT_MAXLEN must be >= 1 and JP_SPMV_DIRECT_RATIO >= 1");
-  if (const char* v = std::getenv("JP_SPMV_SUBWARP_DIV"))  // 0: irregular blocks take the two-phase path (A/B measurements)
+  if (const char* v = std::getenv("JP_SPMV_SUBWARP_DIV"))  // lanes per irregular row = mean row length / this (tuning knob)
     if (*v) rule.subwarp_div = std::atof(v);
-  JP_REQUIRE(rule.subwarp_div >= 0.0, "JP_SPMV_SUBWARP_DIV must be >= 0");
+  JP_REQUIRE(rule.subwarp_div > 0.0, "JP_SPMV_SUBWARP_DIV must be > 0");
   build_blocks(rp, cls, cap, max_rows, env_int("JP_SPMV_DIRECT", 1) != 0, bi, bb, ba, rule);
   upload_blocks(bi, A.blocks_interior, A.n_blocks_interior);
   upload_blocks(bb, A.blocks_boundary, A.n_blocks_boundary);
@@ -679,10 +607,14 @@ int32_t jp_csr_spmm_info(jp_handle A, int64_t* info) {
   return guarded([&] {
     Csr* a = get<Csr>(A, Kind::Csr, "csr matrix");
     JP_REQUIRE(info != nullptr, "jp_csr_spmm_info: null output");
-    info[0] = a->tile_state;
+    info[0] = -1;  // (the shared-memory tile tables of round 1 are gone)
     info[1] = a->runs_state;
     info[2] = a->n_runs_blocks_all;
     info[3] = a->runs_wmax;
+    info[4] = a->dia_state;
+    info[5] = csr_dia_info(*a, 0);
+    info[6] = csr_dia_info(*a, 1);
+    info[7] = csr_dia_info(*a, 2);
   });
 }
 

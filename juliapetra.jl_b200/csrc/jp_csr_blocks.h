@@ -16,13 +16,12 @@ inline size_t stage_smem_bytes(int cap) { return (size_t)(cap + 8) * 12 + (size_
 // cut rows into blocks; cls[r] = 1 when the row touches a remote column
 // Which blocks go thread-per-row straight from the stage (KIND_DIRECT): longest row <= direct_maxlen and
 // longest row <= direct_ratio * mean row length of the block.  32 and 2 are what round 1 measured on stencils; both are
-// tuning knobs (JP_SPMV_DIRECT_MAXLEN, JP_SPMV_DIRECT_RATIO) because irregular short-row blocks may be better off
-// without the shared-memory round trip of the two-phase path even at some lane divergence.
+// tuning knobs (JP_SPMV_DIRECT_MAXLEN, JP_SPMV_DIRECT_RATIO).
 struct DirectRule {
   int32_t maxlen = 32;
   double ratio = 2.0;
-  // irregular blocks: 0 = TWOPHASE / WARPROW (products through shared memory), otherwise KIND_SUBWARP with
-  // T = the largest power of two <= mean row length of the block / subwarp_div lanes per row (2 <= T <= 32)
+  // every other block is KIND_SUBWARP with T = the largest power of two <= mean row length of the block / subwarp_div
+  // lanes per row (2 <= T <= 32); 1.5 = 8 lanes at mean length 16, measured best of 4 / 8 / 16 on the power-law matrix
   double subwarp_div = 1.5;
 };
 
@@ -46,12 +45,12 @@ inline void build_blocks(const std::vector<int32_t>& rp, const std::vector<uint8
       const int64_t nrows = r - start, nnzb = rp[r] - nnz0;
       // near-uniform short rows: max <= 2 * mean  ->  thread-per-row straight from the stage
       if (allow_direct && maxlen <= rule.maxlen && (double)maxlen * (double)nrows <= rule.ratio * (double)nnzb + 32.0) kind = KIND_DIRECT;
-      else if (rule.subwarp_div > 0.0) {
+      else {
         const double target = (double)nnzb / (double)std::max<int64_t>(nrows, 1) / rule.subwarp_div;
         int lg = 1;
         while (lg < 5 && (double)(2 << lg) <= target) ++lg;
         kind = KIND_SUBWARP | (lg << 4);  // shifted by 16 below: the lane count lands in bits 20..23
-      } else kind = maxlen > kLongRowLen ? KIND_WARPROW : KIND_TWOPHASE;
+      }
     }
     BlockDesc b;
     b.row0 = start;
@@ -63,68 +62,6 @@ inline void build_blocks(const std::vector<int32_t>& rp, const std::vector<uint8
     all.push_back(b);
   }
 }
-
-// SpMM tile tables: per block the sorted unique columns it references, per nonzero the position of its column in that
-// list.  Returns false (tables unusable) when the matrix has a LONGROW block, when columns are hardly shared between
-// the rows of a block, or when two stages do not fit the shared memory.
-struct TileTables {
-  std::vector<int32_t> ucols;
-  std::vector<uint16_t> lidx;
-  int32_t umax = 0;
-};
-
-inline bool build_tile_tables(const std::vector<int32_t>& ci, std::vector<BlockDesc>& all, int32_t nnz_cap, int KT, TileTables& out) {
-  const size_t nb = all.size();
-  const size_t nnz = ci.size();
-  std::vector<int32_t> ubuf(nnz);  // block b's unique list is built in place at [p0, p0 + ucount)
-  out.lidx.assign(nnz + 64, 0);
-  const int nthreads = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
-  bool has_longrow = false;
-  auto worker = [&](int tix) {
-    for (size_t bi = tix; bi < nb; bi += nthreads) {
-      BlockDesc& b = all[bi];
-      b.ucount = 0;
-      if (((b.nrows_kind >> 16) & 0xf) == KIND_LONGROW) {
-        has_longrow = true;  // (benign race: only ever set to true)
-        continue;
-      }
-      int32_t* u = ubuf.data() + b.p0;
-      const int32_t n = b.p1 - b.p0;
-      std::copy(ci.begin() + b.p0, ci.begin() + b.p1, u);
-      std::sort(u, u + n);
-      const int32_t uc = (int32_t)(std::unique(u, u + n) - u);
-      b.ucount = uc;
-      for (int32_t i = b.p0; i < b.p1; ++i) out.lidx[i] = (uint16_t)(std::lower_bound(u, u + uc, ci[i]) - u);
-    }
-  };
-  {
-    std::vector<std::thread> th;
-    for (int t = 1; t < nthreads; ++t) th.emplace_back(worker, t);
-    worker(0);
-    for (auto& t : th) t.join();
-  }
-  int64_t sum_u = 0, sum_nnz = 0, off = 0;
-  int32_t umax = 0;
-  for (BlockDesc& b : all) {
-    b.ucol0 = (int32_t)off;
-    off += (b.ucount + 3) & ~3;
-    umax = std::max(umax, b.ucount);
-    if (b.ucount) {
-      sum_u += b.ucount;
-      sum_nnz += b.p1 - b.p0;
-    }
-  }
-  const int upad = (umax + 3) & ~3;
-  // worth it only when columns are shared between the rows of a block, and the tile has to fit beside the stage
-  if (has_longrow || sum_nnz == 0 || (double)sum_u > 0.7 * (double)sum_nnz || 2 * pipe_stage_bytes(nnz_cap, upad, KT) > 220 * 1024 ||
-      off > INT32_MAX - 64)
-    return false;
-  out.ucols.assign((size_t)off + 64, 0);
-  for (const BlockDesc& b : all) std::copy(ubuf.begin() + b.p0, ubuf.begin() + b.p0 + b.ucount, out.ucols.begin() + b.ucol0);
-  out.umax = umax;
-  return true;
-}
-
 
 // SpMM "runs" path (spmm_runs_kernel): per block the columns it references, merged into 16-byte ALIGNED RUNS
 // (start even, length even) so that the block's X tile can be copied global -> shared with 16-byte cp.async, and per

@@ -12,10 +12,11 @@ namespace csrk {
 
 constexpr int kSpmvThreads = 256;
 constexpr int kMaxRowsPerBlock = 512;   // rows staged per block (row pointers in shared memory)
-constexpr int kLongRowLen = 64;         // blocks holding a row longer than this reduce warp-per-row
 
-// KIND_SUBWARP carries log2(lanes per row) in bits 20..23 of BlockDesc::nrows_kind
-enum BlockKind : int { KIND_DIRECT = 0, KIND_TWOPHASE = 1, KIND_WARPROW = 2, KIND_LONGROW = 3, KIND_SUBWARP = 4 };
+// KIND_SUBWARP carries log2(lanes per row) in bits 20..23 of BlockDesc::nrows_kind.  (Kinds 1 and 2 were round 1's
+// two-phase paths -- products through shared memory, then thread- or warp-per-row sums -- replaced by KIND_SUBWARP:
+// profiles/r2_powerlaw10M_subwarp_ab.json.)
+enum BlockKind : int { KIND_DIRECT = 0, KIND_LONGROW = 3, KIND_SUBWARP = 4 };
 constexpr int kSubwarpLongFactor = 16;  // SUBWARP blocks: rows longer than this many passes of their lane group go warp-per-row
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -29,18 +30,6 @@ __device__ __forceinline__ double warp_sum(double v) {
 __device__ __forceinline__ double combine(double yold, double sum, double alpha, double beta) {
   double s = __dmul_rn(sum, alpha);
   return beta == 0.0 ? s : __dadd_rn(__dmul_rn(yold, beta), s);
-}
-
-// left-to-right sum of s_val[s..e) (the reference's order); four shared loads are issued ahead of the adds
-__device__ __forceinline__ double row_sum_sequential(const double* s_val, int s, int e) {
-  double sum = 0.0;
-  int i = s;
-  for (; i + 4 <= e; i += 4) {
-    const double a0 = s_val[i], a1 = s_val[i + 1], a2 = s_val[i + 2], a3 = s_val[i + 3];
-    sum = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(sum, a0), a1), a2), a3);
-  }
-  for (; i < e; ++i) sum = __dadd_rn(sum, s_val[i]);
-  return sum;
 }
 
 // shared-memory stage: vals [cap+8] | colind [cap+8] | row pointers [kMaxRowsPerBlock+8]
@@ -268,62 +257,7 @@ __device__ __forceinline__ double spmv_block(const BlockRange& b, const StageVie
     }
     return dacc;
   }
-  // phase A: products, thread-per-nonzero (every gather of the block is independent of row structure);
-  // 8 nonzeros per thread per pass so 8 gathers are in flight before the first product is needed
-  const int s0 = b.p0 - b.a0, s1 = b.p1 - b.a0;
-  for (int base = s0 + tid; base < s1; base += 8 * kSpmvThreads) {
-    int c[8];
-    double xv[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int i = base + q * kSpmvThreads;
-      c[q] = i < s1 ? sv.s_col[i] : -1;
-    }
-#pragma unroll
-    for (int q = 0; q < 8; ++q)
-      xv[q] = c[q] < 0 ? 0.0 : ((HALO && c[q] >= nloc) ? halo[c[q] - nloc] : __ldg(x + c[q]));
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int i = base + q * kSpmvThreads;
-      if (i < s1) sv.s_val[i] = __dmul_rn(sv.s_val[i], xv[q]);
-    }
-  }
-  __syncthreads();
-  // phase B: row sums
-  if (b.kind == KIND_TWOPHASE) {
-    for (int r = tid; r < b.nrows; r += kSpmvThreads) {
-      const int s = rp[r] - b.a0, e = rp[r + 1] - b.a0;
-      double* yp = y + b.row0 + r;
-      const double ynew = combine(beta == 0.0 ? 0.0 : *yp, row_sum_sequential(sv.s_val, s, e), alpha, beta);
-      *yp = ynew;
-      if (DOT) dacc += (r == tid ? w_first : __ldg(w + b.row0 + r)) * ynew;
-    }
-  } else {
-    // WARPROW: the block holds at least one long row.  Short rows still go thread-per-row (sequential sum, the
-    // reference's order); only rows longer than kLongRowLen are summed by a whole warp.
-    for (int r = tid; r < b.nrows; r += kSpmvThreads) {
-      const int s = rp[r] - b.a0, e = rp[r + 1] - b.a0;
-      if (e - s <= kLongRowLen) {
-        double* yp = y + b.row0 + r;
-        *yp = combine(beta == 0.0 ? 0.0 : *yp, row_sum_sequential(sv.s_val, s, e), alpha, beta);
-        if (DOT) dacc += __ldg(w + b.row0 + r) * *yp;
-      }
-    }
-    const int lane = tid & 31, warp = tid >> 5;
-    for (int r = warp; r < b.nrows; r += kSpmvThreads / 32) {
-      const int s = rp[r] - b.a0, e = rp[r + 1] - b.a0;
-      if (e - s <= kLongRowLen) continue;  // warp-uniform
-      double sum = 0.0;
-      for (int i = s + lane; i < e; i += 32) sum += sv.s_val[i];
-      sum = warp_sum(sum);
-      if (lane == 0) {
-        double* yp = y + b.row0 + r;
-        *yp = combine(beta == 0.0 ? 0.0 : *yp, sum, alpha, beta);
-        if (DOT) dacc += __ldg(w + b.row0 + r) * *yp;
-      }
-    }
-  }
-  return dacc;
+  return dacc;  // (every block kind returns above)
 }
 
 // One partial per WARP: partials[bid * (kSpmvThreads / 32) + warp] = sum of `v` over the warp's lanes.  No block-level
@@ -346,7 +280,7 @@ __device__ __forceinline__ void warp_partial_store(double v, double* __restrict_
 constexpr unsigned kSumChunk = kSpmvThreads * 16;
 __host__ __device__ inline unsigned sum_partials_grid(unsigned n) { return n == 0 ? 1u : (n + kSumChunk - 1) / kSumChunk; }
 
-__global__ void __launch_bounds__(kSpmvThreads) sum_partials_kernel(const double* __restrict__ partials, unsigned n, double* __restrict__ out,
+static __global__ void __launch_bounds__(kSpmvThreads) sum_partials_kernel(const double* __restrict__ partials, unsigned n, double* __restrict__ out,
                                                                       double* __restrict__ level2, unsigned int* __restrict__ ticket) {
   __shared__ double s_red[kSpmvThreads / 32];
   __shared__ bool s_last;
@@ -436,7 +370,7 @@ spmm_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ ro
   stage_block<TMA>(sv, &s_bar, rowptr, colind, vals, b);
   const int32_t* rp = sv.s_rp + b.rpo;
   // blocks holding long rows use a full warp per row; otherwise T lanes per row from the matrix statistics
-  const int Tb = b.kind == KIND_WARPROW ? 32 : (b.kind == KIND_SUBWARP && (1 << b.lg) > T) ? (1 << b.lg) : T;
+  const int Tb = (b.kind == KIND_SUBWARP && (1 << b.lg) > T) ? (1 << b.lg) : T;
   const int lane_t = tid & (Tb - 1), group = tid / Tb, ngroups = kSpmvThreads / Tb;
   for (int v0 = 0; v0 < k; v0 += KT) {
     const int kt = k - v0 < KT ? k - v0 : KT;  // warp-uniform
@@ -491,289 +425,6 @@ spmm_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ ro
             *yp = combine(beta == 0.0 ? 0.0 : *yp, acc[j], alpha, beta);
           }
       }
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// SpMM with the multivector tile staged in shared memory (banded / stencil-like matrices).
-// A k-vector apply gathers nnz*k doubles of X; with X only in L1/L2 that traffic (12 GB for 27-pt 192^3, k = 8) is
-// several times the matrix stream and the L1 that is left beside the staged matrix (~20 KB) cannot hold a block's
-// working set.  At build time every row block gets the sorted list of the UNIQUE columns it references (ucols) and
-// every nonzero the uint16 position of its column in that list (lidx).  The kernel stages vals, lidx, row pointers
-// and ucols with TMA bulk copies, gathers the block's X tile [KT vectors] x [unique columns] ONCE into shared
-// memory (coalesced along the column runs of a banded matrix; a column referenced by 3 neighbouring rows is
-// fetched once, not 3 times), then runs thread-per-row out of shared memory.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int kTileThreads = 256;
-
-struct TileStage {
-  double* s_val;    // [cap + 8]
-  double* xs;       // [KT][upad]
-  int32_t* s_rp;    // [kMaxRowsPerBlock + 8]
-  int32_t* s_ucol;  // [upad]
-  uint16_t* s_lidx; // [cap + 16]
-};
-__host__ __device__ inline size_t tile_smem_bytes(int cap, int upad, int KT) {
-  return (size_t)(cap + 8) * 8 + (size_t)KT * upad * 8 + (size_t)(kMaxRowsPerBlock + 8) * 4 + (size_t)upad * 4 + (size_t)(cap + 16) * 2;
-}
-
-template <int KT, bool HALO>
-__global__ void __launch_bounds__(kTileThreads)
-spmm_tile_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
-                 const double* __restrict__ vals, const uint16_t* __restrict__ lidx, const int32_t* __restrict__ ucols,
-                 const double* __restrict__ x, int64_t ldx, const double* __restrict__ halo, int32_t halo_k, int32_t nloc,
-                 double* __restrict__ y, int64_t ldy, int32_t k, int32_t cap, int32_t upad, double alpha, double beta) {
-  JP_DYN_SMEM(smem_raw);
-  __shared__ double s_red[kTileThreads / 32];
-  __shared__ __align__(8) uint64_t s_bar;
-  TileStage t;
-  t.s_val = reinterpret_cast<double*>(smem_raw);
-  t.xs = t.s_val + cap + 8;
-  t.s_rp = reinterpret_cast<int32_t*>(t.xs + (size_t)KT * upad);
-  t.s_ucol = t.s_rp + kMaxRowsPerBlock + 8;
-  t.s_lidx = reinterpret_cast<uint16_t*>(t.s_ucol + upad);
-  const BlockRange b = decode_block(blocks, blockIdx.x);
-  const int4 aux = __ldg(reinterpret_cast<const int4*>(blocks + blockIdx.x) + 1);
-  const int ucol0 = aux.x, U = aux.y;
-  const int tid = threadIdx.x;
-  if (b.kind == KIND_LONGROW) {
-    long_row<HALO>(colind, vals, x, ldx, halo, halo_k, nloc, y, ldy, k, b.row0, b.p0, b.p1, alpha, beta, s_red);
-    return;
-  }
-  // stage: vals, lidx, row pointers, unique columns (four TMA bulk copies)
-  const int ngrp = (b.p1 - b.a0 + 3) >> 2;
-  const int al0 = b.p0 & ~7;                       // 16-byte aligned first staged lidx
-  const int nl8 = (b.p1 - al0 + 7) & ~7;           // lidx staged (multiple of 8)
-  const int ra0 = b.row0 & ~3;
-  const int nrp = (b.row0 + b.nrows + 1 - ra0 + 3) & ~3;
-  const int nu4 = (U + 3) & ~3;
-  if (tid == 0) mbar_init(&s_bar, 1);
-  __syncthreads();
-  if (tid == 0) {
-    const uint64_t pol = policy_evict_first();
-    mbar_expect_tx(&s_bar, (unsigned)(ngrp * 32 + nl8 * 2 + nrp * 4 + nu4 * 4));
-    if (ngrp > 0) bulk_g2s(t.s_val, vals + b.a0, (unsigned)ngrp * 32, &s_bar, pol);
-    if (nl8 > 0) bulk_g2s(t.s_lidx, lidx + al0, (unsigned)nl8 * 2, &s_bar, pol);
-    bulk_g2s(t.s_rp, rowptr + ra0, (unsigned)nrp * 4, &s_bar, pol);
-    if (nu4 > 0) bulk_g2s(t.s_ucol, ucols + ucol0, (unsigned)nu4 * 4, &s_bar, pol);
-  }
-  mbar_wait(&s_bar, 0);
-  const int32_t* rp = t.s_rp + b.rpo;
-  // lanes per row: as many as keep every thread busy, at most 4 (warp-uniform, power of two)
-  int T = 1;
-  while (T < 4 && b.nrows * (T << 1) <= kTileThreads) T <<= 1;
-  const int lane_t = tid & (T - 1), group = tid / T, ngroups = kTileThreads / T;
-  for (int v0 = 0; v0 < k; v0 += KT) {
-    // X tile: xs[j][u] = X[ucol[u], v0 + j]
-    for (int u = tid; u < U; u += kTileThreads) {
-      const int c = t.s_ucol[u];
-      if (HALO && c >= nloc) {
-        const double* h = halo + (size_t)(c - nloc) * halo_k + v0;
-#pragma unroll
-        for (int j = 0; j < KT; ++j)
-          if (v0 + j < k) t.xs[(size_t)j * upad + u] = h[j];
-      } else {
-        const double* xc = x + c + (size_t)v0 * ldx;
-#pragma unroll
-        for (int j = 0; j < KT; ++j)
-          if (v0 + j < k) t.xs[(size_t)j * upad + u] = __ldg(xc + (size_t)j * ldx);
-      }
-    }
-    __syncthreads();
-    for (int rbase = 0; rbase < b.nrows; rbase += ngroups) {  // warp-uniform trip count (shuffles below)
-      const int r = rbase + group;
-      const bool valid = r < b.nrows;
-      const int s = valid ? rp[r] : 0, e = valid ? rp[r + 1] : 0;
-      double acc[KT];
-#pragma unroll
-      for (int j = 0; j < KT; ++j) acc[j] = 0.0;
-      for (int i = s + lane_t; i < e; i += T) {
-        const int li = t.s_lidx[i - al0];
-        const double v = t.s_val[i - b.a0];
-#pragma unroll
-        for (int j = 0; j < KT; ++j) acc[j] = fma(v, t.xs[(size_t)j * upad + li], acc[j]);
-      }
-      for (int o = T >> 1; o > 0; o >>= 1) {
-#pragma unroll
-        for (int j = 0; j < KT; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-      }
-      if (valid && lane_t == 0) {
-#pragma unroll
-        for (int j = 0; j < KT; ++j)
-          if (v0 + j < k) {
-            double* yp = y + b.row0 + r + (size_t)(v0 + j) * ldy;
-            *yp = combine(beta == 0.0 ? 0.0 : *yp, acc[j], alpha, beta);
-          }
-      }
-    }
-    __syncthreads();  // the next vector tile overwrites xs
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Pipelined SpMM: persistent CTAs (one per SM), two shared-memory stages, warp specialisation.
-//   producer warps (8): wait(empty[s]) -> TMA bulk copies of the block's vals / lidx / row pointers / unique columns
-//                       -> gather the block's X tile [KT vectors] x [unique columns] into shared memory -> arrive(full[s])
-//   consumer warps (8): wait(full[s]) -> T lanes per row out of shared memory, KT accumulators in registers -> y
-//                       -> arrive(empty[s])
-// so the TMA latency and the X-tile gather of item i+1 overlap the arithmetic of item i.  An item is one
-// (row block, vector tile) pair; the tiles of a block run back to back on the same CTA.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int kPipeConsumers = 256, kPipeProducers = 256, kPipeThreads = kPipeConsumers + kPipeProducers;
-
-
-__host__ __device__ inline size_t pipe_stage_bytes(int cap, int upad, int KT) { return (tile_smem_bytes(cap, upad, KT) + 127) & ~(size_t)127; }
-
-template <int KT, bool HALO>
-__global__ void __launch_bounds__(kPipeThreads, 1)
-spmm_pipe_kernel(const BlockDesc* __restrict__ blocks, int32_t n_blocks, const int32_t* __restrict__ rowptr,
-                 const double* __restrict__ vals, const uint16_t* __restrict__ lidx, const int32_t* __restrict__ ucols,
-                 const double* __restrict__ x, int64_t ldx, const double* __restrict__ halo, int32_t halo_k, int32_t nloc,
-                 double* __restrict__ y, int64_t ldy, int32_t k, int32_t cap, int32_t upad, double alpha, double beta) {
-  JP_DYN_SMEM(smem_raw);
-  __shared__ __align__(8) uint64_t tma_bar[2], full_bar[2], empty_bar[2];
-  const int tid = threadIdx.x, lane = tid & 31;
-  const bool producer = tid >= kPipeConsumers;
-  if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&tma_bar[s], 1);
-      mbar_init(&full_bar[s], kPipeProducers / 32);
-      mbar_init(&empty_bar[s], kPipeConsumers / 32);
-    }
-  }
-  __syncthreads();
-  const size_t stage_bytes = pipe_stage_bytes(cap, upad, KT);
-  const int ntiles = (k + KT - 1) / KT;
-  const int my_blocks = blockIdx.x < n_blocks ? (n_blocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const int total_items = my_blocks * ntiles;  // item = (row block, vector tile); the tiles of a block run back to back
-
-  // stage carve-up
-  auto s_val_of = [&](int s) { return reinterpret_cast<double*>(smem_raw + (size_t)s * stage_bytes); };
-
-  if (producer) {
-    const int ptid = tid - kPipeConsumers;
-    // the TMA of item it+1 is issued before the X tile of item it is gathered, so its latency is hidden
-    auto issue_tma = [&](int it) {
-      const int bi = blockIdx.x + (it / ntiles) * gridDim.x;
-      const BlockRange b = decode_block(blocks, bi);
-      const int4 aux = __ldg(reinterpret_cast<const int4*>(blocks + bi) + 1);
-      const int s = it & 1;
-      const unsigned ph = (it >> 1) & 1;
-      mbar_wait(&empty_bar[s], ph ^ 1);  // the consumers are done with this stage (passes at once the first time)
-      double* s_val = s_val_of(s);
-      double* xs = s_val + cap + 8;
-      int32_t* s_rp = reinterpret_cast<int32_t*>(xs + (size_t)KT * upad);
-      int32_t* s_ucol = s_rp + kMaxRowsPerBlock + 8;
-      uint16_t* s_lidx = reinterpret_cast<uint16_t*>(s_ucol + upad);
-      const int al0 = b.p0 & ~7;
-      const int ngrp = (b.p1 - b.a0 + 3) >> 2;
-      const int nl8 = (b.p1 - al0 + 7) & ~7;
-      const int ra0 = b.row0 & ~3;
-      const int nrp = (b.row0 + b.nrows + 1 - ra0 + 3) & ~3;
-      const int nu4 = (aux.y + 3) & ~3;
-      const uint64_t pol = policy_evict_first();
-      mbar_expect_tx(&tma_bar[s], (unsigned)(ngrp * 32 + nl8 * 2 + nrp * 4 + nu4 * 4));
-      if (ngrp > 0) bulk_g2s(s_val, vals + b.a0, (unsigned)ngrp * 32, &tma_bar[s], pol);
-      if (nl8 > 0) bulk_g2s(s_lidx, lidx + al0, (unsigned)nl8 * 2, &tma_bar[s], pol);
-      bulk_g2s(s_rp, rowptr + ra0, (unsigned)nrp * 4, &tma_bar[s], pol);
-      if (nu4 > 0) bulk_g2s(s_ucol, ucols + aux.x, (unsigned)nu4 * 4, &tma_bar[s], pol);
-    };
-    if (ptid == 0 && total_items > 0) issue_tma(0);
-    for (int it = 0; it < total_items; ++it) {
-      if (ptid == 0 && it + 1 < total_items) issue_tma(it + 1);
-      const int bi = blockIdx.x + (it / ntiles) * gridDim.x;
-      const int4 aux = __ldg(reinterpret_cast<const int4*>(blocks + bi) + 1);
-      const int U = aux.y;
-      const int s = it & 1;
-      const unsigned ph = (it >> 1) & 1;
-      const int v0 = (it % ntiles) * KT;
-      const int kt = k - v0 < KT ? k - v0 : KT;
-      double* xs = s_val_of(s) + cap + 8;
-      const int32_t* s_ucol = reinterpret_cast<const int32_t*>(xs + (size_t)KT * upad) + kMaxRowsPerBlock + 8;
-      mbar_wait(&empty_bar[s], ph ^ 1);  // before overwriting xs of this stage
-      mbar_wait(&tma_bar[s], ph);        // the unique-column list has landed
-      // X tile: xs[j][u] = X[ucol[u], v0 + j]; four columns per thread per pass -> 4*KT loads in flight
-      for (int ub = ptid; ub < U; ub += 4 * kPipeProducers) {
-        int c[4];
-        double a[4][KT];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int u = ub + q * kPipeProducers;
-          c[q] = u < U ? s_ucol[u] : -1;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (c[q] < 0) continue;
-          if (HALO && c[q] >= nloc) {
-            const double* h = halo + (size_t)(c[q] - nloc) * halo_k + v0;
-#pragma unroll
-            for (int j = 0; j < KT; ++j) a[q][j] = j < kt ? h[j] : 0.0;
-          } else {
-            const double* xc = x + c[q] + (size_t)v0 * ldx;
-#pragma unroll
-            for (int j = 0; j < KT; ++j) a[q][j] = j < kt ? __ldg(xc + (size_t)j * ldx) : 0.0;
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (c[q] < 0) continue;
-          const int u = ub + q * kPipeProducers;
-#pragma unroll
-          for (int j = 0; j < KT; ++j) xs[(size_t)j * upad + u] = a[q][j];
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[s]);
-    }
-  } else {
-    for (int it = 0; it < total_items; ++it) {
-      const int bi = blockIdx.x + (it / ntiles) * gridDim.x;
-      const BlockRange b = decode_block(blocks, bi);
-      const int s = it & 1;
-      const unsigned ph = (it >> 1) & 1;
-      const int v0 = (it % ntiles) * KT;
-      const int kt = k - v0 < KT ? k - v0 : KT;
-      const int al0 = b.p0 & ~7;
-      const double* s_val = s_val_of(s);
-      const double* xs = s_val + cap + 8;
-      const int32_t* s_rp = reinterpret_cast<const int32_t*>(xs + (size_t)KT * upad);
-      const uint16_t* s_lidx = reinterpret_cast<const uint16_t*>(s_rp + kMaxRowsPerBlock + 8 + upad);
-      mbar_wait(&full_bar[s], ph);
-      mbar_wait(&tma_bar[s], ph);  // completed long ago; orders this thread after the bulk copies themselves
-      const int32_t* rp = s_rp + b.rpo;
-      int T = 1;
-      while (T < 4 && b.nrows * (T << 1) <= kPipeConsumers) T <<= 1;
-      const int lane_t = tid & (T - 1), group = tid / T, ngroups = kPipeConsumers / T;
-      for (int rbase = 0; rbase < b.nrows; rbase += ngroups) {  // warp-uniform trip count (shuffles below)
-        const int r = rbase + group;
-        const bool valid = r < b.nrows;
-        const int rs = valid ? rp[r] : 0, re = valid ? rp[r + 1] : 0;
-        double acc[KT];
-#pragma unroll
-        for (int j = 0; j < KT; ++j) acc[j] = 0.0;
-#pragma unroll 2
-        for (int i = rs + lane_t; i < re; i += T) {
-          const int li = s_lidx[i - al0];
-          const double v = s_val[i - b.a0];
-#pragma unroll
-          for (int j = 0; j < KT; ++j) acc[j] = fma(v, xs[(size_t)j * upad + li], acc[j]);
-        }
-        for (int o = T >> 1; o > 0; o >>= 1) {
-#pragma unroll
-          for (int j = 0; j < KT; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-        }
-        if (valid && lane_t == 0) {
-#pragma unroll
-          for (int j = 0; j < KT; ++j)
-            if (j < kt) {
-              double* yp = y + b.row0 + r + (size_t)(v0 + j) * ldy;
-              *yp = combine(beta == 0.0 ? 0.0 : *yp, acc[j], alpha, beta);
-            }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
   }
 }
@@ -937,164 +588,139 @@ spmm_runs_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// spmm_runs_kernel with the X tile DOUBLE-BUFFERED across the vector tiles of a block (round-2 candidate, opt-in with
-// JP_SPMM_RUNS_DB=1; written from the phase analysis in DESIGN.md 3.2b, not yet measured).  In spmm_runs_kernel every
-// (block, vector tile) phase pays the whole chain  run list from global -> TMA issue -> arrival -> barrier  before its
-// ~0.5 us of arithmetic.  Here
-//   * the run list and the tile bases are read ONCE per block and stay in registers (one run per lane of warp 0);
-//   * while the CTA computes vector tile t out of tile buffer t & 1, warp 0 has already issued the bulk copies of tile
-//     t + 1 into the other buffer (its own mbarrier), so from the second tile on a phase costs its arithmetic only;
-//   * the extra tile buffer takes the CTA from 73 KB to 110 KB: two CTAs per SM instead of three.
-// Blocks with more than 32 runs keep re-reading their run list (rare: a banded block has 3..18 runs).
+// SpMM on a matrix whose nonzeros lie on a few DIAGONALS (stencils: 5 / 7 / 27 distinct values of col - row).
+// What bounds the CSR SpMM kernels above is not HBM but the shared-memory pipe and instruction issue: every FMA needs
+// its x operand from shared memory (8 bytes; 128 bytes per clock per SM = 16 FMA per clock per SM) plus, in CSR, a
+// position load, a dependent address computation and the value load (profiles/r2_ncu_spmm_runs_summary.txt: issue slots
+// 25 % busy, LSU wavefronts 52 %, 12 warps per SM waiting on dependent shared-memory loads).  For a diagonal-structured
+// matrix none of the indirection is needed.  At the first k > 1 apply the values are copied once into diagonal-major
+// order, vals_dia[d][row] (zero where a row has no entry on diagonal d: domain boundaries; no column indices at all, so
+// the matrix stream shrinks from 12 to ~8 bytes per nonzero), and
+//   * one thread = one row; lanes = consecutive rows.  The thread's D coefficients are read ONCE per row block with
+//     coalesced streaming loads and stay in registers for every vector tile;
+//   * the X tile of the block is staged by TMA bulk copies: the columns a block of R rows touches are R + (a few) wide
+//     windows, one per group of adjacent diagonals, merged where they overlap; the window list is the same for every
+//     block (relative to its first row), so it travels as a kernel parameter -- no run table in memory;
+//   * the inner loop is  acc[j] = fma(a[d], xs[j][pos_d + lane], acc[j])  with every address known up front: D * KT
+//     independent conflict-free LDS.64, no dependent loads; diagonals are visited in ascending column order, which is
+//     the order of the CSR row, so the result is bit-identical to the run-staged kernel's.
+// Rows closer to the first / last row than the largest offset (their windows would leave X) are served by the gather
+// kernel on the corresponding CSR row blocks.
 // ---------------------------------------------------------------------------------------------------------------
-__host__ __device__ inline size_t runs_db_smem_bytes(int cap, int wpad, int KT) {
-  return (size_t)(cap + 8) * 8 + 2 * (size_t)KT * wpad * 8 + (size_t)(kRunsMaxRows + 8) * 4 + (size_t)(cap + 16) * 2;
-}
+constexpr int kDiaThreads = 128;   // rows per block (one per thread)
+constexpr int kDiaMaxDiags = 32;
+constexpr int kDiaMaxSegs = 16;
 
-template <int KT, int THREADS>
-__global__ void __launch_bounds__(THREADS)
-spmm_runs_db_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ rowptr, const double* __restrict__ vals,
-                    const uint16_t* __restrict__ lidx, const int2* __restrict__ runs, const double* __restrict__ x, int64_t ldx,
-                    double* __restrict__ y, int64_t ldy, int32_t k, int32_t cap, int32_t wpad, double alpha, double beta) {
+struct DiaParams {
+  int32_t D;                     // diagonals, ascending offset
+  int32_t nseg;                  // tile segments
+  int32_t W;                     // tile width in doubles (even)
+  int32_t seg_cols;              // sum of the segment lengths (doubles copied per vector)
+  int32_t pos[kDiaMaxDiags];     // tile position of x[base + off_d] for the block's first row `base`
+  int32_t seg_rel[kDiaMaxSegs];  // first column of segment s relative to `base` (even)
+  int32_t seg_len[kDiaMaxSegs];  // its length in columns (even)
+  int32_t seg_pos[kDiaMaxSegs];  // where it starts in the tile (even)
+};
+
+template <int KT, int DMAX>
+__global__ void __launch_bounds__(kDiaThreads, 4)  // <= 128 registers: four CTAs (16 warps) per SM beside the 4 x 38 KB tiles
+spmm_dia_kernel(const double* __restrict__ vals_dia, int64_t npad, const double* __restrict__ x, int64_t ldx, double* __restrict__ y,
+                int64_t ldy, int32_t k, int32_t row_lo, int32_t row_hi, double alpha, double beta, const DiaParams P) {
   JP_DYN_SMEM(smem_raw);
-  __shared__ __align__(8) uint64_t s_bar[2];  // one per tile buffer; the first phase of s_bar[0] also covers the matrix stage
-  double* s_val = reinterpret_cast<double*>(smem_raw);                         // [cap + 8]
-  double* xs_base = s_val + cap + 8;                                            // [2][KT][wpad]
-  int32_t* s_rp = reinterpret_cast<int32_t*>(xs_base + 2 * KT * wpad);          // [kRunsMaxRows + 8]
-  uint16_t* s_lidx = reinterpret_cast<uint16_t*>(s_rp + kRunsMaxRows + 8);      // [cap + 16]
-  const BlockRange b = decode_block(blocks, blockIdx.x);
-  const int4 aux = __ldg(reinterpret_cast<const int4*>(blocks + blockIdx.x) + 1);
-  const int run0 = aux.x, nruns = aux.y;
+  __shared__ __align__(8) uint64_t s_bar;
+  double* xs = reinterpret_cast<double*>(smem_raw);  // [KT][W]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ngrp = (b.p1 - b.a0 + 3) >> 2;
-  const int al0 = b.p0 & ~7;
-  const int nl8 = (b.p1 - al0 + 7) & ~7;
-  const int ra0 = b.row0 & ~3;
-  const int nrp = (b.row0 + b.nrows + 1 - ra0 + 3) & ~3;
-  const int ntiles = (k + KT - 1) / KT;
-  if (tid == 0) {
-    mbar_init(&s_bar[0], 1);
-    mbar_init(&s_bar[1], 1);
-  }
+  const int base = row_lo + (int)blockIdx.x * kDiaThreads;  // even: row_lo is even
+  const int r = base + tid;
+  const bool valid = r < row_hi;
+  if (tid == 0) mbar_init(&s_bar, 1);
   __syncthreads();
-  // warp 0, lane q: run q of the block and its position in the tile (kept for every vector tile)
-  int2 my_run = make_int2(0, 0);
-  int my_base = 0;
-  if (warp == 0 && nruns <= 32) {
-    if (lane < nruns) my_run = __ldg(runs + run0 + lane);
-    const int stride = lane < nruns ? run_stride(my_run.y) : 0;
-    int incl = stride;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    my_base = incl - stride;
-  }
-  // issue the bulk copies of vector tile t into tile buffer t & 1 (warp 0 only; the barrier has been armed by lane 0)
-  auto issue_tile = [&](int t) {
-    const int v0 = t * KT;
-    const int kt = k - v0 < KT ? k - v0 : KT;
-    double* xs = xs_base + (size_t)(t & 1) * KT * wpad;
-    uint64_t* bar = &s_bar[t & 1];
+  // issue the bulk copies of vector tile v0 (warp 0; one (segment, vector) pair per lane and pass)
+  auto issue_tile = [&](int v0, int kt) {
+    if (lane == 0) mbar_expect_tx(&s_bar, (unsigned)(P.seg_cols * 8 * kt));
+    __syncwarp();  // the barrier is armed before any lane's copy can complete on it
     const uint64_t pol_x = policy_evict_last();
-    if (nruns <= 32) {
-      if (my_run.y > 0) {
-        const double* src = x + (size_t)v0 * ldx + my_run.x;
-        double* dst = xs + my_base;
-        for (int j = 0; j < kt; ++j) {
-          bulk_g2s(dst, src, (unsigned)my_run.y * 8, bar, pol_x);
-          src += ldx;
-          dst += wpad;
-        }
-      }
-    } else {
-      int carry = 0;
-      for (int q0 = 0; q0 < nruns; q0 += 32) {  // warp-uniform
-        const int q = q0 + lane;
-        int2 run = make_int2(0, 0);
-        if (q < nruns) run = __ldg(runs + run0 + q);
-        const int stride = q < nruns ? run_stride(run.y) : 0;
-        int incl = stride;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int tt = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += tt;
-        }
-        const int base = carry + incl - stride;
-        carry += __shfl_sync(0xffffffffu, incl, 31);
-        if (run.y > 0) {
-          const double* src = x + (size_t)v0 * ldx + run.x;
-          double* dst = xs + base;
-          for (int j = 0; j < kt; ++j) {
-            bulk_g2s(dst, src, (unsigned)run.y * 8, bar, pol_x);
-            src += ldx;
-            dst += wpad;
-          }
-        }
-      }
+    for (int q = lane; q < P.nseg * kt; q += 32) {
+      const int sgm = q / kt, j = q - sgm * kt;
+      bulk_g2s(xs + (size_t)j * P.W + P.seg_pos[sgm], x + (size_t)(v0 + j) * ldx + base + P.seg_rel[sgm], (unsigned)P.seg_len[sgm] * 8, &s_bar,
+               pol_x);
     }
   };
-  const int kt0 = k < KT ? k : KT;
-  if (tid == 0) {  // matrix stage + first tile on s_bar[0]
-    const uint64_t pol = policy_evict_first();
-    mbar_expect_tx(&s_bar[0], (unsigned)(ngrp * 32 + nl8 * 2 + nrp * 4 + aux.w * 8 * kt0));
-    if (ngrp > 0) bulk_g2s(s_val, vals + b.a0, (unsigned)ngrp * 32, &s_bar[0], pol);
-    if (nl8 > 0) bulk_g2s(s_lidx, lidx + al0, (unsigned)nl8 * 2, &s_bar[0], pol);
-    bulk_g2s(s_rp, rowptr + ra0, (unsigned)nrp * 4, &s_bar[0], pol);
-  }
-  if (warp == 0) {
-    __syncwarp();  // s_bar[0] is armed before any lane's copy can complete on it
-    issue_tile(0);
-  }
-  int T = 1;
-  while (T < 4 && b.nrows * (T << 1) <= THREADS) T <<= 1;
-  const int lane_t = tid & (T - 1), group = tid / T, ngroups = THREADS / T;
-  const double* val0 = s_val - b.a0;
-  const uint16_t* lidx0 = s_lidx - al0;
-  for (int t = 0; t < ntiles; ++t) {
-    const int v0 = t * KT;
+  if (warp == 0) issue_tile(0, k < KT ? k : KT);
+  // this row's coefficients: coalesced (lanes = rows), streamed once, kept in registers for all vector tiles
+  double a[DMAX];
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d) a[d] = (d < P.D && valid) ? __ldcs(vals_dia + (size_t)d * npad + r) : 0.0;
+  unsigned phase = 0;
+  for (int v0 = 0; v0 < k; v0 += KT) {
     const int kt = k - v0 < KT ? k - v0 : KT;
-    if (warp == 0 && t + 1 < ntiles) {
-      // prefetch the next vector tile into the other buffer: every thread left it at the __syncthreads that ended
-      // phase t - 1
-      const int ktn = k - (v0 + KT) < KT ? k - (v0 + KT) : KT;
-      if (lane == 0) mbar_expect_tx(&s_bar[(t + 1) & 1], (unsigned)(aux.w * 8 * ktn));
-      __syncwarp();
-      issue_tile(t + 1);
-    }
-    mbar_wait(&s_bar[t & 1], (unsigned)((t >> 1) & 1));
-    const double* xs = xs_base + (size_t)(t & 1) * KT * wpad;
-    const int32_t* rp = s_rp + b.rpo;
-    for (int rbase = 0; rbase < b.nrows; rbase += ngroups) {  // warp-uniform trip count (shuffles below)
-      const int r = rbase + group;
-      const bool valid = r < b.nrows;
-      const int s = valid ? rp[r] : 0, e = valid ? rp[r + 1] : 0;
-      double acc[KT];
+    mbar_wait(&s_bar, phase);
+    phase ^= 1;
+    double acc[KT];
 #pragma unroll
-      for (int j = 0; j < KT; ++j) acc[j] = 0.0;
-      runs_row_accumulate<KT>(acc, lidx0, val0, xs, wpad, s + lane_t, e, T);
-      for (int o = T >> 1; o > 0; o >>= 1) {
+    for (int j = 0; j < KT; ++j) acc[j] = 0.0;
+    const double* xt = xs + tid;
 #pragma unroll
-        for (int j = 0; j < KT; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-      }
-      if (valid && lane_t == 0) {
+    for (int d = 0; d < DMAX; ++d) {
+      if (d < P.D) {
+        const double* xd = xt + P.pos[d];
 #pragma unroll
-        for (int j = 0; j < KT; ++j)
-          if (j < kt) {
-            double* yp = y + b.row0 + r + (size_t)(v0 + j) * ldy;
-            *yp = combine(beta == 0.0 ? 0.0 : *yp, acc[j], alpha, beta);
-          }
+        for (int j = 0; j < KT; ++j) acc[j] = fma(a[d], xd[(size_t)j * P.W], acc[j]);
       }
     }
-    __syncthreads();  // tile buffer t & 1 is free for vector tile t + 2
+    __syncthreads();  // every thread has read the tile: the next one may land
+    if (warp == 0 && v0 + KT < k) issue_tile(v0 + KT, k - (v0 + KT) < KT ? k - (v0 + KT) : KT);
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < KT; ++j)
+        if (j < kt) {
+          double* yp = y + r + (size_t)(v0 + j) * ldy;
+          *yp = combine(beta == 0.0 ? 0.0 : *yp, acc[j], alpha, beta);
+        }
+    }
+  }
+}
+
+// diagonal-major copy of the values: vals_dia[d * npad + row] = value of the entry (row, row + off[d]); one thread per row
+static __global__ void __launch_bounds__(256) dia_fill_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                                                         const double* __restrict__ vals, int32_t n_rows, const DiaParams P,
+                                                         const int32_t* __restrict__ offsets, int64_t npad, double* __restrict__ vals_dia,
+                                                         unsigned long long* __restrict__ missing) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
+    for (int32_t i = rowptr[r]; i < rowptr[r + 1]; ++i) {
+      const int32_t off = colind[i] - (int32_t)r;
+      int lo = 0, hi = P.D - 1, d = -1;
+      while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        const int32_t o = offsets[mid];
+        if (o == off) { d = mid; break; }
+        if (o < off) lo = mid + 1;
+        else hi = mid - 1;
+      }
+      if (d < 0) atomicAdd(missing, 1ull);
+      else vals_dia[(size_t)d * npad + r] = vals[i];
+    }
+  }
+}
+
+// one bit per distinct value of col - row (+ n_rows - 1)
+static __global__ void __launch_bounds__(256) dia_mark_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind, int32_t n_rows,
+                                                         uint32_t* __restrict__ bitmap) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
+    for (int32_t i = rowptr[r]; i < rowptr[r + 1]; ++i) {
+      const uint32_t b = (uint32_t)(colind[i] - (int32_t)r + (n_rows - 1));
+      const uint32_t w = b >> 5, m = 1u << (b & 31);
+      if ((bitmap[w] & m) == 0) atomicOr(bitmap + w, m);  // the plain read filters all but the first setters of a bit
+    }
   }
 }
 
 // jp_csr_create, one pass over the uploaded column indices (rows strided over the threads): make them 0-based, find every
 // row's largest column (-1 for an empty row) and count the indices outside [0, n_cols) -- the O(nnz) part of the
 // validation runs here, not on one host core
-__global__ void csr_validate_kernel(const int32_t* __restrict__ rowptr, int32_t* __restrict__ colind, int32_t n_rows, int32_t n_cols, int32_t base,
+static __global__ void csr_validate_kernel(const int32_t* __restrict__ rowptr, int32_t* __restrict__ colind, int32_t n_rows, int32_t n_cols, int32_t base,
                                     int32_t* __restrict__ rowmax, unsigned long long* __restrict__ bad) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   unsigned long long nbad = 0;

@@ -313,6 +313,8 @@ inline void __threadfence_block() {}
 inline void __threadfence_system() {}
 template <class T>
 T __ldg(const T* p) { return *p; }
+template <class T>
+T __ldcs(const T* p) { return *p; }
 template <class T, class U>
 T atomicAdd(T* p, U v) { T old = *p; *p = (T)(old + (T)v); return old; }
 template <class T, class U>

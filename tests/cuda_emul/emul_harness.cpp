@@ -4,6 +4,7 @@
 #include "emul_runtime.h"
 
 #include "../../juliapetra.jl_b200/csrc/jp_csr_blocks.h"
+#include "../../juliapetra.jl_b200/csrc/jp_dia_plan.h"
 #include "../../juliapetra.jl_b200/csrc/jp_fill_pipeline.h"
 #include "../../juliapetra.jl_b200/csrc/jp_mv_kernels.cuh"
 #include "../../juliapetra.jl_b200/csrc/jp_plan_kernels.cuh"
@@ -86,7 +87,7 @@ void emul_fill_free(void* handle) { delete static_cast<jp::FillOutput*>(handle);
 // One rank's y = beta*y + alpha*A*x through the product's kernels.  rowptr/colind are 0-based; x holds the first
 // x_rows rows of the column space (ld = x_rows) and halo the remaining columns LID-major, vector-minor (halo == null:
 // x is the whole column-map multivector and the HALO=false kernels run).  variant: 0 gather kernels (spmv_kernel for
-// k == 1, spmm_kernel otherwise), 1 spmm_tile_kernel, 2 spmm_pipe_kernel.  stats[4] = blocks, DIRECT, TWOPHASE+WARPROW,
+// k == 1, spmm_kernel otherwise), 6 spmm_runs_kernel.  stats[4] = blocks, DIRECT, SUBWARP,
 // LONGROW.  Returns 0, or -1 when the tile tables are not usable for this matrix.
 int emul_local_apply(int32_t n_rows, int32_t n_cols, int32_t n_local_cols, const int32_t* rowptr, const int32_t* colind,
                      const double* vals, const double* x, int32_t x_rows, const double* halo, double* y, int32_t k, double alpha,
@@ -158,15 +159,12 @@ int emul_local_apply(int32_t n_rows, int32_t n_cols, int32_t n_local_cols, const
     else if (use_halo) launch(spmv_kernel<true, 0>, spmm_kernel<KT, true, 0>);
     else if (tma) launch(spmv_kernel<false, 1>, spmm_kernel<KT, false, 1>);
     else launch(spmv_kernel<false, 0>, spmm_kernel<KT, false, 0>);
-  } else if (variant >= 3 && variant <= 8) {
-    // spmm_runs_kernel on its own block list: variant 3: KT = 4, 64 rows, 128 threads (two lanes per row); variant 4:
-    // KT = 8, 128 rows, 256 threads; variant 5: KT = 4, 64 rows, 64 threads (one lane per row); variant 6: the default
-    // configuration, KT = 4, 128 rows, 128 threads (one lane per row); variants 7 / 8: spmm_runs_db_kernel (double-buffered
-    // tiles), KT = 4, 128 rows with 128 threads / 64 rows with 256 threads
+  } else if (variant == 6) {
+    // spmm_runs_kernel in the library's configuration: KT = 4, 128 rows per block, 128 threads (one lane per row)
     if (use_halo || (x_rows & 1)) return -3;
     std::vector<BlockDesc> ri, rb, ra;
-    build_blocks(rp, cls, cap, (variant == 4 || variant == 6 || variant == 7) ? kRunsMaxRows : 64, allow_direct != 0, ri, rb, ra);
-    const int kt = variant == 4 ? 8 : 4;
+    build_blocks(rp, cls, cap, kRunsMaxRows, allow_direct != 0, ri, rb, ra);
+    const int kt = 4;
     const int max_tile_cols = (int)((110 * 1024 - (int64_t)runs_smem_bytes(cap, 0, kt)) / (8 * kt)) & ~1;
     std::vector<int32_t> ci(colind, colind + nnz);
     RunTables t;
@@ -182,67 +180,12 @@ int emul_local_apply(int32_t n_rows, int32_t n_cols, int32_t n_local_cols, const
       std::memcpy(d_lidx.p, t.lidx.data(), t.lidx.size() * 2);
       const int wpad = (t.wmax + 1) & ~1;
       const size_t sm = runs_smem_bytes(cap, wpad, kt);
-      if (variant == 7 || variant == 8) {
-        const size_t smdb = runs_db_smem_bytes(cap, wpad, 4);
-        if (smdb > 220 * 1024) return -4;
-        if (variant == 7)
-          JP_KLAUNCH((spmm_runs_db_kernel<4, 128>), (unsigned)ra.size(), 128, smdb, nullptr, d_blocks.as<BlockDesc>(), d_rp.as<int32_t>(),
-                     d_va.as<double>(), d_lidx.as<uint16_t>(), d_ucols.as<int2>(), d_x.as<double>(), (int64_t)x_rows, d_y.as<double>(),
-                     (int64_t)n_rows, k, cap, wpad, alpha, beta);
-        else
-          JP_KLAUNCH((spmm_runs_db_kernel<4, 256>), (unsigned)ra.size(), 256, smdb, nullptr, d_blocks.as<BlockDesc>(), d_rp.as<int32_t>(),
-                     d_va.as<double>(), d_lidx.as<uint16_t>(), d_ucols.as<int2>(), d_x.as<double>(), (int64_t)x_rows, d_y.as<double>(),
-                     (int64_t)n_rows, k, cap, wpad, alpha, beta);
-      } else if (variant == 5)
-        JP_KLAUNCH((spmm_runs_kernel<4, 64>), (unsigned)ra.size(), 64, sm, nullptr, d_blocks.as<BlockDesc>(), d_rp.as<int32_t>(),
-                   d_va.as<double>(), d_lidx.as<uint16_t>(), d_ucols.as<int2>(), d_x.as<double>(), (int64_t)x_rows, d_y.as<double>(),
-                   (int64_t)n_rows, k, cap, wpad, alpha, beta);
-      else if (kt == 4)
-        JP_KLAUNCH((spmm_runs_kernel<4, 128>), (unsigned)ra.size(), 128, sm, nullptr, d_blocks.as<BlockDesc>(), d_rp.as<int32_t>(),
-                   d_va.as<double>(), d_lidx.as<uint16_t>(), d_ucols.as<int2>(), d_x.as<double>(), (int64_t)x_rows, d_y.as<double>(),
-                   (int64_t)n_rows, k, cap, wpad, alpha, beta);
-      else
-        JP_KLAUNCH((spmm_runs_kernel<8, 256>), (unsigned)ra.size(), 256, sm, nullptr, d_blocks.as<BlockDesc>(), d_rp.as<int32_t>(),
-                   d_va.as<double>(), d_lidx.as<uint16_t>(), d_ucols.as<int2>(), d_x.as<double>(), (int64_t)x_rows, d_y.as<double>(),
-                   (int64_t)n_rows, k, cap, wpad, alpha, beta);
+      JP_KLAUNCH((spmm_runs_kernel<4, 128>), (unsigned)ra.size(), 128, sm, nullptr, d_blocks.as<BlockDesc>(), d_rp.as<int32_t>(),
+                 d_va.as<double>(), d_lidx.as<uint16_t>(), d_ucols.as<int2>(), d_x.as<double>(), (int64_t)x_rows, d_y.as<double>(),
+                 (int64_t)n_rows, k, cap, wpad, alpha, beta);
     }
   } else {
-    std::vector<int32_t> ci(colind, colind + nnz);
-    TileTables t;
-    if (!build_tile_tables(ci, ba, cap, KT, t)) {
-      rc = -1;
-    } else {
-      d_blocks.alloc(ba.size() * sizeof(BlockDesc) + 16);
-      std::memcpy(d_blocks.p, ba.data(), ba.size() * sizeof(BlockDesc));
-      const BlockDesc* b = d_blocks.as<BlockDesc>();
-      d_ucols.alloc(t.ucols.size() * 4);
-      d_lidx.alloc(t.lidx.size() * 2);
-      std::memcpy(d_ucols.p, t.ucols.data(), t.ucols.size() * 4);
-      std::memcpy(d_lidx.p, t.lidx.data(), t.lidx.size() * 2);
-      const int upad = (t.umax + 3) & ~3;
-      if (variant == 1) {
-        const size_t sm = tile_smem_bytes(cap, upad, KT);
-        if (use_halo)
-          JP_KLAUNCH((spmm_tile_kernel<KT, true>), nb, kTileThreads, sm, nullptr, b, d_rp.as<int32_t>(), d_ci.as<int32_t>(), d_va.as<double>(),
-                     d_lidx.as<uint16_t>(), d_ucols.as<int32_t>(), d_x.as<double>(), (int64_t)x_rows, d_halo.as<double>(), k, nloc,
-                     d_y.as<double>(), (int64_t)n_rows, k, cap, upad, alpha, beta);
-        else
-          JP_KLAUNCH((spmm_tile_kernel<KT, false>), nb, kTileThreads, sm, nullptr, b, d_rp.as<int32_t>(), d_ci.as<int32_t>(), d_va.as<double>(),
-                     d_lidx.as<uint16_t>(), d_ucols.as<int32_t>(), d_x.as<double>(), (int64_t)x_rows, d_halo.as<double>(), k, nloc,
-                     d_y.as<double>(), (int64_t)n_rows, k, cap, upad, alpha, beta);
-      } else {
-        const size_t sm = 2 * pipe_stage_bytes(cap, upad, KT);
-        const unsigned grid = std::min<unsigned>(nb, (unsigned)ctx().sm_count);
-        if (use_halo)
-          JP_KLAUNCH((spmm_pipe_kernel<KT, true>), grid, kPipeThreads, sm, nullptr, b, (int32_t)nb, d_rp.as<int32_t>(), d_va.as<double>(),
-                     d_lidx.as<uint16_t>(), d_ucols.as<int32_t>(), d_x.as<double>(), (int64_t)x_rows, d_halo.as<double>(), k, nloc,
-                     d_y.as<double>(), (int64_t)n_rows, k, cap, upad, alpha, beta);
-        else
-          JP_KLAUNCH((spmm_pipe_kernel<KT, false>), grid, kPipeThreads, sm, nullptr, b, (int32_t)nb, d_rp.as<int32_t>(), d_va.as<double>(),
-                     d_lidx.as<uint16_t>(), d_ucols.as<int32_t>(), d_x.as<double>(), (int64_t)x_rows, d_halo.as<double>(), k, nloc,
-                     d_y.as<double>(), (int64_t)n_rows, k, cap, upad, alpha, beta);
-      }
-    }
+    return -5;  // unknown variant
   }
   std::memcpy(y, d_y.p, (size_t)n_rows * k * 8);
   return rc;
@@ -408,6 +351,67 @@ int emul_plan_op(int32_t op, double* mv, int64_t n_mv, double* other, int64_t n_
   else JP_KLAUNCH(add_rows_kernel, g, kThreads, 0, nullptr, d_mv.as<double>(), n_mv, d_other.as<double>(), n_other, n_ids, k);
   std::memcpy(mv, d_mv.p, (size_t)n_mv * k * 8);
   std::memcpy(other, d_other.p, other_elems * 8);
+  return 0;
+}
+
+// ---- spmm_dia_kernel (diagonal-structured matrices): the library's plan (jp_dia_plan.h) + a host copy of what
+//      dia_mark_kernel / dia_fill_kernel produce.  Rows [range[0], range[1]) of y are computed; rc -1: not eligible ----
+int emul_spmm_dia(int32_t n_rows, int32_t n_cols, const int32_t* rowptr, const int32_t* colind, const double* vals, const double* x, double* y,
+                  int32_t k, double alpha, double beta, int32_t* range) {
+  using namespace jp;
+  using namespace jp::csrk;
+  const int64_t nnz = rowptr[n_rows];
+  // offsets through the bitmap kernel
+  const size_t nwords = ((size_t)n_rows + n_cols + 31) / 32;
+  DeviceBuffer d_rp, d_ci, d_va, bitmap;
+  d_rp.alloc(((size_t)n_rows + 1) * 4);
+  d_ci.alloc((size_t)nnz * 4 + 16);
+  d_va.alloc((size_t)nnz * 8 + 16);
+  bitmap.alloc(nwords * 4);
+  std::memcpy(d_rp.p, rowptr, ((size_t)n_rows + 1) * 4);
+  std::memcpy(d_ci.p, colind, (size_t)nnz * 4);
+  std::memcpy(d_va.p, vals, (size_t)nnz * 8);
+  std::memset(bitmap.p, 0, nwords * 4);
+  JP_KLAUNCH(dia_mark_kernel, 3u, 256, 0, nullptr, d_rp.as<int32_t>(), d_ci.as<int32_t>(), n_rows, bitmap.as<uint32_t>());
+  std::vector<int32_t> offsets;
+  for (size_t w = 0; w < nwords; ++w)
+    for (int b = 0; b < 32; ++b)
+      if (bitmap.as<uint32_t>()[w] >> b & 1u) offsets.push_back((int32_t)((int64_t)w * 32 + b - (n_rows - 1)));
+  DiaParams P;
+  if (offsets.size() > (size_t)kDiaMaxDiags || !dia_plan(offsets, P)) return -1;
+  int32_t row_lo, row_hi;
+  dia_row_range(P, n_rows, n_cols, row_lo, row_hi);
+  range[0] = row_lo;
+  range[1] = row_hi;
+  if (row_hi <= row_lo) return -1;
+  const int64_t npad = (((int64_t)n_rows + kDiaThreads - 1) / kDiaThreads + 1) * kDiaThreads;
+  DeviceBuffer d_dia, d_off, d_missing, d_x, d_y;
+  d_dia.alloc((size_t)P.D * npad * 8);
+  std::memset(d_dia.p, 0, d_dia.bytes);
+  d_off.alloc(offsets.size() * 4);
+  std::memcpy(d_off.p, offsets.data(), offsets.size() * 4);
+  d_missing.alloc(8);
+  std::memset(d_missing.p, 0, 8);
+  JP_KLAUNCH(dia_fill_kernel, 2u, 256, 0, nullptr, d_rp.as<int32_t>(), d_ci.as<int32_t>(), d_va.as<double>(), n_rows, P, d_off.as<int32_t>(), npad,
+             d_dia.as<double>(), d_missing.as<unsigned long long>());
+  if (*d_missing.as<unsigned long long>() != 0) return -2;
+  d_x.alloc((size_t)n_cols * k * 8);  // exactly n_cols rows: a window that leaves X faults in the emulator's guarded buffers
+  std::memcpy(d_x.p, x, (size_t)n_cols * k * 8);
+  d_y.alloc((size_t)n_rows * k * 8 + 64);
+  std::memcpy(d_y.p, y, (size_t)n_rows * k * 8);
+  const unsigned grid = (unsigned)((row_hi - row_lo + kDiaThreads - 1) / kDiaThreads);
+  constexpr int KT = 4;
+  const size_t smem = dia_smem_bytes(P, KT);
+  if (P.D <= 8)
+    JP_KLAUNCH((spmm_dia_kernel<KT, 8>), grid, kDiaThreads, smem, nullptr, d_dia.as<double>(), npad, d_x.as<double>(), (int64_t)n_cols,
+               d_y.as<double>(), (int64_t)n_rows, k, row_lo, row_hi, alpha, beta, P);
+  else if (P.D <= 28)
+    JP_KLAUNCH((spmm_dia_kernel<KT, 28>), grid, kDiaThreads, smem, nullptr, d_dia.as<double>(), npad, d_x.as<double>(), (int64_t)n_cols,
+               d_y.as<double>(), (int64_t)n_rows, k, row_lo, row_hi, alpha, beta, P);
+  else
+    JP_KLAUNCH((spmm_dia_kernel<KT, 32>), grid, kDiaThreads, smem, nullptr, d_dia.as<double>(), npad, d_x.as<double>(), (int64_t)n_cols,
+               d_y.as<double>(), (int64_t)n_rows, k, row_lo, row_hi, alpha, beta, P);
+  std::memcpy(y, d_y.p, (size_t)n_rows * k * 8);
   return 0;
 }
 

@@ -39,7 +39,8 @@ def test_kernels_do_not_depend_on_the_thread_schedule():
 
     def everything():
         out = [emul.local_apply(rp, ci, va, x1, y1, 3.0, 0.5)[0]]                                  # spmv_kernel
-        out += [emul.local_apply(rp, ci, va, x9, y9, 3.0, 0.5, variant=v, cap=cap)[0] for v, cap in ((0, 2048), (2, 2048), (6, 3456), (7, 3456))]
+        out += [emul.local_apply(rp, ci, va, x9, y9, 3.0, 0.5, variant=v, cap=cap)[0] for v, cap in ((0, 2048), (6, 3456))]
+        out += [emul.spmm_dia(rp, ci, va, x9, y9, 3.0, 0.5)[0]]                                     # spmm_dia_kernel
         yd, dots = emul.spmv_dot(rp, ci, va, x1, x1, y1, 3.0, 0.5)
         out += [yd, dots]
         ya, sums = emul.axpby_norm2(y9, -0.37, x9, 1.0, blocks=3, repeats=2)

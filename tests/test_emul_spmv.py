@@ -1,4 +1,4 @@
-"""The localApply kernels (csrc/jp_csr_kernels.cuh: spmv_kernel, spmm_kernel, spmm_tile_kernel, spmm_pipe_kernel, every
+"""The localApply kernels (csrc/jp_csr_kernels.cuh: spmv_kernel, spmm_kernel, spmm_runs_kernel, spmm_dia_kernel, every
 block kind, TMA and cp.async staging, with and without the halo buffer) executed on the CPU model of tests/cuda_emul and
 compared with the CPU oracle's localApply (src/CSRMatrix.jl:1123-1162).  DIRECT blocks are bit-exact; the rest meets the
 1e-12 contract of the north star.  GPU runs of the same kernels: tests/test_gpu_parity.py."""
@@ -45,7 +45,7 @@ def test_spmv_irregular_rows_all_block_kinds(cap, allow_direct):
     n = len(rp) - 1
     x, y0 = _vectors(n, n, 1)
     got, st = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, cap=cap, allow_direct=allow_direct)
-    assert st["twophase_warprow"] > 0 and (cap != 256 or st["longrow"] > 0)
+    assert st["subwarp"] > 0 and (cap != 256 or st["longrow"] > 0)
     ref = _oracle(rp, ci, va, x, y0, 3.0, 0.5)
     assert (np.abs(got - ref) <= _bound(rp, ci, va, x, y0, 3.0, 0.5)).all()
 
@@ -65,16 +65,16 @@ def test_spmv_with_halo_buffer():
     assert (np.abs(got - ref) <= _bound(rp, ci, va, x, y0, 3.0, 0.5)).all()
 
 
-# gather, tile, pipelined tile, runs (KT=4 T=2; KT=8 256 thr; KT=4 T=1; default), double-buffered runs (128 / 256 threads)
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8])
+# gather kernel, run-staged kernel
+@pytest.mark.parametrize("variant", [0, 6])
 @pytest.mark.parametrize("k", [2, 8, 11, 32])
 def test_spmm_kernels(variant, k):
     rp, ci, va = _problem("27pt", 6)
     n = len(rp) - 1
     x, y0 = _vectors(n, n, k)
-    for halo in ((False,) if variant >= 3 else (False, True)):  # the runs kernel serves launches without halo columns
+    for halo in ((False,) if variant == 6 else (False, True)):  # the runs kernel serves launches without halo columns
         got, st = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, variant=variant, T=2, n_local_cols=n - 40 if halo else None,
-                                   halo_split=halo)
+                                   halo_split=halo, cap=3456 if variant == 6 else 2048)
         assert got is not None
         ref = _oracle(rp, ci, va, x, y0, 3.0, 0.5)
         assert (np.abs(got - ref) <= _bound(rp, ci, va, x, y0, 3.0, 0.5)).all()
@@ -88,9 +88,8 @@ def test_spmm_irregular_rows():
         got, st = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, cap=cap, T=4)
         ref = _oracle(rp, ci, va, x, y0, 3.0, 0.5)
         assert (np.abs(got - ref) <= _bound(rp, ci, va, x, y0, 3.0, 0.5)).all()
-    for variant in (1, 3):
-        got, st = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, variant=variant)
-        assert got is None  # random columns: the tile / run tables are rejected and the gather kernel is used
+    got, st = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, variant=6, cap=3456)
+    assert got is None  # random columns: the run tables are rejected and the gather kernel is used
 
 
 @pytest.mark.parametrize("kind,N", [("5pt", 20), ("7pt", 8)])
@@ -98,15 +97,14 @@ def test_spmm_runs_kernel_other_stencils(kind, N):
     rp, ci, va = _problem(kind, N)
     n = len(rp) - 1
     x, y0 = _vectors(n, n, 5)
-    for variant, cap in ((3, 2048), (4, 256), (5, 2048), (6, 3456), (7, 3456), (8, 2048)):
-        got, st = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, variant=variant, cap=cap)
-        ref = _oracle(rp, ci, va, x, y0, 3.0, 0.5)
-        assert (np.abs(got - ref) <= _bound(rp, ci, va, x, y0, 3.0, 0.5)).all()
+    got, st = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, variant=6, cap=3456)
+    ref = _oracle(rp, ci, va, x, y0, 3.0, 0.5)
+    assert (np.abs(got - ref) <= _bound(rp, ci, va, x, y0, 3.0, 0.5)).all()
 
 
 def test_spmm_runs_kernels_with_more_than_32_runs_per_block():
     """40 far-apart double diagonals: every row block references 40 separate column runs, so the tile copy walks the
-    run list in two passes of 32 lanes (and the double-buffered kernel re-reads it per vector tile)"""
+    run list in two passes of 32 lanes"""
     n, ndiag = 16000, 40
     rows = np.arange(n)
     offs = (np.arange(ndiag) - ndiag // 2) * 391
@@ -119,9 +117,8 @@ def test_spmm_runs_kernels_with_more_than_32_runs_per_block():
     va = rng.standard_normal(len(ci))
     x, y0 = _vectors(n, n, 6)
     ref = _oracle(rp, ci, va, x, y0, 3.0, 0.5)
-    for variant in (6, 7):
-        got, st = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, variant=variant, cap=3456)
-        assert got is not None and (np.abs(got - ref) <= _bound(rp, ci, va, x, y0, 3.0, 0.5)).all()
+    got, st = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, variant=6, cap=3456)
+    assert got is not None and (np.abs(got - ref) <= _bound(rp, ci, va, x, y0, 3.0, 0.5)).all()
 
 
 def test_random_csr_structures_every_block_kind():
@@ -214,3 +211,32 @@ def test_reference_golden_2x2_through_the_kernels():
     y0 = np.diag([1.0, 2.0])
     got, _ = emul.local_apply(rp, ci, va, xcol, y0, 3.0, 0.5, n_local_cols=2, halo_split=True)
     assert np.array_equal(got, 0.5 * y0 + np.array([[6.0, 6.0], [0.0, 0.0]]))  # test/CSRMatrixMPITests.jl:52-63
+
+
+@pytest.mark.parametrize("kind,N,k", [("27pt", 12, 8), ("27pt", 10, 5), ("7pt", 14, 4), ("7pt", 12, 9), ("5pt", 46, 2), ("5pt", 40, 7)])
+def test_spmm_diagonal_kernel(kind, N, k):
+    """spmm_dia_kernel (diagonal-major copy built by dia_mark_kernel / dia_fill_kernel, window plan of jp_dia_plan.h): the rows
+    it serves against the oracle, bit-identical to the run-staged kernel (same ascending-column FMA chain); the rows near
+    the first / last row are left alone (the library hands them to the gather kernel).  Sizes that are no multiple of the
+    128-row block exercise the partial last block, k not a multiple of 4 the partial vector tile."""
+    rp, ci, va = _problem(kind, N)
+    n = len(rp) - 1
+    assert n % 2 == 0  # the TMA copies need an even leading dimension (the library takes the gather kernel otherwise)
+    x, y0 = _vectors(n, n, k)
+    for alpha, beta in ((1.0, 0.0), (3.0, 0.5)):
+        got, lo, hi = emul.spmm_dia(rp, ci, va, x, y0, alpha, beta)
+        assert got is not None and hi - lo > n // 3, (lo, hi, n)
+        ref = _oracle(rp, ci, va, x, y0, alpha, beta)
+        err = np.abs(got[lo:hi] - ref[lo:hi])
+        assert (err <= _bound(rp, ci, va, x, y0, alpha, beta)[lo:hi]).all()
+        assert np.array_equal(got[:lo], y0[:lo]) and np.array_equal(got[hi:], y0[hi:])  # untouched
+        runs, _ = emul.local_apply(rp, ci, va, x, y0, alpha, beta, variant=6, cap=3456)
+        if runs is not None:
+            assert np.array_equal(got[lo:hi], runs[lo:hi])
+
+
+def test_spmm_diagonal_kernel_rejects_irregular_matrices():
+    rp, ci, va = _problem("powerlaw", 3000, mean=6.0, max_len=20)
+    n = len(rp) - 1
+    x, y0 = _vectors(n, n, 4)
+    assert emul.spmm_dia(rp, ci, va, x, y0)[0] is None

@@ -1,7 +1,7 @@
 """BASELINE.json configs[2] and [3] at (or near) full size on one GPU against the CPU oracle, component-wise:
 |y_gpu - y_ref| <= 1e-12 * (|alpha| |A| |x| + |beta| |y0|).  These take a few minutes (host-side matrix generation and the
 scalar oracle dominate) but run by default with `-m gpu`.
-  configs[2]  3-D 27-point stencil 192^3, SpMM with k = 8 and k = 32 (run-staged kernel: X tiles by TMA)
+  configs[2]  3-D 27-point stencil 192^3, SpMM with k = 8 and k = 32 (diagonal kernel: X tiles by TMA)
   configs[3]  random power-law matrix, 10 M rows (160 M entries; the 50 M-row bench size needs 100+ GB of host memory for
               the oracle's copy, so parity is taken at 10 M rows, same generator, same row-length law, max row 10 k)
 configs[1] (7-point 256^3) is in test_gpu_parity.py; configs[4] (CG loop, 8 GPUs) in multi_gpu_cases.py and in bench.py's
@@ -52,7 +52,7 @@ def test_config2_27pt_192_spmm_full_size(stencil27_192, k):
     if k == 8:
         _check(A, m, x, y0, 3.0, 0.5)
     info = A.spmm_info()
-    assert info["runs_state"] == 1 and info["runs_blocks"] > 0, info  # the run-staged SpMM kernel served these applies
+    assert info["dia_state"] == 1 and info["dia_rows"] > 0.98 * n, info  # the diagonal SpMM kernel served these applies
 
 
 def test_config3_powerlaw_10M_rows():

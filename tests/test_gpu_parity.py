@@ -424,71 +424,49 @@ def test_transposed_apply_with_importer_serial():
     assert np.allclose(Y.data, ref, rtol=1e-13, atol=1e-13) and np.allclose(OY.get(1), ref, rtol=1e-13, atol=1e-13)
 
 
-@pytest.mark.parametrize("k", [8, 11])
-def test_spmm_shared_memory_tile_path(monkeypatch, k):
-    """opt-in SpMM kernel that stages the block's X tile in shared memory (unique-column lists, JP_SPMM_TILE=1)"""
-    monkeypatch.setenv("JP_SPMM_TILE", "1")
-    monkeypatch.setenv("JP_SPMM_RUNS", "0")  # the run-staged kernel (default for banded matrices) would take precedence
-    c, m, A = serial_matrix("27pt", 20)
-    n = m.numMyElements()
-    x = synthetic.vector_block(1, n, k, seed=1)
-    y0 = synthetic.vector_block(1, n, k, seed=2)
-    check_apply(A, x, y0, 3.0, 0.5, exact=False)
-    check_apply(A, x, y0, 1.0, 0.0, exact=False)
-    assert A.spmm_info()["tile_state"] == 1 and A.spmm_info()["runs_state"] == -1
-
-
-def test_spmm_default_path_selection():
-    """banded matrices take the run-staged kernel by default, random ones and odd leading dimensions the gather kernel"""
+def test_spmm_default_path_selection(monkeypatch):
+    """diagonal-structured matrices (stencils) take the diagonal kernel, random ones and odd leading dimensions the gather
+    kernel; with the diagonal copy switched off a banded matrix takes the run-staged kernel"""
     c, m, A = serial_matrix("27pt", 16)
     n = m.numMyElements()
     check_apply(A, synthetic.vector_block(1, n, 5, seed=1), synthetic.vector_block(1, n, 5, seed=2), 3.0, 0.5, exact=False)
-    assert A.spmm_info()["runs_state"] == 1
+    info = A.spmm_info()
+    assert info["dia_state"] == 1 and info["dia_diagonals"] == 27 and info["dia_rows"] > n // 2 and info["runs_state"] == -1, info
     c, m, A = serial_matrix("27pt", 15)  # n = 3375 is odd: X's columns are not all 16-byte aligned -> gather kernel
     n = m.numMyElements()
     check_apply(A, synthetic.vector_block(1, n, 5, seed=1), synthetic.vector_block(1, n, 5, seed=2), 3.0, 0.5, exact=False)
     c, m, A = serial_matrix("powerlaw", 20000)
     n = m.numMyElements()
     check_apply(A, synthetic.vector_block(1, n, 5, seed=1), synthetic.vector_block(1, n, 5, seed=2), 3.0, 0.5, exact=False)
-    assert A.spmm_info()["runs_state"] == -1
-
-
-@pytest.mark.parametrize("kt", ["4", "8"])
-@pytest.mark.parametrize("rows_threads", [("128", "128"), ("64", "128"), ("64", "64"), ("64", "256")])
-@pytest.mark.parametrize("kind,N,k", [("27pt", 20, 8), ("27pt", 20, 11), ("27pt", 12, 32)])
-def test_spmm_run_staged_path(monkeypatch, kind, N, k, kt, rows_threads):
-    """SpMM kernel that stages the block's X tile through aligned column runs with TMA bulk copies, in every
-    configuration of vector tile, rows per block and lanes per row"""
-    if kt == "8" and rows_threads[1] == "64":
-        pytest.skip("KT = 8 is built for 128 and 256 threads")
-    monkeypatch.setenv("JP_SPMM_RUNS", "1")
-    monkeypatch.setenv("JP_SPMM_RUNS_KT", kt)
-    monkeypatch.setenv("JP_SPMM_RUNS_ROWS", rows_threads[0])
-    monkeypatch.setenv("JP_SPMM_RUNS_THREADS", rows_threads[1])
-    c, m, A = serial_matrix(kind, N)
-    n = m.numMyElements()
-    x = synthetic.vector_block(1, n, k, seed=1)
-    y0 = synthetic.vector_block(1, n, k, seed=2)
-    check_apply(A, x, y0, 3.0, 0.5, exact=False)
-    check_apply(A, x, y0, 1.0, 0.0, exact=False)
     info = A.spmm_info()
-    assert info["runs_state"] == 1 and info["runs_blocks"] > 0, info  # the run-staged kernel really ran
+    assert info["runs_state"] == -1 and info["dia_state"] == -1, info
+    monkeypatch.setenv("JP_SPMM_DIA", "0")
+    c, m, A = serial_matrix("27pt", 16)
+    n = m.numMyElements()
+    check_apply(A, synthetic.vector_block(1, n, 5, seed=1), synthetic.vector_block(1, n, 5, seed=2), 3.0, 0.5, exact=False)
+    info = A.spmm_info()
+    assert info["dia_state"] == -1 and info["runs_state"] == 1, info
 
 
-@pytest.mark.parametrize("rows_threads", [("128", "128"), ("64", "256")])
-@pytest.mark.parametrize("kind,N,k", [("27pt", 20, 8), ("27pt", 20, 11), ("27pt", 12, 32)])
-def test_spmm_double_buffered_tiles(monkeypatch, kind, N, k, rows_threads):
-    """round-2 candidate (JP_SPMM_RUNS_DB=1): the X tile of the run-staged kernel double-buffered across vector tiles"""
-    monkeypatch.setenv("JP_SPMM_RUNS_DB", "1")
-    monkeypatch.setenv("JP_SPMM_RUNS_ROWS", rows_threads[0])
-    monkeypatch.setenv("JP_SPMM_RUNS_THREADS", rows_threads[1])
+@pytest.mark.parametrize("kind,N,k", [("27pt", 20, 8), ("27pt", 20, 11), ("27pt", 12, 32), ("7pt", 24, 6), ("5pt", 90, 3)])
+def test_spmm_diagonal_and_run_staged_kernels(monkeypatch, kind, N, k):
+    """the two SpMM kernels that stage X tiles with TMA bulk copies -- spmm_dia_kernel (diagonal-major values, the default
+    for stencils) and spmm_runs_kernel (CSR with aligned column runs, the fallback for banded matrices) -- against the
+    oracle, and against each other bit for bit (both add a row's entries in ascending column order with FMAs)"""
     c, m, A = serial_matrix(kind, N)
     n = m.numMyElements()
     x = synthetic.vector_block(1, n, k, seed=1)
     y0 = synthetic.vector_block(1, n, k, seed=2)
-    check_apply(A, x, y0, 3.0, 0.5, exact=False)
+    got_dia = check_apply(A, x, y0, 3.0, 0.5, exact=False)
     check_apply(A, x, y0, 1.0, 0.0, exact=False)
-    assert A.spmm_info()["runs_state"] == 1
+    assert A.spmm_info()["dia_state"] == 1, A.spmm_info()
+    monkeypatch.setenv("JP_SPMM_DIA", "0")
+    c, m, A2 = serial_matrix(kind, N)
+    got_runs = check_apply(A2, x, y0, 3.0, 0.5, exact=False)
+    check_apply(A2, x, y0, 1.0, 0.0, exact=False)
+    info = A2.spmm_info()
+    assert info["runs_state"] == 1 and info["runs_blocks"] > 0, info  # the run-staged kernel really ran
+    assert np.array_equal(got_dia, got_runs)
 
 
 def test_full_size_7pt_256_properties_and_oracle():

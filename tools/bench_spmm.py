@@ -18,19 +18,9 @@ import jpetra_b200 as jp  # noqa: E402
 from jpetra_b200 import _lib, synthetic  # noqa: E402
 
 VARIANTS = [
-    ("gather", {"JP_SPMM_RUNS": "0"}),
-    ("default", {}),
-    ("runs_kt4", {"JP_SPMM_RUNS": "1", "JP_SPMM_RUNS_KT": "4"}),
-    ("runs_kt8", {"JP_SPMM_RUNS": "1", "JP_SPMM_RUNS_KT": "8"}),
-    ("runs_kt4_cap1024", {"JP_SPMM_RUNS": "1", "JP_SPMM_RUNS_KT": "4", "JP_SPMM_RUNS_CAP": "1024"}),
-    ("runs_kt4_t256", {"JP_SPMM_RUNS": "1", "JP_SPMM_RUNS_KT": "4", "JP_SPMM_RUNS_THREADS": "256"}),
-    ("runs_kt8_t256", {"JP_SPMM_RUNS": "1", "JP_SPMM_RUNS_KT": "8", "JP_SPMM_RUNS_THREADS": "256"}),
-    # one lane per row (conflict-free shared reads for odd row lengths, no shuffles)
-    ("runs_kt4_rows128_t128", {"JP_SPMM_RUNS": "1", "JP_SPMM_RUNS_KT": "4", "JP_SPMM_RUNS_ROWS": "128", "JP_SPMM_RUNS_CAP": "3456"}),
-    ("runs_kt4_rows64_t64", {"JP_SPMM_RUNS": "1", "JP_SPMM_RUNS_KT": "4", "JP_SPMM_RUNS_THREADS": "64"}),
-    # round-2 candidates: X tile double-buffered across the vector tiles of a block (spmm_runs_db_kernel)
-    ("runs_db", {"JP_SPMM_RUNS_DB": "1"}),
-    ("runs_db_rows64_t256", {"JP_SPMM_RUNS_DB": "1", "JP_SPMM_RUNS_ROWS": "64", "JP_SPMM_RUNS_THREADS": "256", "JP_SPMM_RUNS_CAP": "2048"}),
+    ("gather", {"JP_SPMM_RUNS": "0", "JP_SPMM_DIA": "0"}),  # spmm_kernel: X gathered through L1 / L2
+    ("runs", {"JP_SPMM_DIA": "0"}),                       # spmm_runs_kernel: CSR + X tiles through aligned column runs
+    ("default", {}),                                      # spmm_dia_kernel for diagonal-structured matrices
 ]
 
 
@@ -76,7 +66,7 @@ def main():
     for label, env in ([("default_direct", {})] if args.direct else VARIANTS):
         if not args.direct and keep and label not in keep:
             continue
-        for key in ("JP_SPMM_RUNS", "JP_SPMM_RUNS_KT", "JP_SPMM_RUNS_CAP", "JP_SPMM_RUNS_THREADS", "JP_SPMM_RUNS_ROWS", "JP_SPMM_RUNS_DB", "JP_SPMM_TILE"):
+        for key in ("JP_SPMM_DIA", "JP_SPMM_RUNS"):
             os.environ.pop(key, None)
         os.environ.update(env)
         h = C.c_int64(A.h if args.direct else 0)
@@ -102,11 +92,11 @@ def main():
             y = Y.data
             if label == "gather":
                 ref[k] = y
-            info = np.zeros(4, dtype=np.int64)
+            info = np.zeros(8, dtype=np.int64)
             _lib.check(lib.jp_csr_spmm_info(h.value, _lib.ptr(info)))
             gbs = (nnz * 12 + (n + 1) * 4 + 16 * n * k) / t / 1e6
             out["cases"].append({"variant": label, "k": k, "ms": t, "algorithmic_gbs": gbs, "frac_of_peak": gbs / peak,
-                                 "gflops": 2.0 * nnz * k / t / 1e6, "runs_state": int(info[1]), "widest_tile": int(info[3]),
+                                 "gflops": 2.0 * nnz * k / t / 1e6, "runs_state": int(info[1]), "widest_tile": int(info[3]), "dia_state": int(info[4]), "dia_rows": int(info[6]),
                                  "max_abs_diff_vs_gather": float(np.abs(y - ref[k]).max()) if k in ref else None})
             del X, Y
         if not args.direct:
