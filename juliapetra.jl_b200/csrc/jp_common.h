@@ -319,7 +319,8 @@ void allgather_host_bytes(Comm& c, const void* in, size_t bytes, void* out);  //
 int64_t allreduce_min_host(Comm& c, int64_t v);
 void release_host_path_cache();
 void release_reduce_workspace();
-double* mv_dot_local(const MultiVector& x, const MultiVector& y);  // k local dot products -> device workspace (compute stream)
+// k local dot products -> device workspace, or straight into `out` (k doubles on the device) when given (compute stream)
+double* mv_dot_local(const MultiVector& x, const MultiVector& y, double* out = nullptr);
 void mv_finish_reduction(Comm& c, double* dev_out, int32_t k, double* host_out);  // allreduce + D2H + synchronise
 // y = beta*y + alpha*A*x over all row blocks (x = the whole column-map vector) and sum_r w[r]*y[r] -> returned device slot
 double* launch_spmv_dot(Csr& A, const double* x, double* y, double alpha, double beta, const double* w, cudaStream_t stream);

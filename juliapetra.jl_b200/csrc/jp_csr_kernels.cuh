@@ -17,7 +17,7 @@ constexpr int kMaxRowsPerBlock = 512;   // rows staged per block (row pointers i
 // two-phase paths -- products through shared memory, then thread- or warp-per-row sums -- replaced by KIND_SUBWARP:
 // profiles/r2_powerlaw10M_subwarp_ab.json.)
 enum BlockKind : int { KIND_DIRECT = 0, KIND_LONGROW = 3, KIND_SUBWARP = 4 };
-constexpr int kSubwarpLongFactor = 16;  // SUBWARP blocks: rows longer than this many passes of their lane group go warp-per-row
+constexpr int kSubwarpLongFactor = 8;   // SUBWARP blocks: rows longer than this many passes of their lane group go warp-per-row
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -195,19 +195,21 @@ __device__ __forceinline__ double spmv_block(const BlockRange& b, const StageVie
       double acca = 0.0, accb = 0.0;
       ia += lane_t;
       ib += lane_t;
+      // two entries of each of the two rows per step: four gathers of this lane are issued before the first FMA needs its
+      // operand (the kernel is bound by gather latency x dependent steps: profiles/r2_ncu_spmv_powerlaw10M_summary.txt)
       while (ia < ea || ib < eb) {
-        if (ia < ea) {
-          const int c = sv.s_col[ia];
-          const double xv = (HALO && c >= nloc) ? halo[c - nloc] : ldg_gather(x + c, pol_x);
-          acca = fma(sv.s_val[ia], xv, acca);
-          ia += T;
-        }
-        if (ib < eb) {
-          const int c = sv.s_col[ib];
-          const double xv = (HALO && c >= nloc) ? halo[c - nloc] : ldg_gather(x + c, pol_x);
-          accb = fma(sv.s_val[ib], xv, accb);
-          ib += T;
-        }
+        const int ca0 = ia < ea ? sv.s_col[ia] : -1, ca1 = ia + T < ea ? sv.s_col[ia + T] : -1;
+        const int cb0 = ib < eb ? sv.s_col[ib] : -1, cb1 = ib + T < eb ? sv.s_col[ib + T] : -1;
+        const double xa0 = ca0 < 0 ? 0.0 : ((HALO && ca0 >= nloc) ? halo[ca0 - nloc] : ldg_gather(x + ca0, pol_x));
+        const double xa1 = ca1 < 0 ? 0.0 : ((HALO && ca1 >= nloc) ? halo[ca1 - nloc] : ldg_gather(x + ca1, pol_x));
+        const double xb0 = cb0 < 0 ? 0.0 : ((HALO && cb0 >= nloc) ? halo[cb0 - nloc] : ldg_gather(x + cb0, pol_x));
+        const double xb1 = cb1 < 0 ? 0.0 : ((HALO && cb1 >= nloc) ? halo[cb1 - nloc] : ldg_gather(x + cb1, pol_x));
+        if (ca0 >= 0) acca = fma(sv.s_val[ia], xa0, acca);
+        if (ca1 >= 0) acca = fma(sv.s_val[ia + T], xa1, acca);
+        if (cb0 >= 0) accb = fma(sv.s_val[ib], xb0, accb);
+        if (cb1 >= 0) accb = fma(sv.s_val[ib + T], xb1, accb);
+        ia += 2 * T;
+        ib += 2 * T;
       }
       for (int o = T >> 1; o > 0; o >>= 1) {
         acca += __shfl_xor_sync(0xffffffffu, acca, o);
@@ -610,6 +612,8 @@ spmm_runs_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict
 constexpr int kDiaThreads = 128;   // rows per block (one per thread)
 constexpr int kDiaMaxDiags = 32;
 constexpr int kDiaMaxSegs = 16;
+constexpr int kDiaTileStride = 1536;  // doubles between the vectors of the X tile: a compile-time constant, so that the KT
+                                      // reads of one diagonal are one address + immediate offsets (W <= kDiaTileStride)
 
 struct DiaParams {
   int32_t D;                     // diagonals, ascending offset
@@ -622,35 +626,48 @@ struct DiaParams {
   int32_t seg_pos[kDiaMaxSegs];  // where it starts in the tile (even)
 };
 
+// issue the bulk copies of one vector tile (called by warp 0): lane = 4 * segment + vector, eight segments per pass
+template <int KT>
+__device__ __forceinline__ void dia_issue_tile(const DiaParams& P, double* xs, uint64_t* bar, const double* __restrict__ x, int64_t ldx,
+                                               int base, int v0, int kt) {
+  static_assert(KT == 4, "lane mapping below assumes four vectors per tile");
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) mbar_expect_tx(bar, (unsigned)(P.seg_cols * 8 * kt));
+  __syncwarp();  // the barrier is armed before any lane's copy can complete on it
+  const uint64_t pol_x = policy_evict_last();
+  const int j = lane & 3;
+  for (int sgm = lane >> 2; sgm < P.nseg; sgm += 8)
+    if (j < kt)
+      bulk_g2s(xs + j * kDiaTileStride + P.seg_pos[sgm], x + (size_t)(v0 + j) * ldx + base + P.seg_rel[sgm], (unsigned)P.seg_len[sgm] * 8, bar,
+               pol_x);
+}
+
 template <int KT, int DMAX>
 __global__ void __launch_bounds__(kDiaThreads, 4)  // <= 128 registers: four CTAs (16 warps) per SM beside the 4 x 38 KB tiles
 spmm_dia_kernel(const double* __restrict__ vals_dia, int64_t npad, const double* __restrict__ x, int64_t ldx, double* __restrict__ y,
                 int64_t ldy, int32_t k, int32_t row_lo, int32_t row_hi, double alpha, double beta, const DiaParams P) {
   JP_DYN_SMEM(smem_raw);
   __shared__ __align__(8) uint64_t s_bar;
-  double* xs = reinterpret_cast<double*>(smem_raw);  // [KT][W]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* xs = reinterpret_cast<double*>(smem_raw);  // [KT][kDiaTileStride], W columns of each row in use
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int base = row_lo + (int)blockIdx.x * kDiaThreads;  // even: row_lo is even
   const int r = base + tid;
   const bool valid = r < row_hi;
   if (tid == 0) mbar_init(&s_bar, 1);
   __syncthreads();
-  // issue the bulk copies of vector tile v0 (warp 0; one (segment, vector) pair per lane and pass)
-  auto issue_tile = [&](int v0, int kt) {
-    if (lane == 0) mbar_expect_tx(&s_bar, (unsigned)(P.seg_cols * 8 * kt));
-    __syncwarp();  // the barrier is armed before any lane's copy can complete on it
-    const uint64_t pol_x = policy_evict_last();
-    for (int q = lane; q < P.nseg * kt; q += 32) {
-      const int sgm = q / kt, j = q - sgm * kt;
-      bulk_g2s(xs + (size_t)j * P.W + P.seg_pos[sgm], x + (size_t)(v0 + j) * ldx + base + P.seg_rel[sgm], (unsigned)P.seg_len[sgm] * 8, &s_bar,
-               pol_x);
-    }
-  };
-  if (warp == 0) issue_tile(0, k < KT ? k : KT);
-  // this row's coefficients: coalesced (lanes = rows), streamed once, kept in registers for all vector tiles
+  if (warp == 0) dia_issue_tile<KT>(P, xs, &s_bar, x, ldx, base, 0, k < KT ? k : KT);
+  // this row's coefficients: coalesced (lanes = rows), streamed once, kept in registers for all vector tiles.  Diagonals
+  // d >= D (the template rounds D up) get a zero coefficient and tile position 0: a harmless fma(0, finite, acc).
   double a[DMAX];
+  {
+    const double* vp = vals_dia + r;
 #pragma unroll
-  for (int d = 0; d < DMAX; ++d) a[d] = (d < P.D && valid) ? __ldcs(vals_dia + (size_t)d * npad + r) : 0.0;
+    for (int d = 0; d < DMAX; ++d) {
+      a[d] = (d < P.D && valid) ? __ldcs(vp) : 0.0;
+      vp += npad;
+    }
+  }
+  const double* xt = xs + tid;  // this lane's column of the tile
   unsigned phase = 0;
   for (int v0 = 0; v0 < k; v0 += KT) {
     const int kt = k - v0 < KT ? k - v0 : KT;
@@ -659,17 +676,14 @@ spmm_dia_kernel(const double* __restrict__ vals_dia, int64_t npad, const double*
     double acc[KT];
 #pragma unroll
     for (int j = 0; j < KT; ++j) acc[j] = 0.0;
-    const double* xt = xs + tid;
 #pragma unroll
     for (int d = 0; d < DMAX; ++d) {
-      if (d < P.D) {
-        const double* xd = xt + P.pos[d];
+      const double* xd = xt + P.pos[d];
 #pragma unroll
-        for (int j = 0; j < KT; ++j) acc[j] = fma(a[d], xd[(size_t)j * P.W], acc[j]);
-      }
+      for (int j = 0; j < KT; ++j) acc[j] = fma(a[d], xd[j * kDiaTileStride], acc[j]);
     }
     __syncthreads();  // every thread has read the tile: the next one may land
-    if (warp == 0 && v0 + KT < k) issue_tile(v0 + KT, k - (v0 + KT) < KT ? k - (v0 + KT) : KT);
+    if (warp == 0 && v0 + KT < k) dia_issue_tile<KT>(P, xs, &s_bar, x, ldx, base, v0 + KT, k - (v0 + KT) < KT ? k - (v0 + KT) : KT);
     if (valid) {
 #pragma unroll
       for (int j = 0; j < KT; ++j)

@@ -36,6 +36,7 @@ inline bool dia_plan(const std::vector<int32_t>& offsets, DiaParams& P) {
     P.seg_pos[s] = pos;
     pos += P.seg_len[s];
   }
+  if (pos > kDiaTileStride) return false;  // the tile rows have a fixed stride (jp_csr_kernels.cuh)
   P.W = pos;
   P.seg_cols = pos;
   for (int d = 0; d < D; ++d) {
@@ -46,7 +47,7 @@ inline bool dia_plan(const std::vector<int32_t>& offsets, DiaParams& P) {
   return true;
 }
 
-inline size_t dia_smem_bytes(const DiaParams& P, int KT) { return (size_t)KT * P.W * 8; }
+inline size_t dia_smem_bytes(const DiaParams& P, int KT) { return ((size_t)(KT - 1) * kDiaTileStride + P.W) * 8; }
 
 // rows [row_lo, row_hi) whose windows -- for EVERY block of kDiaThreads rows starting at row_lo, the last, partial one
 // included -- stay inside [0, n_cols); row_lo is even.  Empty (row_lo >= row_hi) when the matrix is too small.

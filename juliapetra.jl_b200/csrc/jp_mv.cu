@@ -52,10 +52,11 @@ ReduceWorkspace reduce_workspace(int32_t k) {
   return w;
 }
 
-// local sums for every vector -> w.out (device), stream-ordered on compute
+// local sums for every vector -> w.out (device; or `out` when given), stream-ordered on compute
 template <int MODE>
-double* reduce_local(const MultiVector& x, const MultiVector* y, double p) {
+double* reduce_local(const MultiVector& x, const MultiVector* y, double p, double* out = nullptr) {
   ReduceWorkspace w = reduce_workspace(x.k);
+  if (out) w.out = out;
   int blocks = grid_for(x.n, 8);
   if (blocks > kMaxReduceBlocks) blocks = kMaxReduceBlocks;
   dim3 grid(blocks, x.k);
@@ -132,7 +133,7 @@ void finish_reduction(Comm& c, double* dev_out, int32_t k, double* host_out) {
 
 }  // namespace
 
-double* mv_dot_local(const MultiVector& x, const MultiVector& y) { return reduce_local<0>(x, &y, 0.0); }
+double* mv_dot_local(const MultiVector& x, const MultiVector& y, double* out) { return reduce_local<0>(x, &y, 0.0, out); }
 void mv_finish_reduction(Comm& c, double* dev_out, int32_t k, double* host_out) { finish_reduction(c, dev_out, k, host_out); }
 
 void release_reduce_workspace() {

@@ -115,8 +115,7 @@ int32_t jp_mv_dot_dev(jp_handle comm, jp_handle x, jp_handle y, jp_handle s, int
     Scalars* sc = scalars(s);
     check_slot(*sc, slot, "jp_mv_dot_dev");
     JP_REQUIRE(mx->k == 1 && my->k == 1 && mx->n == my->n, "jp_mv_dot_dev: two single vectors of the same length");
-    double* dev = mv_dot_local(*mx, *my);  // the host-scalar path's kernel and workspace
-    JP_CUDA(cudaMemcpyAsync(sc->d() + slot, dev, 8, cudaMemcpyDeviceToDevice, ctx().compute));
+    mv_dot_local(*mx, *my, sc->d() + slot);  // the host-scalar path's kernel, its result written straight into the slot
     comm_allreduce_device(*c, sc->d() + slot, 1, ctx().compute);
   });
 }

@@ -452,7 +452,9 @@ def test_spmm_default_path_selection(monkeypatch):
 def test_spmm_diagonal_and_run_staged_kernels(monkeypatch, kind, N, k):
     """the two SpMM kernels that stage X tiles with TMA bulk copies -- spmm_dia_kernel (diagonal-major values, the default
     for stencils) and spmm_runs_kernel (CSR with aligned column runs, the fallback for banded matrices) -- against the
-    oracle, and against each other bit for bit (both add a row's entries in ascending column order with FMAs)"""
+    oracle, and against each other (on the rows the diagonal kernel serves both add a row's entries in ascending column order
+    with FMAs -- bit-identical, tests/test_emul_spmv.py; the first and last rows go through the gather kernel's lanes-per-row
+    tree, so the comparison here is to rounding)"""
     c, m, A = serial_matrix(kind, N)
     n = m.numMyElements()
     x = synthetic.vector_block(1, n, k, seed=1)
@@ -466,7 +468,7 @@ def test_spmm_diagonal_and_run_staged_kernels(monkeypatch, kind, N, k):
     check_apply(A2, x, y0, 1.0, 0.0, exact=False)
     info = A2.spmm_info()
     assert info["runs_state"] == 1 and info["runs_blocks"] > 0, info  # the run-staged kernel really ran
-    assert np.array_equal(got_dia, got_runs)
+    assert np.abs(got_dia - got_runs).max() <= 1e-13 * np.abs(got_runs).max()
 
 
 def test_full_size_7pt_256_properties_and_oracle():
