@@ -17,7 +17,7 @@ constexpr int kMaxRowsPerBlock = 512;   // rows staged per block (row pointers i
 // two-phase paths -- products through shared memory, then thread- or warp-per-row sums -- replaced by KIND_SUBWARP:
 // profiles/r2_powerlaw10M_subwarp_ab.json.)
 enum BlockKind : int { KIND_DIRECT = 0, KIND_LONGROW = 3, KIND_SUBWARP = 4 };
-constexpr int kSubwarpLongFactor = 8;   // SUBWARP blocks: rows longer than this many passes of their lane group go warp-per-row
+constexpr int kSubwarpLongFactor = 16;  // SUBWARP blocks: rows longer than this many passes of their lane group go warp-per-row
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -195,21 +195,21 @@ __device__ __forceinline__ double spmv_block(const BlockRange& b, const StageVie
       double acca = 0.0, accb = 0.0;
       ia += lane_t;
       ib += lane_t;
-      // two entries of each of the two rows per step: four gathers of this lane are issued before the first FMA needs its
-      // operand (the kernel is bound by gather latency x dependent steps: profiles/r2_ncu_spmv_powerlaw10M_summary.txt)
+      // (issuing two entries per row and step -- four gathers in flight per lane -- measured no faster: the kernel is at
+      // the memory system's random-sector rate, profiles/r2_ncu_spmv_powerlaw10M_summary.txt)
       while (ia < ea || ib < eb) {
-        const int ca0 = ia < ea ? sv.s_col[ia] : -1, ca1 = ia + T < ea ? sv.s_col[ia + T] : -1;
-        const int cb0 = ib < eb ? sv.s_col[ib] : -1, cb1 = ib + T < eb ? sv.s_col[ib + T] : -1;
-        const double xa0 = ca0 < 0 ? 0.0 : ((HALO && ca0 >= nloc) ? halo[ca0 - nloc] : ldg_gather(x + ca0, pol_x));
-        const double xa1 = ca1 < 0 ? 0.0 : ((HALO && ca1 >= nloc) ? halo[ca1 - nloc] : ldg_gather(x + ca1, pol_x));
-        const double xb0 = cb0 < 0 ? 0.0 : ((HALO && cb0 >= nloc) ? halo[cb0 - nloc] : ldg_gather(x + cb0, pol_x));
-        const double xb1 = cb1 < 0 ? 0.0 : ((HALO && cb1 >= nloc) ? halo[cb1 - nloc] : ldg_gather(x + cb1, pol_x));
-        if (ca0 >= 0) acca = fma(sv.s_val[ia], xa0, acca);
-        if (ca1 >= 0) acca = fma(sv.s_val[ia + T], xa1, acca);
-        if (cb0 >= 0) accb = fma(sv.s_val[ib], xb0, accb);
-        if (cb1 >= 0) accb = fma(sv.s_val[ib + T], xb1, accb);
-        ia += 2 * T;
-        ib += 2 * T;
+        if (ia < ea) {
+          const int c = sv.s_col[ia];
+          const double xv = (HALO && c >= nloc) ? halo[c - nloc] : ldg_gather(x + c, pol_x);
+          acca = fma(sv.s_val[ia], xv, acca);
+          ia += T;
+        }
+        if (ib < eb) {
+          const int c = sv.s_col[ib];
+          const double xv = (HALO && c >= nloc) ? halo[c - nloc] : ldg_gather(x + c, pol_x);
+          accb = fma(sv.s_val[ib], xv, accb);
+          ib += T;
+        }
       }
       for (int o = T >> 1; o > 0; o >>= 1) {
         acca += __shfl_xor_sync(0xffffffffu, acca, o);
@@ -650,7 +650,7 @@ spmm_dia_kernel(const double* __restrict__ vals_dia, int64_t npad, const double*
   __shared__ __align__(8) uint64_t s_bar;
   double* xs = reinterpret_cast<double*>(smem_raw);  // [KT][kDiaTileStride], W columns of each row in use
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int base = row_lo + (int)blockIdx.x * kDiaThreads;  // even: row_lo is even
+  const int base = row_lo + (int)blockIdx.x * kDiaThreads;  // its parity is row_lo's: the plan's windows are aligned for it
   const int r = base + tid;
   const bool valid = r < row_hi;
   if (tid == 0) mbar_init(&s_bar, 1);

@@ -69,15 +69,20 @@ void csr_prepare_dia(Csr& A) {
   const int D = (int)offsets.size();
   if (D == 0 || (double)A.n_rows * D > 1.25 * (double)A.nnz) return;
   auto dia = std::unique_ptr<DiaData, DiaDeleter>(new DiaData());
-  if (!dia_plan(offsets, dia->P)) return;
-  if (dia_smem_bytes(dia->P, 4) > 100 * 1024) return;  // at least two CTAs per SM
-  dia_row_range(dia->P, A.n_rows, A.n_cols, dia->row_lo, dia->row_hi);
-  // align the range to the all-blocks list: the edge rows are whole CSR row blocks
+  // The diagonal kernel serves whole CSR row blocks [b_lo, b_hi) of the all-blocks list; the edge blocks go to the gather
+  // kernel.  The first served row fixes the parity of every kernel block's first row, hence the alignment of the windows.
   const std::vector<BlockDesc>& ba = A.h_blocks_all;
   int32_t b_lo = 0, b_hi = (int32_t)ba.size();
-  while (b_lo < (int32_t)ba.size() && (ba[b_lo].row0 < dia->row_lo || (ba[b_lo].row0 & 1))) ++b_lo;
+  const int32_t need_lo = std::max(0, -offsets.front() + 1);  // + 1: a window may start one column early for alignment
+  while (b_lo < (int32_t)ba.size() && ba[b_lo].row0 < need_lo) ++b_lo;
+  if (b_lo >= (int32_t)ba.size()) return;
+  const int parity = ba[b_lo].row0 & 1;
+  if (!dia_plan(offsets, dia->P, parity)) return;
+  if (dia_smem_bytes(dia->P, 4) > 100 * 1024) return;  // at least two CTAs per SM
+  dia_row_range(dia->P, A.n_rows, A.n_cols, dia->row_lo, dia->row_hi, parity);
+  if (ba[b_lo].row0 < dia->row_lo) return;  // (cannot happen: need_lo covers the alignment slack)
   while (b_hi > b_lo && ba[b_hi - 1].row0 + (ba[b_hi - 1].nrows_kind & 0xffff) > dia->row_hi) --b_hi;
-  if (b_hi - b_lo < 8) return;
+  if (b_hi - b_lo < 4) return;
   dia->b_lo = b_lo;
   dia->b_hi = b_hi;
   dia->row_lo = ba[b_lo].row0;

@@ -357,7 +357,7 @@ int emul_plan_op(int32_t op, double* mv, int64_t n_mv, double* other, int64_t n_
 // ---- spmm_dia_kernel (diagonal-structured matrices): the library's plan (jp_dia_plan.h) + a host copy of what
 //      dia_mark_kernel / dia_fill_kernel produce.  Rows [range[0], range[1]) of y are computed; rc -1: not eligible ----
 int emul_spmm_dia(int32_t n_rows, int32_t n_cols, const int32_t* rowptr, const int32_t* colind, const double* vals, const double* x, double* y,
-                  int32_t k, double alpha, double beta, int32_t* range) {
+                  int32_t k, double alpha, double beta, int32_t parity, int32_t* range) {
   using namespace jp;
   using namespace jp::csrk;
   const int64_t nnz = rowptr[n_rows];
@@ -378,9 +378,9 @@ int emul_spmm_dia(int32_t n_rows, int32_t n_cols, const int32_t* rowptr, const i
     for (int b = 0; b < 32; ++b)
       if (bitmap.as<uint32_t>()[w] >> b & 1u) offsets.push_back((int32_t)((int64_t)w * 32 + b - (n_rows - 1)));
   DiaParams P;
-  if (offsets.size() > (size_t)kDiaMaxDiags || !dia_plan(offsets, P)) return -1;
+  if (offsets.size() > (size_t)kDiaMaxDiags || !dia_plan(offsets, P, parity)) return -1;
   int32_t row_lo, row_hi;
-  dia_row_range(P, n_rows, n_cols, row_lo, row_hi);
+  dia_row_range(P, n_rows, n_cols, row_lo, row_hi, parity);
   range[0] = row_lo;
   range[1] = row_hi;
   if (row_hi <= row_lo) return -1;

@@ -167,17 +167,18 @@ def plan_op(op, mv, other, lids_a=None, lids_b=None, n_ids=None, blocks=2):
     return m, o
 
 
-def spmm_dia(rowptr0, colind0, vals, x, y, alpha=1.0, beta=0.0):
+def spmm_dia(rowptr0, colind0, vals, x, y, alpha=1.0, beta=0.0, parity=0):
     """spmm_dia_kernel on the CPU model with the library's plan (jp_dia_plan.h) and the device builders (dia_mark_kernel,
     dia_fill_kernel).  Returns (y_new, row_lo, row_hi): rows [row_lo, row_hi) are computed by the diagonal kernel, the
-    others are left as they were (the library serves them with the gather kernel); (None, 0, 0) when not eligible."""
+    others are left as they were (the library serves them with the gather kernel); (None, 0, 0) when not eligible.
+    parity: the parity of the first row served (the library takes it from the CSR row block it starts at)."""
     rp = np.ascontiguousarray(rowptr0, dtype=np.int32)
     ci = np.ascontiguousarray(colind0, dtype=np.int32)
     va = np.ascontiguousarray(vals, dtype=np.float64)
     xx, yy = _f(x), _f(y).copy(order="F")
     rng = np.zeros(2, dtype=np.int32)
     rc = lib().emul_spmm_dia(C.c_int32(len(rp) - 1), C.c_int32(xx.shape[0]), _p(rp), _p(ci), _p(va), _p(xx), _p(yy), C.c_int32(xx.shape[1]),
-                             C.c_double(alpha), C.c_double(beta), _p(rng))
+                             C.c_double(alpha), C.c_double(beta), C.c_int32(parity), _p(rng))
     if rc != 0:
         return None, 0, 0
     return yy, int(rng[0]), int(rng[1])

@@ -223,9 +223,9 @@ def test_spmm_diagonal_kernel(kind, N, k):
     n = len(rp) - 1
     assert n % 2 == 0  # the TMA copies need an even leading dimension (the library takes the gather kernel otherwise)
     x, y0 = _vectors(n, n, k)
-    for alpha, beta in ((1.0, 0.0), (3.0, 0.5)):
-        got, lo, hi = emul.spmm_dia(rp, ci, va, x, y0, alpha, beta)
-        assert got is not None and hi - lo > n // 3, (lo, hi, n)
+    for alpha, beta, parity in ((1.0, 0.0, 0), (3.0, 0.5, 1)):
+        got, lo, hi = emul.spmm_dia(rp, ci, va, x, y0, alpha, beta, parity=parity)
+        assert got is not None and hi - lo > n // 3 and lo % 2 == parity, (lo, hi, n)
         ref = _oracle(rp, ci, va, x, y0, alpha, beta)
         err = np.abs(got[lo:hi] - ref[lo:hi])
         assert (err <= _bound(rp, ci, va, x, y0, alpha, beta)[lo:hi]).all()
