@@ -177,7 +177,6 @@ __device__ __forceinline__ double spmv_block(const BlockRange& b, const StageVie
     const int T = 1 << b.lg, lane_t = tid & (T - 1), grp = tid >> b.lg, ngrp = kSpmvThreads >> b.lg;
     const int longlen = kSubwarpLongFactor * T;
     const uint64_t pol_x = policy_evict_last();
-    bool any_long = false;
     for (int rbase = 0; rbase < b.nrows; rbase += 2 * ngrp) {  // warp-uniform trip count (shuffles below)
       const int ra = rbase + grp, rb = ra + ngrp;
       int ia = 0, ea = 0, ib = 0, eb = 0;
@@ -185,12 +184,12 @@ __device__ __forceinline__ double spmv_block(const BlockRange& b, const StageVie
       if (wa) {
         ia = rp[ra] - b.a0;
         ea = rp[ra + 1] - b.a0;
-        if (ea - ia > longlen) { ea = ia; wa = false; any_long = true; }
+        if (ea - ia > longlen) { ea = ia; wa = false; }
       }
       if (wb) {
         ib = rp[rb] - b.a0;
         eb = rp[rb + 1] - b.a0;
-        if (eb - ib > longlen) { eb = ib; wb = false; any_long = true; }
+        if (eb - ib > longlen) { eb = ib; wb = false; }
       }
       double acca = 0.0, accb = 0.0;
       ia += lane_t;
@@ -230,7 +229,10 @@ __device__ __forceinline__ double spmv_block(const BlockRange& b, const StageVie
         }
       }
     }
-    if (__syncthreads_or(any_long)) {
+    // second pass, no block barrier in between (rows are independent; a barrier here made every warp wait for the block's
+    // longest short row: 18 stall cycles per issued instruction, profiles/r2_ncu_spmv_powerlaw10M_summary.txt): every warp
+    // looks for long rows among its share of the block's rows as soon as it is done with the first pass
+    {
       const int lane = tid & 31, warp = tid >> 5;
       for (int r = warp; r < b.nrows; r += kSpmvThreads / 32) {
         const int s = rp[r] - b.a0, e = rp[r + 1] - b.a0;
