@@ -168,9 +168,6 @@ int32_t jp_init(int32_t device) {
                               "; the kernels are built for sm_100a only");
     c.device = device;
     c.sm_count = prop.multiProcessorCount;
-    if (const char* v = std::getenv("JP_L2_FETCH")) {  // experiment: L2 fetch granularity hint (32 | 64 | 128 bytes)
-      if (*v) JP_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(v)));
-    }
     JP_CUDA(cudaStreamCreateWithFlags(&c.compute, cudaStreamNonBlocking));
     int lo = 0, hi = 0;
     JP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
