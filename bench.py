@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--fused", action="store_true", help="cg workloads: apply! + dot through the fused jp_apply_dot call")
     ap.add_argument("--device-scalars", action="store_true", help="cg workloads: dot / norm results stay on the device (jp_*_dev): no host sync per iteration")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--trans", action="store_true", help="time apply!(Y, A, X, TRANS) instead (profiling case: the cached transposed matrix)")
     ap.add_argument("--ref-ranks", type=int, default=0, help="--impl reference: simulated MPI ranks (default: host cores, max 32)")
     return ap.parse_args()
 
@@ -330,7 +331,7 @@ def main():
         if cg and args.fused:
             pAp = A.apply_dot_(Y, X)  # jp_apply_dot: no host round trip between apply! and dot
         else:
-            _lib.check(lib.jp_apply(comm.handle, Y.h, A.h, X.h, plan, jp.NO_TRANS, 1.0, 0.0))
+            _lib.check(lib.jp_apply(comm.handle, Y.h, A.h, X.h, plan, jp.TRANS if args.trans else jp.NO_TRANS, 1.0, 0.0))
         if cg:
             if not args.fused:
                 pAp = X.dot(Y)
@@ -483,7 +484,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": bench_config(spec, nnz, k, world),
+            "config": bench_config(spec, nnz, k, world), "mode": "TRANS" if args.trans else "NO_TRANS",
             "setup_s": round(setup_s, 1), "aligning_steps": align, "per_step": per_step,
             "hbm_gbs": bytes_apply / (ms_per_step * 1e-3) / 1e9, "host_enqueue_ms_per_step": host_enqueue_ms, "host_enqueue_burst_ms_per_step": host_burst_ms,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload),

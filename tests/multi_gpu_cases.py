@@ -172,6 +172,20 @@ def main():
         n1 = R1.norm(2)[0]
         n2 = R2.axpby_norm2_(-0.37, Xj, 1.0)[0]
         assert np.array_equal(R1.data, R2.data) and (np.abs(n1 - n2) <= TOL * n1).all()
+    # ---- one plan, changing multivector widths: k = 2 (arena sized for 4 vectors), k = 6 (the peer-memory arena is regrown
+    #      collectively: mappings closed, barrier, old arena retired), k = 1 (fused kernel on the regrown arena), k = 6 again ----
+    rm = jp.BlockMap(global_rows("7pt", 20), comm)
+    Aj = synthetic.build_matrix(jp, rm, "7pt", 20)
+    oc, om, OA = oracle_problem("7pt", 20, P)
+    for k in (2, 6, 1, 6):
+        xs = [synthetic.vector_block(om.info(p)["minMyGID"], om.info(p)["numMyElements"], k, seed=3) for p in everyone]
+        OX, OY = O.OMV.from_arrays(om, xs), O.OMV(om, k)
+        OA.apply(OY, OX, O.NO_TRANS, 1.0, 0.0)
+        Yk = Aj.apply(jp.DenseMultiVector(rm, xs[rank]))
+        ref = OY.get(pid)
+        assert np.abs(Yk.data - ref).max() <= 1e-12 * 12.0, (pid, k)
+        if k == 1:
+            assert np.array_equal(Yk.data, ref)
     # ---- distributed TRANS (Tpetra semantics, see oracle/jp_oracle.cpp applyMatrix) ----
     for kind, size, k in (("7pt", 12, 2), ("powerlaw", 6000, 1), ("27pt", 8, 3)):
         rm = jp.BlockMap(global_rows(kind, size), comm)
@@ -261,11 +275,23 @@ def main():
             lo, hi = ouni.info(pid)["minMyGID"] - 1, ouni.info(pid)["maxMyGID"]
             bound = dense_abs_bound(triples, P * 40, xs, ys, mode == jp.TRANS, lo, hi)
             assert (np.abs(Ye.data - ref) <= TOL * bound + 1e-300).all(), ("exporter", pid, k, int(mode))
-    # commReduce on a replicated map (test/DenseMultiVectorTests.jl:96-99)
+    # commReduce on a replicated map (test/DenseMultiVectorTests.jl:96-99): 18 doubles go through the peer-memory allreduce
+    # kernel, 150 doubles through ncclAllReduce
     rep = jp.BlockMap(6, 6, comm)
     v = jp.DenseMultiVector(rep, (10.0 ** pid) * np.ones((6, 3)))
     v.commReduce()
     assert np.array_equal(v.data, sum(10.0 ** i for i in everyone) * np.ones((6, 3)))
+    v = jp.DenseMultiVector(rep, (2.0 ** pid) * np.ones((6, 25)))
+    v.commReduce()
+    assert np.array_equal(v.data, float(sum(2 ** i for i in everyone)) * np.ones((6, 25)))
+    # a multivector wider than the mapped result block's fast path is still reduced correctly (k = 70 dot products)
+    wide = jp.BlockMap(P * 50, comm)
+    xw = synthetic.vector_block(wide.minMyGID(), wide.numMyElements(), 70, seed=4)
+    Xw = jp.DenseMultiVector(wide, xw)
+    dw = Xw.dot(Xw)[0]
+    allx = [synthetic.vector_block(1 + 50 * (p - 1), 50, 70, seed=4) for p in everyone]
+    dref = sum((a * a).sum(axis=0) for a in allx)
+    assert np.abs(dw - dref).max() <= 1e-12 * dref.max()
     comm.barrier()
     dist.barrier()
     if rank == 0:
