@@ -94,10 +94,10 @@ int32_t jp_csr_destroy(jp_handle A);
 /* info[8] = n_rows, n_cols, n_local_cols, nnz, interior row blocks, boundary row blocks, max row length,
  *           threads per row chosen from the row-length statistics */
 int32_t jp_csr_info(jp_handle A, int64_t* info);
-/* which SpMM path the matrix takes for k > 1 (decided lazily at the first such apply): info[8] = shared-memory tile
- * tables (0 not decided, 1 active, -1 not used), run-staged tables (same coding), row blocks of the run-staged path,
- * widest X tile in columns, diagonal-major copy (same coding), its number of diagonals, rows served by the diagonal
- * kernel, width of its X tile in columns */
+/* which derived layouts the matrix has (each decided lazily at the first apply that could use it; 0 not decided, 1 active,
+ * -1 not used): info[10] = reserved (-1), run-staged SpMM tables, row blocks of the run-staged path, widest X tile in
+ * columns, diagonal-major copy for SpMM, its number of diagonals, rows served by the diagonal kernel, width of its X tile
+ * in columns, column-slab copy for SpMV on large irregular matrices, its number of slabs */
 int32_t jp_csr_spmm_info(jp_handle A, int64_t* info);
 /* read the device copy back (0-based) -- parity tests */
 int32_t jp_csr_download(jp_handle A, int32_t* rowptr, int32_t* colind, double* vals);

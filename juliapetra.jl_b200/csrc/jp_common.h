@@ -191,6 +191,11 @@ struct DiaDeleter {
   void operator()(DiaData* p) const;
 };
 
+struct CbData;  // jp_colblock.cu
+struct CbDeleter {
+  void operator()(CbData* p) const;
+};
+
 struct Csr : Object {
   Csr() : Object(Kind::Csr) {}
   int32_t n_rows = 0, n_cols = 0, n_local_cols = 0;
@@ -215,6 +220,9 @@ struct Csr : Object {
   // SpMM on diagonal-structured matrices (spmm_dia_kernel; built lazily at the first k > 1 apply, jp_dia.cu)
   int dia_state = 0;  // 0 = not decided, 1 = active, -1 = not a diagonal-structured matrix / disabled
   std::unique_ptr<DiaData, DiaDeleter> dia;
+  // SpMV (k = 1) of a large irregular matrix through column slabs (spmv_cb_kernel; built lazily, jp_colblock.cu)
+  int cb_state = 0;  // 0 = not decided, 1 = active, -1 = not that kind of matrix / disabled
+  std::unique_ptr<CbData, CbDeleter> cb;
   // A^T as a device CSR of its own, built at the first transposed apply (jp_transpose.cu)
   std::unique_ptr<Csr> transposed;
   // cache of the row-map multivector (A.exportMV, src/CSRMatrix.jl:11): the exporter branch of apply! (rangeMap != rowMap)
@@ -285,6 +293,9 @@ void launch_spmv_trans(Csr& A, const double* x, int64_t ldx, double* y, int64_t 
                        double beta, cudaStream_t stream);
 void csr_prepare_spmm(Csr& A);  // decides (once) the SpMM path of the matrix: diagonal copy, run tables, or the gather kernel
 void csr_prepare_dia(Csr& A);   // decides (once) whether the matrix gets a diagonal-major copy for spmm_dia_kernel
+void csr_prepare_colblock(Csr& A);  // decides (once) whether the matrix gets a column-slab copy for spmv_cb_kernel
+void launch_spmv_colblock(const Csr& A, const double* x, double* y, double alpha, double beta, cudaStream_t stream);
+int64_t csr_colblock_info(const Csr& A, int what);  // 0: slabs, 1: columns per slab
 void launch_spmm_dia(const Csr& A, const double* x, int64_t ldx, double* y, int64_t ldy, int32_t k, double alpha, double beta,
                      cudaStream_t stream);
 // the gather SpMM kernel on a contiguous piece of a block list (k > 1, no halo columns)

@@ -397,6 +397,13 @@ void launch_spmv_blocks(const Csr& A, const void* blocks_int4, int32_t n_blocks,
   const bool whole_all = blocks_int4 == A.blocks_all.p && n_blocks == A.n_blocks_all;
   // (the interior-only launch is the compute-stream half of the multi-GPU two-stream path)
   const bool whole_interior = blocks_int4 == A.blocks_interior.p && n_blocks == A.n_blocks_interior;
+  if (k == 1 && !use_halo && whole_all) {  // a large irregular matrix sweeps its nonzeros column slab by column slab
+    csr_prepare_colblock(const_cast<Csr&>(A));
+    if (A.cb_state == 1) {
+      launch_spmv_colblock(A, x, y, alpha, beta, stream);
+      return;
+    }
+  }
   const bool tma_ok = (ldx & 1) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;  // bulk copies need 16-byte aligned sources
   if (k > 1 && A.dia_state == 1 && !use_halo && tma_ok && whole_all) {
     launch_spmm_dia(A, x, ldx, y, ldy, k, alpha, beta, stream);  // diagonal-structured matrix
@@ -615,6 +622,8 @@ int32_t jp_csr_spmm_info(jp_handle A, int64_t* info) {
     info[5] = csr_dia_info(*a, 0);
     info[6] = csr_dia_info(*a, 1);
     info[7] = csr_dia_info(*a, 2);
+    info[8] = a->cb_state;
+    info[9] = csr_colblock_info(*a, 0);
   });
 }
 

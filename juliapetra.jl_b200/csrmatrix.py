@@ -393,10 +393,10 @@ class CSRMatrix:
                          "threads_per_row"), (int(v) for v in info)))
 
     def spmm_info(self):
-        info = np.zeros(8, dtype=np.int64)
+        info = np.zeros(10, dtype=np.int64)
         _lib.check(_lib.lib().jp_csr_spmm_info(self.h, _lib.ptr(info)))
-        return dict(zip(("tile_state", "runs_state", "runs_blocks", "runs_widest_tile", "dia_state", "dia_diagonals", "dia_rows", "dia_tile_width"),
-                        (int(v) for v in info)))
+        return dict(zip(("tile_state", "runs_state", "runs_blocks", "runs_widest_tile", "dia_state", "dia_diagonals", "dia_rows", "dia_tile_width",
+                         "colblock_state", "colblock_slabs"), (int(v) for v in info)))
 
     # ---- Operator (src/Operator.jl:35-88, src/RowMatrix.jl:261-357, 406-416) ----
     def apply_(self, Y: DenseMultiVector, X: DenseMultiVector, mode=NO_TRANS, alpha=1.0, beta=0.0):

@@ -5,6 +5,7 @@
 
 #include "../../juliapetra.jl_b200/csrc/jp_csr_blocks.h"
 #include "../../juliapetra.jl_b200/csrc/jp_dia_plan.h"
+#include "../../juliapetra.jl_b200/csrc/jp_cb_kernels.cuh"
 #include "../../juliapetra.jl_b200/csrc/jp_fill_pipeline.h"
 #include "../../juliapetra.jl_b200/csrc/jp_mv_kernels.cuh"
 #include "../../juliapetra.jl_b200/csrc/jp_plan_kernels.cuh"
@@ -412,6 +413,65 @@ int emul_spmm_dia(int32_t n_rows, int32_t n_cols, const int32_t* rowptr, const i
     JP_KLAUNCH((spmm_dia_kernel<KT, 32>), grid, kDiaThreads, smem, nullptr, d_dia.as<double>(), npad, d_x.as<double>(), (int64_t)n_cols,
                d_y.as<double>(), (int64_t)n_rows, k, row_lo, row_hi, alpha, beta, P);
   std::memcpy(y, d_y.p, (size_t)n_rows * k * 8);
+  return 0;
+}
+
+// ---- spmv_cb_kernel / spmv_cb_carry_kernel (column-slab SpMV of large irregular matrices, csrc/jp_cb_kernels.cuh) with the
+//      device builders (cb_keys / cb_expand_rows / cb_gather / cb_slab_ptr) and a host stable sort in place of the radix
+//      sort.  slab_cols: columns per slab.  y = beta*y + alpha*A*x, k = 1 ----
+int emul_spmv_cb(int32_t n_rows, int32_t n_cols, const int32_t* rowptr, const int32_t* colind, const double* vals, const double* x, double* y,
+                 double alpha, double beta, int32_t slab_cols) {
+  using namespace jp;
+  using namespace jp::cbk;
+  const int64_t nnz = rowptr[n_rows];
+  const int32_t n_slabs = (n_cols + slab_cols - 1) / slab_cols;
+  DeviceBuffer d_rp, d_ci, d_va, key, order, key_s, order_s, row_of, row, col, val, slab_ptr, carry, d_x, d_y;
+  d_rp.alloc(((size_t)n_rows + 1) * 4);
+  d_ci.alloc((size_t)nnz * 4 + 16);
+  d_va.alloc((size_t)nnz * 8 + 16);
+  std::memcpy(d_rp.p, rowptr, ((size_t)n_rows + 1) * 4);
+  std::memcpy(d_ci.p, colind, (size_t)nnz * 4);
+  std::memcpy(d_va.p, vals, (size_t)nnz * 8);
+  key.alloc((size_t)nnz * 4 + 16);
+  order.alloc((size_t)nnz * 4 + 16);
+  key_s.alloc((size_t)nnz * 4 + 16);
+  order_s.alloc((size_t)nnz * 4 + 16);
+  row_of.alloc((size_t)nnz * 4 + 16);
+  JP_KLAUNCH(cb_keys_kernel, 3u, kCbThreads, 0, nullptr, d_ci.as<int32_t>(), nnz, slab_cols, key.as<uint32_t>(), order.as<uint32_t>());
+  JP_KLAUNCH(cb_expand_rows_kernel, 2u, kCbThreads, 0, nullptr, d_rp.as<int32_t>(), n_rows, row_of.as<int32_t>());
+  {  // stable sort of the positions by slab (the library uses cub::DeviceRadixSort, which is stable)
+    std::vector<uint32_t> idx(order.as<uint32_t>(), order.as<uint32_t>() + nnz);
+    const uint32_t* k = key.as<uint32_t>();
+    std::stable_sort(idx.begin(), idx.end(), [k](uint32_t a, uint32_t b) { return k[a] < k[b]; });
+    for (int64_t i = 0; i < nnz; ++i) {
+      order_s.as<uint32_t>()[i] = idx[i];
+      key_s.as<uint32_t>()[i] = k[idx[i]];
+    }
+  }
+  row.alloc((size_t)nnz * 4);  // exact sizes: an over-read faults in the guarded buffers
+  col.alloc((size_t)nnz * 4);
+  val.alloc((size_t)nnz * 8);
+  JP_KLAUNCH(cb_gather_kernel, 3u, kCbThreads, 0, nullptr, order_s.as<uint32_t>(), row_of.as<int32_t>(), d_ci.as<int32_t>(), d_va.as<double>(), nnz,
+             row.as<int32_t>(), col.as<int32_t>(), val.as<double>());
+  slab_ptr.alloc(((size_t)n_slabs + 1) * 8);
+  JP_KLAUNCH(cb_slab_ptr_kernel, 2u, kCbThreads, 0, nullptr, key_s.as<uint32_t>(), nnz, n_slabs, slab_ptr.as<long long>());
+  d_x.alloc((size_t)n_cols * 8);
+  std::memcpy(d_x.p, x, (size_t)n_cols * 8);
+  d_y.alloc((size_t)n_rows * 8);
+  for (int32_t r = 0; r < n_rows; ++r) d_y.as<double>()[r] = beta == 0.0 ? 0.0 : y[r] * beta;  // launch_scale_fill
+  int64_t max_slab = 0;
+  for (int s = 0; s < n_slabs; ++s) max_slab = std::max<int64_t>(max_slab, slab_ptr.as<long long>()[s + 1] - slab_ptr.as<long long>()[s]);
+  carry.alloc((size_t)(2 * ((max_slab + 31) / 32) + 2) * sizeof(CbCarry));
+  for (int s = 0; s < n_slabs; ++s) {
+    const int64_t e0 = slab_ptr.as<long long>()[s], e1 = slab_ptr.as<long long>()[s + 1];
+    if (e1 <= e0) continue;
+    const int64_t passes = (e1 - e0 + 31) / 32;
+    const unsigned grid = (unsigned)((e1 - e0 + kCbPerBlock - 1) / kCbPerBlock);
+    JP_KLAUNCH(spmv_cb_kernel, grid, kCbThreads, 0, nullptr, row.as<int32_t>(), col.as<int32_t>(), val.as<double>(), e0, e1, d_x.as<double>(),
+               d_y.as<double>(), alpha, carry.as<CbCarry>());
+    JP_KLAUNCH(spmv_cb_carry_kernel, 2u, kCbThreads, 0, nullptr, carry.as<CbCarry>(), 2 * passes, d_y.as<double>(), alpha);
+  }
+  std::memcpy(y, d_y.p, (size_t)n_rows * 8);
   return 0;
 }
 

@@ -184,6 +184,19 @@ def spmm_dia(rowptr0, colind0, vals, x, y, alpha=1.0, beta=0.0, parity=0):
     return yy, int(rng[0]), int(rng[1])
 
 
+def spmv_cb(rowptr0, colind0, vals, x, y, alpha=1.0, beta=0.0, slab_cols=1024):
+    """column-slab SpMV (spmv_cb_kernel + spmv_cb_carry_kernel and the device builders) on the CPU model; k = 1"""
+    rp = np.ascontiguousarray(rowptr0, dtype=np.int32)
+    ci = np.ascontiguousarray(colind0, dtype=np.int32)
+    va = np.ascontiguousarray(vals, dtype=np.float64)
+    xx = np.ascontiguousarray(np.asarray(x, dtype=np.float64).ravel())
+    yy = np.ascontiguousarray(np.asarray(y, dtype=np.float64).ravel()).copy()
+    rc = lib().emul_spmv_cb(C.c_int32(len(rp) - 1), C.c_int32(len(xx)), _p(rp), _p(ci), _p(va), _p(xx), _p(yy), C.c_double(alpha), C.c_double(beta),
+                            C.c_int32(slab_cols))
+    assert rc == 0
+    return yy.reshape(-1, 1)
+
+
 def transpose_csr(rowptr0, colind0, vals, n_cols):
     """A^T as CSR the way csrc/jp_transpose.cu builds it: a STABLE sort of the nonzero positions by column index, so the
     entries of a row of A^T are in ascending row order of A (0-based arrays in, 0-based arrays out)"""

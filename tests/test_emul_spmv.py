@@ -240,3 +240,21 @@ def test_spmm_diagonal_kernel_rejects_irregular_matrices():
     n = len(rp) - 1
     x, y0 = _vectors(n, n, 4)
     assert emul.spmm_dia(rp, ci, va, x, y0)[0] is None
+
+
+@pytest.mark.parametrize("slab_cols", [64, 700, 5000])
+@pytest.mark.parametrize("kind,N,kw", [("powerlaw", 4000, dict(mean=16.0, max_len=1500)), ("powerlaw", 1500, dict(mean=3.0, max_len=40)), ("7pt", 9, {})])
+def test_spmv_column_slab_kernel(kind, N, kw, slab_cols):
+    """spmv_cb_kernel: nonzeros in slab-major order, segmented warp sums, carries for runs that cross a 32-nonzero pass
+    (rows with hundreds of entries in one slab span many passes, warps and CTAs), against the oracle; deterministic"""
+    rp, ci, va = _problem(kind, N, **kw)
+    n = len(rp) - 1
+    x, y0 = _vectors(n, n, 1)
+    for alpha, beta in ((1.0, 0.0), (3.0, 0.5), (-2.0, 1.0)):
+        got = emul.spmv_cb(rp, ci, va, x, y0, alpha, beta, slab_cols=slab_cols)
+        ref = _oracle(rp, ci, va, x, y0, alpha, beta)
+        assert (np.abs(got - ref) <= _bound(rp, ci, va, x, y0, alpha, beta)).all()
+    emul.set_schedule("random", 5)
+    again = emul.spmv_cb(rp, ci, va, x, y0, -2.0, 1.0, slab_cols=slab_cols)
+    emul.set_schedule("forward")
+    assert np.array_equal(got, again)

@@ -65,7 +65,8 @@ def test_config3_powerlaw_10M_rows():
     y0 = synthetic.vector_block(1, n, 1, seed=2)
     _check(A, m, x, y0, 1.0, 0.0)
     got = _check(A, m, x, y0, 3.0, 0.5)
-    # determinism: the row-length-adaptive kernels use no atomics
+    assert A.spmm_info()["colblock_state"] == 1 and A.spmm_info()["colblock_slabs"] >= 3  # x (80 MB) is swept in column slabs
+    # determinism: neither the row-block kernels nor the column-slab kernel use atomics
     X, Y = jp.DenseMultiVector(m, x), jp.DenseMultiVector(m, y0)
     A.apply_(Y, X, jp.NO_TRANS, 3.0, 0.5)
     assert np.array_equal(Y.data, got)

@@ -537,3 +537,27 @@ def test_against_committed_golden_digests(key, kind, size):
     assert dig(AX.data) == g["ax_sha256"]
     assert abs(X.dot(AX)[0, 0] - g["dot_x_ax"]) <= 1e-12 * float((np.abs(x).T @ np.abs(AX.data))[0, 0])
     assert abs(AX.norm(2)[0, 0] - g["norm2_ax"]) <= 1e-12 * g["norm2_ax"]
+
+
+@pytest.mark.parametrize("slab_mb", ["1", "0"])
+def test_spmv_column_slabs_on_a_large_irregular_matrix(monkeypatch, slab_mb):
+    """a power-law matrix whose x (3.2 MB) is larger than two column slabs of 1 MB takes spmv_cb_kernel (nonzeros in
+    slab-major order, segmented warp sums, carries; no atomics); JP_CB_SLAB_MB=0 keeps the row-block kernel.  NO_TRANS and
+    TRANS (the cached transposed matrix is swept the same way), k = 1; k > 1 stays with the gather SpMM kernel"""
+    monkeypatch.setenv("JP_CB_SLAB_MB", slab_mb)
+    c, m, A = serial_matrix("powerlaw", 400_000, max_len=3000)
+    n = m.numMyElements()
+    x = synthetic.vector_block(1, n, 1, seed=1)
+    y0 = synthetic.vector_block(1, n, 1, seed=2)
+    got = check_apply(A, x, y0, 3.0, 0.5, exact=False)
+    check_apply(A, x, y0, 1.0, 0.0, exact=False)
+    info = A.spmm_info()
+    assert (info["colblock_state"], info["colblock_slabs"]) == ((1, 4) if slab_mb == "1" else (-1, 0)), info
+    assert np.array_equal(check_apply(A, x, y0, 3.0, 0.5, exact=False), got)  # deterministic
+    X, Yt = jp.DenseMultiVector(m, x), jp.DenseMultiVector(m, y0)
+    A.apply_(Yt, X, jp.TRANS, 3.0, 0.5)
+    ref = O.local_apply_raw(np.array(y0, order="F", copy=True), A.rowOffsets, A.localIndices1D, A.values, x, O.TRANS, 3.0, 0.5)
+    bound = O.local_apply_raw(np.abs(y0).copy(order="F"), A.rowOffsets, A.localIndices1D, np.abs(A.values), np.abs(x), O.TRANS, 3.0, 0.5)
+    assert (np.abs(Yt.data - ref) <= TOL * bound + 1e-300).all()
+    x3 = synthetic.vector_block(1, n, 3, seed=1)
+    check_apply(A, x3, synthetic.vector_block(1, n, 3, seed=2), 3.0, 0.5, exact=False)

@@ -92,7 +92,7 @@ def main():
             y = Y.data
             if label == "gather":
                 ref[k] = y
-            info = np.zeros(8, dtype=np.int64)
+            info = np.zeros(10, dtype=np.int64)
             _lib.check(lib.jp_csr_spmm_info(h.value, _lib.ptr(info)))
             gbs = (nnz * 12 + (n + 1) * 4 + 16 * n * k) / t / 1e6
             out["cases"].append({"variant": label, "k": k, "ms": t, "algorithmic_gbs": gbs, "frac_of_peak": gbs / peak,
