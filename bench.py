@@ -197,7 +197,7 @@ def sha256_of(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-def parity_checks(jp, comm, A, X, Y, x_host, spec, k, world, rank, e2e_y):
+def parity_checks(jp, comm, A, X, Y, x_host, spec, k, world, rank, e2e_y, cg_scalars=None, R=None):
     """Run on every rank after the timed loop; returns (ok, report).  Everything here goes through the same C-ABI entry
     points as the timed loop: Y is what the LAST timed apply left on the device."""
     rep = {}
@@ -209,7 +209,7 @@ def parity_checks(jp, comm, A, X, Y, x_host, spec, k, world, rank, e2e_y):
         fx = None
     y = Y.data
     pid, P = comm.myPid(), comm.numProc()
-    if fx is not None and k == 1 and not spec.get("cg"):
+    if fx is not None and k == 1:
         mine = sha256_of(y) == fx["y_sha256"][rank]
         rep["y_bit_exact_ranks"] = int(comm.sumAll([1 if mine else 0])[0])
         ok &= rep["y_bit_exact_ranks"] == P
@@ -222,7 +222,14 @@ def parity_checks(jp, comm, A, X, Y, x_host, spec, k, world, rank, e2e_y):
         rep["norm2_rel_err"] = abs(nr - fx["norm2_y"]) / fx["norm2_y"]
         rep["tolerance"] = 1e-12
         ok &= rep["dot_rel_err"] <= 1e-12 and rep["norm2_rel_err"] <= 1e-12
-    if spec["kind"] in ("5pt", "7pt", "27pt") and not spec.get("cg"):
+        if R is not None and "norm2_r" in fx:  # the residual vector of the CG-style loop
+            rep["norm2_r_rel_err"] = abs(float(R.norm(2)[0, 0]) - fx["norm2_r"]) / fx["norm2_r"]
+            ok &= rep["norm2_r_rel_err"] <= 1e-12
+        if cg_scalars is not None and "norm2_r" in fx:  # what the device-resident-scalar loop left on the device: p'Ap, |r|^2
+            rep["dev_pAp_rel_err"] = abs(cg_scalars[0] - fx["dot_x_y"]) / abs(fx["dot_x_y"])
+            rep["dev_rr_rel_err"] = abs(cg_scalars[1] - fx["norm2_r"] ** 2) / fx["norm2_r"] ** 2
+            ok &= rep["dev_pAp_rel_err"] <= 1e-12 and rep["dev_rr_rel_err"] <= 1e-12
+    if spec["kind"] in ("5pt", "7pt", "27pt"):
         # A is symmetric: the transposed apply (scatter + reverse-mode halo exchange with ADD) must reproduce A*X within the
         # reduction-order tolerance, component-wise: |Yt - Y|_i <= 1e-12 * max(|Y_i|, diag*|x_i|) <= 1e-12 * (|A||x|)_i
         Yt = jp.DenseMultiVector(Y.getMap(), k)
@@ -469,7 +476,8 @@ def main():
     if not args.no_parity:
         if not cg:
             _lib.check(lib.jp_apply(comm.handle, Y.h, A.h, X.h, plan, jp.NO_TRANS, 1.0, 0.0))  # Y of the very path that was timed
-        parity_ok, parity = parity_checks(jp, comm, A, X, Y, x_host, spec, k, world, rank, y_e2e)
+        cg_scalars = S.download() if (cg and args.device_scalars) else None
+        parity_ok, parity = parity_checks(jp, comm, A, X, Y, x_host, spec, k, world, rank, y_e2e, cg_scalars, R if cg else None)
 
     # ---- CPU baseline: the oracle's localApply on one core, same matrix (rank 0 at N=1 only) ----
     cpu = None

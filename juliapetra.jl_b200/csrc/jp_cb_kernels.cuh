@@ -4,7 +4,7 @@
 // multivector (400 MB) fits neither the L2 nor the TLBs' reach, every one of the 762 M gathers of the row-block kernel is
 // its own memory transaction and costs ~100 bytes of DRAM traffic: 81.7 GB per apply against 10.6 GB algorithmic, and the
 // kernel runs at the DRAM's random-access throughput.  The classic fix is cache blocking: cut the columns into slabs whose
-// piece of x stays resident in the L2 (24 MB by default), and sweep the matrix slab by slab.
+// piece of x stays resident in the L2 (32 MB by default), and sweep the matrix slab by slab.
 //
 // Layout (built once, at the first k = 1 apply; 16 bytes per nonzero on top of the CSR): the nonzeros in SLAB-MAJOR order
 // -- a stable sort of the CSR positions by slab id, so that inside a slab they are ordered by row, then by the CSR order of

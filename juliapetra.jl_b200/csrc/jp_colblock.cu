@@ -42,7 +42,8 @@ int grid_for(int64_t n) {
 void csr_prepare_colblock(Csr& A) {
   if (A.cb_state != 0) return;
   A.cb_state = -1;
-  const int slab_mb = env_int("JP_CB_SLAB_MB", 24);  // 0: never (A/B measurements and the tests of the row-block kernel)
+  // slab size: 16 / 24 / 32 MB measured 1.285 / 1.259 / 1.224 ms on the 10 M-row power-law matrix (profiles/r2_powerlaw_colblock.json)
+  const int slab_mb = env_int("JP_CB_SLAB_MB", 32);  // 0: never (A/B measurements and the tests of the row-block kernel)
   if (slab_mb <= 0 || A.nnz == 0 || A.n_cols != A.n_local_cols) return;
   const int64_t slab_bytes = (int64_t)slab_mb << 20;
   if ((int64_t)A.n_cols * 8 <= 2 * slab_bytes) return;  // x (nearly) fits the L2 as it is
