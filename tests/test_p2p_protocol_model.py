@@ -92,3 +92,119 @@ def test_protocol_adversarial_schedule_one_rank_far_ahead():
     # rank 0 already writes the halo of apply e + 1 while rank 1 is still inside apply e (with ONE buffer it had to wait for
     # rank 1's boundary rows of apply e); it cannot get further ahead because its own boundary rows need rank 1's pack
     assert lead == 1
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CTA-level model of ONE rank's fused kernel (csrc/jp_csr.cu fused_halo_body): does forward progress depend on the order
+# in which the hardware dispatches CTAs?  A rank has `slots` resident CTA slots; CTAs are dispatched in an ARBITRARY order
+# (the scheduler below may start the boundary CTAs first); a CTA that waits for a flag keeps its slot.
+#   claims = True   the shipped kernel: pack work is cut into items claimed from a ticket counter by the pack CTAs and by
+#                   every boundary CTA before it starts to wait
+#   claims = False  round 1's kernel: pack CTA i does pack item i, boundary CTAs just wait
+# ---------------------------------------------------------------------------------------------------------------
+def run_cta_model(P, sends, epochs, n_pack, n_int, n_bnd, slots, order, rng, claims):
+    sources = {q: [p for p in range(P) if q in sends[p]] for q in range(P)}
+    ready = {(q, p): 0 for p in range(P) for q in sends[p]}
+    ack = {(p, q): 0 for p in range(P) for q in sends[p]}
+    halo = {(q, p): [None, None] for p in range(P) for q in sends[p]}
+
+    class Rank:
+        pass
+
+    ranks = []
+    for p in range(P):
+        r = Rank()
+        r.epoch, r.pending, r.resident = 1, None, []
+        ranks.append(r)
+
+    def start_kernel(p):
+        r = ranks[p]
+        ctas = [("pack", i) for i in range(n_pack)] + [("int", i) for i in range(n_int)] + [("bnd", i) for i in range(n_bnd)]
+        r.pending = order(ctas, rng)       # the dispatch order is the scheduler's choice, not the program's
+        r.claimed, r.items_done, r.bnd_done = 0, 0, 0
+
+    for p in range(P):
+        start_kernel(p)
+    guard = 0
+    while any(r.epoch <= epochs for r in ranks):
+        progressed = False
+        for p in rng.sample(range(P), P):
+            r = ranks[p]
+            if r.epoch > epochs:
+                continue
+            e = r.epoch
+            while r.pending and len(r.resident) < slots:   # dispatch into free slots
+                kind, i = r.pending.pop(0)
+                r.resident.append({"kind": kind, "i": i, "state": "claim" if kind in ("pack", "bnd") else "work", "item": None})
+                progressed = True
+            for cta in list(r.resident):
+                if cta["state"] == "claim":
+                    if claims:
+                        if r.claimed < n_pack:
+                            cta["item"], r.claimed = r.claimed, r.claimed + 1
+                            cta["state"] = "pack_wait"
+                        else:
+                            cta["state"] = "work" if cta["kind"] == "bnd" else "done"
+                    else:
+                        cta["item"] = cta["i"] if cta["kind"] == "pack" else None
+                        cta["state"] = "pack_wait" if cta["kind"] == "pack" else "work"
+                    progressed = True
+                elif cta["state"] == "pack_wait":
+                    if all(ack[(p, q)] >= e - 2 for q in sends[p]):      # back-pressure of the two-buffer protocol
+                        r.items_done += 1
+                        if r.items_done == n_pack:                       # whoever finishes the last item publishes
+                            for q in sends[p]:
+                                assert halo[(q, p)][e & 1] is None or halo[(q, p)][e & 1][1] == e - 2
+                                halo[(q, p)][e & 1] = (p, e)
+                                ready[(q, p)] = e
+                        cta["state"] = "claim" if claims else "done"
+                        progressed = True
+                elif cta["state"] == "work":
+                    if cta["kind"] == "bnd":
+                        if not all(ready[(p, s)] >= e for s in sources[p]):
+                            continue                                     # spins, keeps its slot
+                        for s in sources[p]:
+                            assert halo[(p, s)][e & 1] == (s, e)
+                        r.bnd_done += 1
+                        if r.bnd_done == n_bnd:
+                            for s in sources[p]:
+                                ack[(s, p)] = e
+                    cta["state"] = "done"
+                    progressed = True
+                if cta["state"] == "done":
+                    r.resident.remove(cta)
+                    progressed = True
+            if not r.pending and not r.resident:                         # kernel finished: next apply
+                if n_bnd == 0:
+                    for s in sources[p]:
+                        ack[(s, p)] = e
+                r.epoch += 1
+                if r.epoch <= epochs:
+                    start_kernel(p)
+                progressed = True
+        if not progressed:
+            return False                                                 # every resident CTA spins, nothing can be dispatched
+        guard += 1
+        assert guard < 1_000_000
+    return True
+
+
+def _boundary_first(ctas, rng):
+    return sorted(ctas, key=lambda c: {"bnd": 0, "int": 1, "pack": 2}[c[0]])
+
+
+def _shuffled(ctas, rng):
+    ctas = list(ctas)
+    rng.shuffle(ctas)
+    return ctas
+
+
+def test_fused_kernel_progress_does_not_depend_on_cta_dispatch_order():
+    sends = {0: [1], 1: [0, 2], 2: [1]}
+    for seed in range(10):
+        rng = random.Random(seed)
+        for order in (_boundary_first, _shuffled):
+            assert run_cta_model(3, sends, epochs=6, n_pack=3, n_int=5, n_bnd=4, slots=2, order=order, rng=rng, claims=True)
+    # the same adversarial dispatch order dead-locks round 1's kernel: every slot is held by a boundary CTA that waits for
+    # a neighbour whose pack CTAs cannot be dispatched for the same reason
+    assert not run_cta_model(3, sends, epochs=6, n_pack=3, n_int=5, n_bnd=4, slots=2, order=_boundary_first, rng=random.Random(0), claims=False)
