@@ -161,14 +161,15 @@ def test_random_csr_structures_every_block_kind():
 
 def test_random_banded_structures_run_staged_kernels():
     """property test: random banded matrices (random band width, fill density, row count; empty rows; several bands) through
-    the run-staged SpMM kernels (default configuration and the double-buffered variant); structures the run-table
-    builder turns away (not banded enough) must be turned away, never mis-computed"""
+    the run-staged SpMM kernel; structures the run-table builder turns away (not banded enough) must be turned away, never
+    mis-computed"""
     import os
     from hypothesis import given, settings, strategies as st
 
     @settings(max_examples=int(os.environ.get("JP_HYPOTHESIS_EXAMPLES", "30")), deadline=None, derandomize=True)
-    @given(st.integers(0, 2 ** 31), st.integers(1, 300), st.integers(1, 12), st.sampled_from([2, 5, 9]), st.sampled_from([6, 7, 3, 8]))
-    def run(seed, half_rows, width, k, variant):
+    @given(st.integers(0, 2 ** 31), st.integers(1, 300), st.integers(1, 12), st.sampled_from([2, 5, 9]))
+    def run(seed, half_rows, width, k):
+        variant = 6
         rng = np.random.default_rng(seed)
         n = 2 * half_rows  # even: X's columns stay 16-byte aligned
         nbands = int(rng.integers(1, 4))
@@ -186,7 +187,7 @@ def test_random_banded_structures_run_staged_kernels():
         va = rng.standard_normal(len(ci))
         x = rng.standard_normal((n, k))
         y0 = rng.standard_normal((n, k))
-        got, stats = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, variant=variant, cap=3456 if variant in (6, 7) else 2048)
+        got, stats = emul.local_apply(rp, ci, va, x, y0, 3.0, 0.5, variant=variant, cap=3456)
         if got is None:
             return
         ref = _oracle(rp, ci, va, x, y0, 3.0, 0.5)
@@ -258,3 +259,78 @@ def test_spmv_column_slab_kernel(kind, N, kw, slab_cols):
     again = emul.spmv_cb(rp, ci, va, x, y0, -2.0, 1.0, slab_cols=slab_cols)
     emul.set_schedule("forward")
     assert np.array_equal(got, again)
+
+
+def test_random_csr_structures_column_slab_kernel():
+    """property test: random row-length profiles (empty rows, rows with hundreds of entries in one slab, a single row holding
+    everything), columns in random order inside a row, random slab widths -- spmv_cb_kernel + spmv_cb_carry_kernel and the
+    device builders against the oracle"""
+    import os
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=int(os.environ.get("JP_HYPOTHESIS_EXAMPLES", "40")), deadline=None, derandomize=True)
+    @given(st.integers(0, 2 ** 31), st.integers(1, 500), st.sampled_from([1, 3, 17, 64, 1000]))
+    def run(seed, n_rows, slab_cols):
+        rng = np.random.default_rng(seed)
+        n_cols = int(rng.integers(1, 700))
+        profile = rng.integers(0, 4)
+        if profile == 0:
+            lens = rng.integers(0, 9, size=n_rows)
+        elif profile == 1:
+            lens = rng.integers(0, 70, size=n_rows)
+        elif profile == 2:
+            lens = np.where(rng.random(n_rows) < 0.03, rng.integers(300, 2500, size=n_rows), rng.integers(0, 6, size=n_rows))
+        else:
+            lens = np.zeros(n_rows, dtype=np.int64)
+            lens[int(rng.integers(0, n_rows))] = int(rng.integers(1, 4000))
+        rp = np.zeros(n_rows + 1, dtype=np.int32)
+        np.cumsum(lens, out=rp[1:])
+        ci = rng.integers(0, n_cols, size=int(rp[-1])).astype(np.int32)  # unsorted, with repeats: the kernel must not care
+        va = rng.standard_normal(len(ci))
+        x = rng.standard_normal((n_cols, 1))
+        y0 = rng.standard_normal((n_rows, 1))
+        alpha, beta = ((3.0, 0.5), (1.0, 0.0), (-1.5, 1.0))[seed % 3]
+        got = emul.spmv_cb(rp, ci, va, x, y0, alpha, beta, slab_cols=min(slab_cols, n_cols))
+        ref = _oracle(rp, ci, va, x, y0, alpha, beta)
+        assert (np.abs(got - ref) <= _bound(rp, ci, va, x, y0, alpha, beta)).all(), np.abs(got - ref).max()
+
+    run()
+
+
+def test_random_diagonal_structures_diagonal_kernel():
+    """property test: random sets of diagonals (isolated ones, adjacent groups, far apart, up to 32), random fill, random
+    sizes and both window parities -- the plan of jp_dia_plan.h, the builders and spmm_dia_kernel against the oracle on the
+    rows the kernel serves; the other rows must be left alone"""
+    import os
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=int(os.environ.get("JP_HYPOTHESIS_EXAMPLES", "30")), deadline=None, derandomize=True)
+    @given(st.integers(0, 2 ** 31), st.integers(300, 900), st.integers(1, 32), st.sampled_from([1, 4, 7]), st.sampled_from([0, 1]))
+    def run(seed, half_rows, ndiag, k, parity):
+        rng = np.random.default_rng(seed)
+        n = 2 * half_rows
+        span = int(rng.integers(2, max(3, n // 3)))
+        offs = np.unique(np.concatenate([[0], rng.integers(-span, span + 1, size=ndiag - 1)]))
+        fill = rng.uniform(0.6, 1.0)
+        rows = np.arange(n)
+        cols = rows[:, None] + offs[None, :]
+        ok = (cols >= 0) & (cols < n) & (rng.random(cols.shape) < fill)
+        ok[:, list(offs).index(0)] = True
+        for d in range(len(offs)):  # every offset must occur at least once, or the plan sees fewer diagonals -- harmless, but keep it exact
+            r_ok = np.nonzero((cols[:, d] >= 0) & (cols[:, d] < n))[0]
+            ok[r_ok[0], d] = True
+        rp = np.zeros(n + 1, dtype=np.int32)
+        np.cumsum(ok.sum(axis=1), out=rp[1:])
+        ci = cols[ok].astype(np.int32)
+        va = rng.standard_normal(len(ci))
+        x = rng.standard_normal((n, k))
+        y0 = rng.standard_normal((n, k))
+        got, lo, hi = emul.spmm_dia(rp, ci, va, x, y0, 3.0, 0.5, parity=parity)
+        if got is None:
+            return  # too small for a single block of 128 rows with in-bounds windows
+        assert lo % 2 == parity and 0 <= lo < hi <= n
+        ref = _oracle(rp, ci, va, x, y0, 3.0, 0.5)
+        assert (np.abs(got[lo:hi] - ref[lo:hi]) <= _bound(rp, ci, va, x, y0, 3.0, 0.5)[lo:hi]).all()
+        assert np.array_equal(got[:lo], y0[:lo]) and np.array_equal(got[hi:], y0[hi:])
+
+    run()
